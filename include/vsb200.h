@@ -1,0 +1,161 @@
+/*
+ * vsb200.h — C ABI of libvsb200.so, the B200-native (sm_100a) ANN engine that
+ * replaces the USearch index behind scylladb/vector-store's index actor.
+ *
+ * Drop-in boundary.  In the reference the engine is reached through the
+ * crate-private trait `UsearchIndex` (crates/vector-store/src/vs_index/usearch.rs:142-160)
+ * whose only implementation forwards to the `usearch` crate's cxx FFI
+ * (usearch.rs:169-251).  Every entry point below names the reference call it
+ * replaces.  All functions are thread-safe on one handle, copy their inputs
+ * before returning, never call back into the host and never fall back to a CPU
+ * path: if no CUDA device is usable `vsb_create` fails with VSB_ECUDA.
+ *
+ * Conventions
+ *   - keys are opaque u64 (reference PrimaryId: 16-bit epoch | 48-bit row id,
+ *     table/primary_id.rs:27-62); all 64 bits are stored and returned.
+ *   - vectors cross the boundary as row-major f32, exactly like
+ *     `usearch::Index::add(key, &[f32])` / `search(&[f32], k)`; the cast to the
+ *     storage scalar (f32/f16/bf16/i8/b1) happens on the device, on add AND on
+ *     the query.
+ *   - results: per query `k` slots, ascending by (distance, key); unused slots
+ *     hold key = UINT64_MAX and distance = +inf; `counts[q]` = valid entries.
+ *   - "_dev" variants take DEVICE pointers and a `cudaStream_t` (as void*) and
+ *     never synchronise; they are what bench.py times for the in-HBM number
+ *     and what the multi-GPU path feeds straight into the NCCL all-gather.
+ */
+#ifndef VSB200_H
+#define VSB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vsb_index vsb_index;
+
+typedef enum {
+    VSB_OK = 0,
+    VSB_EINVAL = 1,  /* bad argument / unsupported option combination          */
+    VSB_EDIM = 2,    /* reference: vs_index::Error::WrongEmbeddingDimension     */
+    VSB_EDUPKEY = 3, /* usearch multi=false: add of an existing key             */
+    VSB_EFULL = 4,   /* usearch: "Reserve capacity ahead of insertions!"        */
+    VSB_EOOM = 5,    /* HBM budget exhausted (reference: memory.rs Allocate::Cannot) */
+    VSB_ECUDA = 6,   /* CUDA runtime/driver failure, incl. "no device"          */
+    VSB_ENCCL = 7
+} vsb_status;
+
+/* usearch.rs:480-485  SpaceType -> MetricKind */
+typedef enum { VSB_L2SQ = 0, VSB_COS = 1, VSB_IP = 2, VSB_HAMMING = 3 } vsb_metric;
+/* usearch.rs:503-513  Quantization -> ScalarKind */
+typedef enum { VSB_F32 = 0, VSB_F16 = 1, VSB_BF16 = 2, VSB_I8 = 3, VSB_B1 = 4 } vsb_scalar;
+
+/* replaces usearch::IndexOptions as filled at usearch.rs:74-82 (A1/A2 in SURVEY §8a).
+ * 0 in connectivity / expansion_* selects the reference defaults 16 / 128 / 64
+ * (crates/vector-store/src/lib.rs:394-437). */
+typedef struct {
+    uint32_t dimensions;
+    int32_t metric;           /* vsb_metric; VSB_B1 storage forces VSB_HAMMING (usearch.rs:450-464) */
+    int32_t storage;          /* vsb_scalar */
+    uint32_t connectivity;    /* M; the flat graph uses degree 2M like HNSW level 0 */
+    uint32_t expansion_add;   /* build-time candidate width (kNN list length before pruning) */
+    uint32_t expansion_search;/* beam width (itopk) of the graph search; ef = max(this, k) */
+    int32_t device;           /* CUDA device ordinal; -1 = current device */
+    uint32_t flags;           /* VSB_FLAG_* */
+    uint64_t seed;            /* seed for the entry-point sample; 0 = default */
+} vsb_options;
+
+#define VSB_FLAG_NONE 0u
+
+/* Runtime tunables of the graph search (all 0 = keep current). */
+typedef struct {
+    uint32_t expansion_search; /* itopk; rounded up to a multiple of 32, <= 512 */
+    uint32_t max_iterations;   /* parent expansions per query; 0 = auto */
+    uint32_t n_seeds;          /* entry points taken from the seed layer, <= 32 */
+    uint32_t min_graph_size;   /* below this many live vectors search is brute force */
+} vsb_search_params;
+
+/* Counters the roofline arithmetic is computed from. */
+typedef struct {
+    uint64_t kernel_launches;      /* kernels launched by this handle since creation */
+    uint64_t distance_evals;       /* graph-search distance evaluations (last instrumented search) */
+    uint64_t parent_expansions;    /* graph-search parent expansions (last instrumented search) */
+    uint64_t queries;              /* queries in the last instrumented search */
+    uint64_t n_slots;              /* rows resident in HBM (live + tombstoned) */
+    uint64_t n_graphed;            /* rows covered by the graph; the rest is the brute-force tail */
+    uint64_t graph_degree;         /* R */
+    uint64_t row_bytes;            /* bytes per stored vector (16-byte padded) */
+    uint64_t n_seed_rows;          /* rows in the entry-point sample */
+    uint64_t hbm_bytes;            /* device bytes held by this handle */
+} vsb_stats;
+
+/* usearch.rs:172  usearch::Index::new(&options) */
+vsb_status vsb_create(const vsb_options* options, vsb_index** out);
+/* drop of ThreadedUsearchIndex / UsearchIndex::stop (usearch.rs:250) */
+void vsb_destroy(vsb_index* index);
+
+/* usearch.rs:181-185  reserve_capacity_and_threads(size, threads); never blocks searches */
+vsb_status vsb_reserve(vsb_index* index, uint64_t capacity);
+/* usearch.rs:187-189  capacity() */
+uint64_t vsb_capacity(const vsb_index* index);
+/* the AtomicUsize the actor keeps for Count (usearch.rs:866-877) */
+uint64_t vsb_size(const vsb_index* index);
+
+/* usearch.rs:191-197  add(key, &[f32]) — batched: n rows of `dimensions` f32.
+ * All-or-nothing: a duplicate key (in the index or inside the batch) fails the
+ * whole call with VSB_EDUPKEY; size+n > capacity fails with VSB_EFULL.
+ * Added vectors are searchable as soon as the call returns (brute-force tail). */
+vsb_status vsb_add(vsb_index* index, const uint64_t* keys, const float* rows, uint64_t n);
+/* usearch.rs:199-201  remove(key) -> usize.  Unknown keys are skipped. */
+vsb_status vsb_remove(vsb_index* index, const uint64_t* keys, uint64_t n, uint64_t* n_removed);
+/* usearch has no equivalent: `contains` for the host-side mirror's duplicate checks. */
+int vsb_contains(const vsb_index* index, uint64_t key);
+
+/* Bulk (re)build of the graph over every live vector added so far (A5, K5+K6).
+ * Until it is called (and for vectors added after it) search is exact brute force
+ * over the un-graphed tail, merged with the graph result. */
+vsb_status vsb_build(vsb_index* index);
+
+vsb_status vsb_set_search_params(vsb_index* index, const vsb_search_params* params);
+vsb_status vsb_get_stats(vsb_index* index, vsb_stats* out);
+/* Re-runs nothing: switches the graph-search kernel to its counting build for the
+ * next searches (identical algorithm; counters off by default for timing runs). */
+vsb_status vsb_set_instrumented(vsb_index* index, int on);
+
+/* usearch.rs:203-222  search(&[f32], k) -> Matches{keys, distances}; batched over q queries. */
+vsb_status vsb_search(vsb_index* index, const float* queries, uint64_t q, uint32_t k,
+                      uint64_t* keys, float* distances, uint32_t* counts);
+/* exact brute force (ground truth; bit-exact vs oracle/exact.c) */
+vsb_status vsb_search_exact(vsb_index* index, const float* queries, uint64_t q, uint32_t k,
+                            uint64_t* keys, float* distances, uint32_t* counts);
+/* usearch.rs:224-248  filtered_search(&[f32], k, |key| -> bool).  The host predicate
+ * becomes a bitmap over the table's row ids: bit (key & (2^48-1)) set = admissible
+ * (rows >= bitmap_bits are inadmissible).  Exact brute force over admissible rows. */
+vsb_status vsb_search_filtered(vsb_index* index, const float* queries, uint64_t q, uint32_t k,
+                               const uint32_t* allow_bitmap, uint64_t bitmap_bits,
+                               uint64_t* keys, float* distances, uint32_t* counts);
+
+/* Device-resident variants: d_* are device pointers on the index's device,
+ * `stream` is a cudaStream_t.  No host synchronisation. `exact` != 0 selects brute force. */
+vsb_status vsb_search_dev(vsb_index* index, const float* d_queries, uint64_t q, uint32_t k,
+                          uint64_t* d_keys, float* d_distances, uint32_t* d_counts,
+                          void* stream, int exact);
+/* K8 shard merge: `parts` result blocks laid out [parts][q][k] (exactly what an
+ * all-gather of per-shard vsb_search_dev outputs produces) -> [q][k], by (distance, key). */
+vsb_status vsb_merge_topk_dev(const uint64_t* d_keys, const float* d_distances, uint32_t parts,
+                              uint64_t q, uint32_t k, uint64_t* d_out_keys, float* d_out_distances,
+                              uint32_t* d_out_counts, int device, void* stream);
+
+/* A11: usearch.rs:1179-1205  f32_to_b1x8 (host utility, same bit order) */
+void vsb_f32_to_b1x8(const float* v, uint64_t n, uint8_t* out /* ceil(n/8) bytes */);
+
+/* thread-local message of the last failing call on this thread */
+const char* vsb_last_error(void);
+/* "vsb200-x.y.z" — what VsIndexFactory::index_engine_version would report (usearch.rs:109-114) */
+const char* vsb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSB200_H */

@@ -1,0 +1,216 @@
+// graph_build.cu — K6: turn exact k_init-NN lists into the fixed-degree search graph.
+//
+// Replaces the link-selection half of usearch::Index::add (reference call site
+// vs_index/usearch.rs:191-197): instead of HNSW's per-insert neighbour heuristic
+// the bulk build prunes a kNN graph by rank-based detour counting (CAGRA), then adds reverse
+// edges.  Everything here is integer work on slot ids and is fully deterministic, so the graph is
+// compared bit-for-bit with oracle/graph_oracle.py.
+//
+//   1. prune_detour_kernel : for node u with list L (ascending by distance), edge u->L[j] gets
+//      detour[j] = #{ i<j : L[j] appears in knn(L[i]) at a position t < j }.  Keep the R edges with
+//      the smallest (detour, j).
+//   2. reverse edges       : every kept edge u->v at rank r proposes u to v.  Proposals are radix
+//      sorted by (v, r, u) so each node's reverse list is its R best-ranked proposers, ties by slot.
+//   3. merge_graph_kernel  : row = fwd[0:R/2] ++ reverse (new ones only) ++ fwd[R/2:R], cut at R.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kernels.h"
+#include "select.cuh"
+
+namespace vsb {
+
+namespace {
+
+constexpr int K6_WARPS = 4;
+constexpr int K6_MAXK = 128;   // k_init upper bound
+constexpr int K6_HASH = 256;   // >= 2 * K6_MAXK
+
+__global__ void __launch_bounds__(K6_WARPS * 32) prune_detour_kernel(const uint64_t* __restrict__ knn, uint32_t n,
+                                                                     uint32_t k_init, uint32_t R,
+                                                                     const uint32_t* __restrict__ deny,
+                                                                     uint32_t* __restrict__ fwd) {
+    __shared__ uint32_t sL[K6_WARPS][K6_MAXK];
+    __shared__ uint32_t sDet[K6_WARPS][K6_MAXK];
+    __shared__ uint32_t sHid[K6_WARPS][K6_HASH];
+    __shared__ uint32_t sHrank[K6_WARPS][K6_HASH];
+    __shared__ uint64_t sOrd[K6_WARPS][K6_MAXK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t u = blockIdx.x * K6_WARPS + warp;
+    if (u >= n) return;
+    if (deny != nullptr && bit_test(deny, u)) {  // tombstoned rows keep no edges and propose none
+        for (uint32_t r = lane; r < R; r += 32) fwd[(size_t)u * R + r] = kInvalidSlot;
+        return;
+    }
+    uint32_t* L = sL[warp];
+    uint32_t* det = sDet[warp];
+    uint32_t* hid = sHid[warp];
+    uint32_t* hrank = sHrank[warp];
+    uint64_t* ord = sOrd[warp];
+
+    for (int i = lane; i < K6_HASH; i += 32) hid[i] = kInvalidSlot;
+    uint32_t k0 = 0;
+    for (uint32_t j = lane; j < K6_MAXK; j += 32) {
+        uint32_t v = kInvalidSlot;
+        if (j < k_init) {
+            const uint64_t p = knn[(size_t)u * k_init + j];
+            if (p != kInvalidPacked) v = packed_lo(p);
+        }
+        L[j] = v;
+        det[j] = 0;
+        ord[j] = kInvalidPacked;
+        k0 += __popc(__ballot_sync(kFullMask, v != kInvalidSlot));
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < k0; j += 32) {
+        const uint32_t v = L[j];
+        uint32_t h = (v * 0x9E3779B1u) >> 24;
+        while (true) {
+            const uint32_t old = atomicCAS(&hid[h], kInvalidSlot, v);
+            if (old == kInvalidSlot) {
+                hrank[h] = j;
+                break;
+            }
+            h = (h + 1) & (K6_HASH - 1);
+        }
+    }
+    __syncwarp();
+    for (uint32_t i = 0; i < k0; ++i) {
+        const uint64_t* row = knn + (size_t)L[i] * k_init;
+        for (uint32_t t = lane; t < k_init; t += 32) {
+            const uint64_t p = row[t];
+            if (p == kInvalidPacked) continue;
+            const uint32_t y = packed_lo(p);
+            uint32_t h = (y * 0x9E3779B1u) >> 24;
+            while (true) {
+                const uint32_t id = hid[h];
+                if (id == kInvalidSlot) break;
+                if (id == y) {
+                    const uint32_t j = hrank[h];
+                    if (j > i && t < j) atomicAdd(&det[j], 1u);
+                    break;
+                }
+                h = (h + 1) & (K6_HASH - 1);
+            }
+        }
+    }
+    __syncwarp();
+    // order by (detour, rank)
+    const LessBySlot less;
+    for (uint32_t b = 0; b < K6_MAXK; b += 32) {
+        const uint32_t j = b + lane;
+        uint64_t v = j < k0 ? (((uint64_t)det[j] << 32) | j) : kInvalidPacked;
+        if (__ballot_sync(kFullMask, v != kInvalidPacked) == 0) break;
+        v = warp_sort32(v, lane, less);
+        warp_list_merge(ord, K6_MAXK, v, lane, less);
+    }
+    for (uint32_t r = lane; r < R; r += 32) {
+        const uint64_t o = r < K6_MAXK ? ord[r] : kInvalidPacked;
+        fwd[(size_t)u * R + r] = (o == kInvalidPacked) ? kInvalidSlot : L[packed_lo(o)];
+    }
+}
+
+// proposals: key = v << 36 | r << 28 | u   (n < 2^28, r < 256)
+__global__ void make_proposals_kernel(const uint32_t* __restrict__ fwd, uint32_t n, uint32_t R,
+                                      uint64_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * R) return;
+    const uint32_t u = (uint32_t)(i / R), r = (uint32_t)(i % R);
+    const uint32_t v = fwd[i];
+    out[i] = (v == kInvalidSlot) ? kInvalidPacked : (((uint64_t)v << 36) | ((uint64_t)r << 28) | u);
+}
+
+__global__ void mark_segments_kernel(const uint64_t* __restrict__ sorted, size_t m, uint32_t* __restrict__ seg_start) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint64_t p = sorted[i];
+    if (p == kInvalidPacked) return;
+    const uint32_t v = (uint32_t)(p >> 36);
+    if (i == 0 || (uint32_t)(sorted[i - 1] >> 36) != v) seg_start[v] = (uint32_t)i;
+}
+
+__global__ void scatter_reverse_kernel(const uint64_t* __restrict__ sorted, size_t m,
+                                       const uint32_t* __restrict__ seg_start, uint32_t R,
+                                       uint32_t* __restrict__ rev, uint32_t* __restrict__ rev_cnt) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint64_t p = sorted[i];
+    if (p == kInvalidPacked) return;
+    const uint32_t v = (uint32_t)(p >> 36);
+    const uint32_t u = (uint32_t)(p & 0x0FFFFFFFu);
+    const uint32_t pos = (uint32_t)i - seg_start[v];
+    if (pos < R) {
+        rev[(size_t)v * R + pos] = u;
+        atomicMax(&rev_cnt[v], pos + 1);
+    }
+}
+
+constexpr int K6_MAXR = 128;
+
+__global__ void merge_graph_kernel(const uint32_t* __restrict__ fwd, const uint32_t* __restrict__ rev,
+                                   const uint32_t* __restrict__ rev_cnt, uint32_t n, uint32_t R,
+                                   uint32_t* __restrict__ graph, uint32_t graph_stride) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    uint32_t out[K6_MAXR];
+    uint32_t c = 0;
+    auto push_unique = [&](uint32_t v) {
+        if (v == kInvalidSlot || v == u || c >= R) return;
+        for (uint32_t i = 0; i < c; ++i)
+            if (out[i] == v) return;
+        out[c++] = v;
+    };
+    const uint32_t half = R / 2;
+    for (uint32_t r = 0; r < half; ++r) push_unique(fwd[(size_t)u * R + r]);
+    const uint32_t rc = rev_cnt[u];
+    for (uint32_t r = 0; r < rc; ++r) push_unique(rev[(size_t)u * R + r]);
+    for (uint32_t r = half; r < R; ++r) push_unique(fwd[(size_t)u * R + r]);
+    for (uint32_t r = 0; r < graph_stride; ++r) graph[(size_t)u * graph_stride + r] = r < c ? out[r] : kInvalidSlot;
+}
+
+}  // namespace
+
+void launch_prune_detour(const uint64_t* knn, uint32_t n, uint32_t k_init, uint32_t R, const uint32_t* deny,
+                         uint32_t* fwd, cudaStream_t stream) {
+    if (n == 0) return;
+    prune_detour_kernel<<<(n + K6_WARPS - 1) / K6_WARPS, K6_WARPS * 32, 0, stream>>>(knn, n, k_init, R, deny, fwd);
+    g_kernel_launches += 1;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t reverse_edges_scratch_bytes(uint32_t n, uint32_t R) {
+    const size_t m = (size_t)n * R;
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, temp, (const uint64_t*)nullptr, (uint64_t*)nullptr, m, 0, 64);
+    return align_up(m * 8, 256) * 2 + align_up((size_t)n * 4, 256) + align_up(temp, 256);
+}
+
+void launch_reverse_edges(const uint32_t* fwd, uint32_t n, uint32_t R, uint32_t* rev, uint32_t* rev_cnt,
+                          void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+    if (n == 0) return;
+    const size_t m = (size_t)n * R;
+    uint8_t* base = static_cast<uint8_t*>(scratch);
+    uint64_t* prop = reinterpret_cast<uint64_t*>(base);
+    uint64_t* sorted = reinterpret_cast<uint64_t*>(base + align_up(m * 8, 256));
+    uint32_t* seg_start = reinterpret_cast<uint32_t*>(base + 2 * align_up(m * 8, 256));
+    void* temp = base + 2 * align_up(m * 8, 256) + align_up((size_t)n * 4, 256);
+    size_t temp_bytes = scratch_bytes - (2 * align_up(m * 8, 256) + align_up((size_t)n * 4, 256));
+    const int T = 256;
+    make_proposals_kernel<<<(unsigned)((m + T - 1) / T), T, 0, stream>>>(fwd, n, R, prop);
+    cub::DeviceRadixSort::SortKeys(temp, temp_bytes, prop, sorted, m, 0, 64, stream);
+    cudaMemsetAsync(rev_cnt, 0, (size_t)n * 4, stream);
+    cudaMemsetAsync(rev, 0xFF, (size_t)n * R * 4, stream);
+    mark_segments_kernel<<<(unsigned)((m + T - 1) / T), T, 0, stream>>>(sorted, m, seg_start);
+    scatter_reverse_kernel<<<(unsigned)((m + T - 1) / T), T, 0, stream>>>(sorted, m, seg_start, R, rev, rev_cnt);
+    g_kernel_launches += 3;  // + the CUB radix-sort passes, which are library kernels and not counted
+}
+
+void launch_merge_graph(const uint32_t* fwd, const uint32_t* rev, const uint32_t* rev_cnt, uint32_t n,
+                        uint32_t R, uint32_t* graph, uint32_t graph_stride, cudaStream_t stream) {
+    if (n == 0) return;
+    const int T = 128;
+    merge_graph_kernel<<<(n + T - 1) / T, T, 0, stream>>>(fwd, rev, rev_cnt, n, R, graph, graph_stride);
+    g_kernel_launches += 1;
+}
+
+}  // namespace vsb

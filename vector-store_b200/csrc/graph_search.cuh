@@ -1,0 +1,297 @@
+// graph_search.cuh — K4: warp-per-query beam search over the fixed-degree graph.
+//
+// Replaces the HNSW base-layer traversal inside usearch::Index::search (reference call site
+// vs_index/usearch.rs:203-222).  One warp owns one query:
+//   * the query lives in registers (each lane keeps the 16-byte chunks it will ever touch);
+//   * the candidate list (itopk = ef entries, packed ord(dist)<<32|slot, ascending) and the
+//     visited hash live in shared memory;
+//   * every iteration expands the best un-expanded candidate: one coalesced 128-byte read of its
+//     graph row, a visited-hash filter, then the surviving neighbours' vectors are streamed with
+//     128-bit ld.global.nc loads (a 1536-byte bf16 row = 3 fully coalesced warp loads),
+//     reduced with the canonical butterfly, sorted with a shuffle bitonic network and folded
+//     into the list.
+// HBM-bound by design: bytes/query = E * row_bytes + P * R * 4 (E, P counted in-kernel).
+#pragma once
+#include "kernels.h"
+#include "select.cuh"
+
+namespace vsb {
+
+constexpr int K4_WARPS = 4;
+constexpr uint32_t kHashEmpty = 0xFFFFFFFFu;
+
+struct K4Args {
+    const uint8_t* q_rows;
+    const float* q_nrm;
+    uint32_t nq, q_row_bytes;
+    const uint8_t* x_rows;
+    const float* x_nrm;
+    uint32_t x_row_bytes;
+    const uint32_t* graph;
+    uint32_t graph_stride, degree;
+    const uint64_t* seed_lists;  // [nq][seed_splits][32]
+    uint32_t seed_splits, n_seeds;
+    const uint32_t* seed_slots;
+    const uint32_t* deny;
+    const uint64_t* keys;
+    uint32_t itopk, max_iters, k, hash_bits;
+    int metric;
+    uint64_t* out_keys;
+    float* out_dists;
+    uint32_t* out_counts;
+    unsigned long long* counters;
+};
+
+__device__ __forceinline__ bool hash_insert(uint32_t* tab, uint32_t mask, uint32_t bits, uint32_t slot) {
+    uint32_t h = (slot * 0x9E3779B1u) >> (32 - bits);
+#pragma unroll 1
+    for (int probe = 0; probe < 64; ++probe) {
+        const uint32_t old = atomicCAS(&tab[h], kHashEmpty, slot);
+        if (old == kHashEmpty) return true;
+        if (old == slot) return false;
+        h = (h + 1) & mask;
+    }
+    return false;  // saturated neighbourhood: treat as visited
+}
+
+template <int ST, int CPL>
+__global__ void __launch_bounds__(K4_WARPS * 32) graph_search_kernel(K4Args a) {
+    constexpr int E = Storage<ST>::ELEMS;
+    constexpr bool kFloat = Storage<ST>::kFloat;
+    constexpr int U = CPL <= 3 ? 4 : (CPL <= 6 ? 2 : 1);
+    constexpr int QF = kFloat ? CPL * E : 1;
+
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * K4_WARPS + warp;
+    if (q >= a.nq) return;
+
+    const uint32_t hsize = 1u << a.hash_bits, hmask = hsize - 1;
+    const size_t per_warp = (size_t)a.itopk * 8 + (size_t)hsize * 4;
+    uint64_t* list = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warp * per_warp);
+    uint32_t* hash = reinterpret_cast<uint32_t*>(list + a.itopk);
+    const LessBySlot less;
+    const bool is_l2 = a.metric == VSB_METRIC_L2SQ;
+    const int n_chunks = a.x_row_bytes / 16;
+
+    for (uint32_t i = lane; i < a.itopk; i += 32) list[i] = kInvalidPacked;
+    for (uint32_t i = lane; i < hsize; i += 32) hash[i] = kHashEmpty;
+
+    // ---- query into registers ----
+    const uint4* qrow = reinterpret_cast<const uint4*>(a.q_rows + (size_t)q * a.q_row_bytes);
+    float qf[QF];
+    uint4 qc[kFloat ? 1 : CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        const int c = j * 32 + lane;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (c < n_chunks) v = qrow[c];
+        if constexpr (kFloat)
+            Storage<ST>::unpack(v, &qf[j * E]);
+        else
+            qc[j] = v;
+    }
+    const float qn = a.q_nrm[q];
+    __syncwarp();
+
+    uint32_t n_hashed = 0;
+    unsigned long long n_evals = 0, n_parents = 0;
+
+    // Evaluates the canonical distance of every lane's candidate `nb` (kInvalidSlot = none),
+    // folds the results into the list.
+    auto process_batch = [&](uint32_t nb) {
+        bool is_new = false;
+        if (nb != kInvalidSlot) is_new = hash_insert(hash, hmask, a.hash_bits, nb);
+        uint32_t m = __ballot_sync(kFullMask, is_new);
+        if (m == 0) return;
+        n_hashed += __popc(m);
+        n_evals += __popc(m);
+        float my_d = 0.0f;
+        uint32_t todo = m;
+        while (todo) {
+            int src[U];
+            uint32_t slot[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                src[u] = todo ? (__ffs(todo) - 1) : -1;
+                if (todo) todo &= todo - 1;
+                slot[u] = __shfl_sync(kFullMask, nb, src[u] < 0 ? 0 : src[u]);
+            }
+            uint4 x[U][CPL];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint4* xrow = reinterpret_cast<const uint4*>(a.x_rows + (size_t)slot[u] * a.x_row_bytes);
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    const int c = j * 32 + lane;
+                    x[u][j] = make_uint4(0, 0, 0, 0);
+                    if (src[u] >= 0 && c < n_chunks) x[u][j] = ldg_nc_v4(xrow + c);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (src[u] < 0) continue;  // warp-uniform
+                float facc = 0.0f;
+                int iacc = 0;
+                if constexpr (kFloat) {
+                    if (is_l2) {
+                        ChunkAcc<ST, VSB_METRIC_L2SQ> acc;
+#pragma unroll
+                        for (int j = 0; j < CPL; ++j) {
+                            float xf[E];
+                            Storage<ST>::unpack(x[u][j], xf);
+                            acc.add_f(&qf[j * E], xf);
+                        }
+                        facc = acc.f;
+                    } else {
+                        ChunkAcc<ST, VSB_METRIC_IP> acc;
+#pragma unroll
+                        for (int j = 0; j < CPL; ++j) {
+                            float xf[E];
+                            Storage<ST>::unpack(x[u][j], xf);
+                            acc.add_f(&qf[j * E], xf);
+                        }
+                        facc = acc.f;
+                    }
+                    facc = butterfly_sum(facc);
+                } else {
+                    if (is_l2) {
+                        ChunkAcc<ST, VSB_METRIC_L2SQ> acc;
+#pragma unroll
+                        for (int j = 0; j < CPL; ++j) acc.add(qc[j], x[u][j]);
+                        iacc = acc.i;
+                    } else {
+                        ChunkAcc<ST, VSB_METRIC_IP> acc;
+#pragma unroll
+                        for (int j = 0; j < CPL; ++j) acc.add(qc[j], x[u][j]);
+                        iacc = acc.i;
+                    }
+                    iacc = butterfly_sum_i(iacc);
+                }
+                float d;
+                if constexpr (ST == VSB_ST_B1) {
+                    d = finish_distance<ST, VSB_METRIC_HAMMING>(facc, iacc, 0.0f, 0.0f);
+                } else {
+                    if (is_l2)
+                        d = finish_distance<ST, VSB_METRIC_L2SQ>(facc, iacc, 0.0f, 0.0f);
+                    else if (a.metric == VSB_METRIC_IP)
+                        d = finish_distance<ST, VSB_METRIC_IP>(facc, iacc, 0.0f, 0.0f);
+                    else
+                        d = finish_distance<ST, VSB_METRIC_COS>(facc, iacc, qn, a.x_nrm[slot[u]]);
+                }
+                if (lane == src[u]) my_d = d;
+            }
+        }
+        uint64_t res = is_new ? pack_ds(my_d, nb) : kInvalidPacked;
+        res = warp_sort32(res, lane, less);
+        warp_list_merge(list, (int)a.itopk, res, lane, less);
+    };
+
+    // ---- seeds: merge the seed layer's split lists (32 each, ascending), map to slots ----
+    {
+        uint64_t sv = a.seed_lists[((size_t)q * a.seed_splits) * 32 + lane];
+        for (uint32_t s = 1; s < a.seed_splits; ++s) {
+            const uint64_t v = a.seed_lists[((size_t)q * a.seed_splits + s) * 32 + lane];
+            const uint64_t rc = shfl_u64(v, 31 - lane);
+            sv = warp_bitonic_merge32(rc < sv ? rc : sv, lane, less);
+        }
+        uint32_t nb = kInvalidSlot;
+        if (lane < (int)a.n_seeds && sv != kInvalidPacked) nb = a.seed_slots[packed_lo(sv)];
+        process_batch(nb);
+    }
+
+    // ---- main loop ----
+    const uint32_t max_iters = a.max_iters;
+    for (uint32_t it = 0; it < max_iters; ++it) {
+        // visited hash getting crowded: forget everything except what is still in the list
+        if (n_hashed > hsize / 2) {
+            for (uint32_t i = lane; i < hsize; i += 32) hash[i] = kHashEmpty;
+            __syncwarp();
+            n_hashed = 0;
+            for (uint32_t b = 0; b < a.itopk; b += 32) {
+                const uint64_t e = list[b + lane];
+                if (e != kInvalidPacked) hash_insert(hash, hmask, a.hash_bits, packed_lo(e) & ~kExpandedBit);
+                n_hashed += __popc(__ballot_sync(kFullMask, e != kInvalidPacked));
+            }
+            __syncwarp();
+        }
+        // best un-expanded candidate
+        uint32_t parent = kInvalidSlot;
+        for (uint32_t b = 0; b < a.itopk; b += 32) {
+            const uint64_t e = list[b + lane];
+            const bool unexp = e != kInvalidPacked && !(packed_lo(e) & kExpandedBit);
+            const uint32_t m = __ballot_sync(kFullMask, unexp);
+            if (m) {
+                const int src = __ffs(m) - 1;
+                parent = __shfl_sync(kFullMask, packed_lo(e), src);
+                if (lane == src) list[b + lane] = e | kExpandedBit;
+                break;
+            }
+        }
+        __syncwarp();
+        if (parent == kInvalidSlot) break;
+        ++n_parents;
+        const uint32_t* grow = a.graph + (size_t)parent * a.graph_stride;
+        for (uint32_t r0 = 0; r0 < a.degree; r0 += 32) {
+            uint32_t nb = kInvalidSlot;
+            if (r0 + lane < a.degree) nb = __ldg(grow + r0 + lane);
+            process_batch(nb);
+        }
+    }
+
+    // ---- emit the first k live entries ----
+    uint32_t count = 0;
+    for (uint32_t b = 0; b < a.itopk; b += 32) {
+        const uint64_t e = list[b + lane];
+        const uint32_t slot = packed_lo(e) & ~kExpandedBit;
+        bool valid = e != kInvalidPacked;
+        if (valid && a.deny != nullptr && bit_test(a.deny, slot)) valid = false;
+        const uint32_t m = __ballot_sync(kFullMask, valid);
+        const uint32_t pos = count + __popc(m & ((1u << lane) - 1));
+        if (valid && pos < a.k) {
+            a.out_keys[(size_t)q * a.k + pos] = a.keys[slot];
+            a.out_dists[(size_t)q * a.k + pos] = ord_to_f32(packed_hi(e));
+        }
+        count += __popc(m);
+    }
+    if (count > a.k) count = a.k;
+    for (uint32_t i = count + lane; i < a.k; i += 32) {
+        a.out_keys[(size_t)q * a.k + i] = 0xFFFFFFFFFFFFFFFFull;
+        a.out_dists[(size_t)q * a.k + i] = __int_as_float(0x7F800000);
+    }
+    if (lane == 0) {
+        if (a.out_counts != nullptr) a.out_counts[q] = count;
+        if (a.counters != nullptr) {
+            atomicAdd(&a.counters[0], n_evals);
+            atomicAdd(&a.counters[1], n_parents);
+        }
+    }
+}
+
+template <int ST, int CPL>
+void launch_k4_inst(const K4Args& a, dim3 grid, size_t smem, cudaStream_t stream) {
+    cudaFuncSetAttribute(graph_search_kernel<ST, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    graph_search_kernel<ST, CPL><<<grid, K4_WARPS * 32, smem, stream>>>(a);
+}
+
+// one translation unit per storage scalar instantiates this
+template <int ST>
+void launch_k4_storage(const K4Args& a, int cpl, dim3 grid, size_t smem, cudaStream_t stream) {
+    switch (cpl) {
+        case 1: launch_k4_inst<ST, 1>(a, grid, smem, stream); break;
+        case 2: launch_k4_inst<ST, 2>(a, grid, smem, stream); break;
+        case 3: launch_k4_inst<ST, 3>(a, grid, smem, stream); break;
+        case 4: launch_k4_inst<ST, 4>(a, grid, smem, stream); break;
+        case 6: launch_k4_inst<ST, 6>(a, grid, smem, stream); break;
+        case 8: launch_k4_inst<ST, 8>(a, grid, smem, stream); break;
+        default: launch_k4_inst<ST, 12>(a, grid, smem, stream); break;
+    }
+}
+
+void launch_k4_f32(const K4Args& a, int cpl, dim3 grid, size_t smem, cudaStream_t stream);
+void launch_k4_f16(const K4Args& a, int cpl, dim3 grid, size_t smem, cudaStream_t stream);
+void launch_k4_bf16(const K4Args& a, int cpl, dim3 grid, size_t smem, cudaStream_t stream);
+void launch_k4_i8(const K4Args& a, int cpl, dim3 grid, size_t smem, cudaStream_t stream);
+void launch_k4_b1(const K4Args& a, int cpl, dim3 grid, size_t smem, cudaStream_t stream);
+
+}  // namespace vsb

@@ -1,0 +1,8 @@
+// graph_search_bf16.cu — K4 instantiations for the bf16 storage scalar (see graph_search.cuh).
+#include "graph_search.cuh"
+
+namespace vsb {
+void launch_k4_bf16(const K4Args& a, int cpl, dim3 grid, size_t smem, cudaStream_t stream) {
+    launch_k4_storage<VSB_ST_BF16>(a, cpl, grid, smem, stream);
+}
+}  // namespace vsb

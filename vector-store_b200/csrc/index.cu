@@ -1,0 +1,713 @@
+// index.cu — host side of libvsb200: the index object behind the C ABI of include/vsb200.h.
+//
+// Mirrors what `ThreadedUsearchIndex` + `usearch::Index` are to the reference
+// (crates/vector-store/src/vs_index/usearch.rs:162-251): opaque u64 keys, unique keys
+// (multi=false), explicit capacity (`reserve`), add / remove / search, and a live count.
+//
+// HBM layout (all sized by `capacity`, grown by vsb_reserve with a stream-ordered copy):
+//   rows   [cap][row_bytes]  storage-typed vectors, rows padded to 16 bytes
+//   sq,nrm [cap] f32         canonical sum of squares and its sqrt (cosine / L2 norm trick)
+//   keys   [cap] u64         slot -> key
+//   deny   [cap/32] u32      tombstone bitmap (remove() never moves rows)
+//   graph  [n_graphed][stride] u32   fixed-degree neighbour rows (built by vsb_build)
+//   seed_* [S]               contiguous copy of the entry-point sample ("upper layer")
+// Slots are append-only; slots >= n_graphed form the brute-force tail, so an added vector is
+// searchable as soon as vsb_add returns (dropping AsyncInProgress promises that).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/vsb200.h"
+#include "kernels.h"
+
+namespace vsb {
+std::atomic<uint64_t> g_kernel_launches{0};
+}
+
+namespace {
+
+thread_local std::string g_last_error;
+
+vsb_status fail(vsb_status st, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return st;
+}
+
+#define CU(expr)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(e_ == cudaErrorMemoryAllocation ? VSB_EOOM : VSB_ECUDA, "%s: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                  \
+    } while (0)
+
+#define ST(expr)                        \
+    do {                                \
+        vsb_status s_ = (expr);         \
+        if (s_ != VSB_OK) return s_;    \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    // grow-only scratch (contents not preserved)
+    cudaError_t ensure(size_t want) {
+        if (want <= bytes) return cudaSuccess;
+        release();
+        size_t sz = want + want / 4;
+        cudaError_t e = cudaMalloc(&p, sz);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return e;
+        }
+        bytes = sz;
+        return cudaSuccess;
+    }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct vsb_index {
+    std::mutex mu;
+    vsb_options opt{};
+    uint32_t dim = 0, row_bytes = 0;
+    int metric = 0, storage = 0, device = 0, sm_count = 148;
+    uint32_t degree = 32, graph_stride = 32, k_init = 64;
+    uint32_t itopk = 64, max_iters = 0, n_seeds = 32, min_graph_size = 4096;
+    bool instrumented = false;
+
+    cudaStream_t stream = nullptr;
+    cudaStream_t last_stream = nullptr;
+
+    uint64_t capacity = 0;
+    uint32_t n_slots = 0, n_graphed = 0, n_seed_rows = 0;
+    uint64_t live = 0;
+    std::atomic<uint64_t> live_atomic{0};
+    std::atomic<uint64_t> capacity_atomic{0};
+    bool any_tombstone = false;
+
+    DevBuf rows, sq, nrm, keys, deny, graph;
+    DevBuf seed_rows, seed_sq, seed_nrm, seed_slots;
+    DevBuf q_in, q_rows, q_sq, q_nrm, part, seed_part, tmp_keys, tmp_dists, counters, add_in, allow;
+    std::unordered_map<uint64_t, uint32_t> key2slot;
+    std::vector<uint32_t> h_deny;
+
+    uint64_t last_evals = 0, last_parents = 0, last_queries = 0;
+
+    size_t hbm_bytes() const {
+        const DevBuf* all[] = {&rows, &sq, &nrm, &keys, &deny, &graph, &seed_rows, &seed_sq, &seed_nrm, &seed_slots,
+                               &q_in, &q_rows, &q_sq, &q_nrm, &part, &seed_part, &tmp_keys, &tmp_dists, &counters,
+                               &add_in, &allow};
+        size_t s = 0;
+        for (auto* b : all) s += b->bytes;
+        return s;
+    }
+
+    vsb::RowsView corpus_view() const {
+        vsb::RowsView v;
+        v.rows = rows.as<uint8_t>();
+        v.sq = sq.as<float>();
+        v.nrm = nrm.as<float>();
+        v.row_bytes = row_bytes;
+        v.n = n_slots;
+        return v;
+    }
+
+    vsb_status use_stream(cudaStream_t s) {
+        if (last_stream != nullptr && last_stream != s) CU(cudaStreamSynchronize(last_stream));
+        last_stream = s;
+        return VSB_OK;
+    }
+
+    vsb_status reserve(uint64_t cap);
+    vsb_status add(const uint64_t* k, const float* r, uint64_t n);
+    vsb_status remove(const uint64_t* k, uint64_t n, uint64_t* removed);
+    vsb_status build();
+    vsb_status exact_block(const vsb::RowsView& q, const vsb::RowsView& x, uint32_t x_lo, uint32_t x_hi,
+                           const uint32_t* deny_bm, const uint64_t* key_arr, const uint32_t* allow_bm,
+                           uint64_t allow_bits, uint32_t k, uint64_t* out_keys, float* out_dists,
+                           uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t s);
+    vsb_status search_dev(const float* d_q, uint64_t nq, uint32_t k, uint64_t* d_keys, float* d_dists,
+                          uint32_t* d_counts, cudaStream_t s, bool exact, const uint32_t* d_allow,
+                          uint64_t allow_bits);
+    vsb_status search_host(const float* queries, uint64_t nq, uint32_t k, uint64_t* keys_out, float* dists_out,
+                           uint32_t* counts_out, bool exact, const uint32_t* allow_bitmap, uint64_t allow_bits);
+};
+
+static uint32_t storage_row_bytes(int storage, uint32_t dim) {
+    uint64_t bits = 0;
+    switch (storage) {
+        case VSB_F32: bits = (uint64_t)dim * 32; break;
+        case VSB_F16:
+        case VSB_BF16: bits = (uint64_t)dim * 16; break;
+        case VSB_I8: bits = (uint64_t)dim * 8; break;
+        default: bits = dim; break;
+    }
+    return (uint32_t)(((bits + 127) / 128) * 16);
+}
+
+vsb_status vsb_index::reserve(uint64_t cap) {
+    if (cap <= capacity) return VSB_OK;
+    if (cap >= (1ull << 28)) return fail(VSB_EINVAL, "capacity %llu exceeds the 2^28 rows one shard holds", (unsigned long long)cap);
+    CU(cudaSetDevice(device));
+    const uint64_t words = (cap + 31) / 32;
+    DevBuf n_rows, n_sq, n_nrm, n_keys, n_deny;
+    auto alloc = [&](DevBuf& b, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(&b.p, bytes ? bytes : 16);
+        if (e == cudaSuccess) b.bytes = bytes ? bytes : 16; else b.p = nullptr;
+        return e;
+    };
+    CU(alloc(n_rows, cap * row_bytes));
+    CU(alloc(n_sq, cap * 4));
+    CU(alloc(n_nrm, cap * 4));
+    CU(alloc(n_keys, cap * 8));
+    CU(alloc(n_deny, words * 4));
+    ST(use_stream(stream));
+    CU(cudaMemsetAsync(n_deny.p, 0, words * 4, stream));
+    if (n_slots > 0) {
+        CU(cudaMemcpyAsync(n_rows.p, rows.p, (size_t)n_slots * row_bytes, cudaMemcpyDeviceToDevice, stream));
+        CU(cudaMemcpyAsync(n_sq.p, sq.p, (size_t)n_slots * 4, cudaMemcpyDeviceToDevice, stream));
+        CU(cudaMemcpyAsync(n_nrm.p, nrm.p, (size_t)n_slots * 4, cudaMemcpyDeviceToDevice, stream));
+        CU(cudaMemcpyAsync(n_keys.p, keys.p, (size_t)n_slots * 8, cudaMemcpyDeviceToDevice, stream));
+        CU(cudaMemcpyAsync(n_deny.p, deny.p, (size_t)((n_slots + 31) / 32) * 4, cudaMemcpyDeviceToDevice, stream));
+    }
+    CU(cudaStreamSynchronize(stream));
+    std::swap(rows, n_rows);
+    std::swap(sq, n_sq);
+    std::swap(nrm, n_nrm);
+    std::swap(keys, n_keys);
+    std::swap(deny, n_deny);
+    h_deny.resize(words, 0u);
+    capacity = cap;
+    capacity_atomic.store(cap);
+    key2slot.reserve((size_t)cap);
+    return VSB_OK;
+}
+
+vsb_status vsb_index::add(const uint64_t* k, const float* r, uint64_t n) {
+    if (n == 0) return VSB_OK;
+    if (k == nullptr || r == nullptr) return fail(VSB_EINVAL, "null keys/rows");
+    if (live + n > capacity || (uint64_t)n_slots + n > capacity)
+        return fail(VSB_EFULL, "size %llu + %llu exceeds capacity %llu: reserve capacity ahead of insertions",
+                    (unsigned long long)n_slots, (unsigned long long)n, (unsigned long long)capacity);
+    {
+        std::unordered_set<uint64_t> batch;
+        if (n > 1) batch.reserve((size_t)n);
+        for (uint64_t i = 0; i < n; ++i) {
+            if (k[i] == 0xFFFFFFFFFFFFFFFFull) return fail(VSB_EINVAL, "key UINT64_MAX is reserved");
+            if (key2slot.count(k[i]) || (n > 1 && !batch.insert(k[i]).second))
+                return fail(VSB_EDUPKEY, "duplicate key %llu", (unsigned long long)k[i]);
+        }
+    }
+    CU(cudaSetDevice(device));
+    ST(use_stream(stream));
+    const uint64_t chunk_rows = std::max<uint64_t>(1, (256ull << 20) / ((uint64_t)dim * 4));
+    for (uint64_t b = 0; b < n; b += chunk_rows) {
+        const uint64_t nb = std::min(chunk_rows, n - b);
+        CU(add_in.ensure(nb * dim * 4));
+        CU(cudaMemcpyAsync(add_in.p, r + b * dim, nb * dim * 4, cudaMemcpyHostToDevice, stream));
+        const uint32_t s0 = n_slots + (uint32_t)b;
+        vsb::launch_convert_rows(storage, add_in.as<float>(), (uint32_t)nb, dim, rows.as<uint8_t>() + (size_t)s0 * row_bytes,
+                                 row_bytes, sq.as<float>() + s0, nrm.as<float>() + s0, stream);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(keys.as<uint64_t>() + s0, k + b, nb * 8, cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));  // add_in is reused by the next chunk
+    }
+    for (uint64_t i = 0; i < n; ++i) key2slot.emplace(k[i], n_slots + (uint32_t)i);
+    n_slots += (uint32_t)n;
+    live += n;
+    live_atomic.store(live);
+    return VSB_OK;
+}
+
+vsb_status vsb_index::remove(const uint64_t* k, uint64_t n, uint64_t* removed) {
+    uint64_t cnt = 0;
+    uint32_t lo_word = 0xFFFFFFFFu, hi_word = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        auto it = key2slot.find(k[i]);
+        if (it == key2slot.end()) continue;
+        const uint32_t slot = it->second;
+        h_deny[slot >> 5] |= 1u << (slot & 31);
+        lo_word = std::min(lo_word, slot >> 5);
+        hi_word = std::max(hi_word, slot >> 5);
+        key2slot.erase(it);
+        ++cnt;
+    }
+    if (cnt) {
+        CU(cudaSetDevice(device));
+        ST(use_stream(stream));
+        CU(cudaMemcpyAsync(deny.as<uint32_t>() + lo_word, h_deny.data() + lo_word, (size_t)(hi_word - lo_word + 1) * 4,
+                           cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+        live -= cnt;
+        live_atomic.store(live);
+        any_tombstone = true;
+    }
+    if (removed) *removed = cnt;
+    return VSB_OK;
+}
+
+// exact top-k of the queries `q` against rows [x_lo, x_hi) of `x` (K1 + K3)
+vsb_status vsb_index::exact_block(const vsb::RowsView& q, const vsb::RowsView& x, uint32_t x_lo, uint32_t x_hi,
+                                  const uint32_t* deny_bm, const uint64_t* key_arr, const uint32_t* allow_bm,
+                                  uint64_t allow_bits, uint32_t k, uint64_t* out_keys, float* out_dists,
+                                  uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t s) {
+    vsb::ExactParams p;
+    p.storage = storage;
+    p.metric = metric;
+    p.q = q;
+    p.x = x;
+    p.x_lo = x_lo;
+    p.x_hi = x_hi;
+    p.deny = deny_bm;
+    p.keys = key_arr;
+    p.allow = allow_bm;
+    p.allow_bits = allow_bits;
+    const uint32_t extra = std::max<uint32_t>(16, k / 4) + (self_base >= 0 ? 1 : 0);
+    p.kp = round_up(k + extra, 32);
+    if (p.kp > 256) return fail(VSB_EINVAL, "k=%u too large for the exact path (max 200)", k);
+    p.n_splits = vsb::exact_pick_splits(q.n, x_hi - x_lo, sm_count);
+    CU(part.ensure(vsb::exact_part_elems(q.n, p.n_splits, p.kp) * 8));
+    p.part = part.as<uint64_t>();
+    vsb::launch_exact_candidates(p, s);
+    CU(cudaGetLastError());
+    vsb::launch_exact_rerank(p, k, out_keys, out_dists, out_counts, out_packed, self_base, s);
+    CU(cudaGetLastError());
+    return VSB_OK;
+}
+
+vsb_status vsb_index::build() {
+    CU(cudaSetDevice(device));
+    ST(use_stream(stream));
+    if (live < min_graph_size || !vsb::graph_search_supported(row_bytes)) {
+        n_graphed = 0;
+        n_seed_rows = 0;
+        return VSB_OK;
+    }
+    const uint32_t n = n_slots;
+    const uint32_t R = degree;
+    const uint32_t kin = std::min<uint32_t>(k_init, 128);
+    DevBuf knn, fwd, rev, rev_cnt, scratch;
+    CU(knn.ensure((size_t)n * kin * 8));
+    const vsb::RowsView x = corpus_view();
+    const uint32_t* deny_bm = any_tombstone ? deny.as<uint32_t>() : nullptr;
+    const uint32_t QB = 16384;
+    for (uint32_t b0 = 0; b0 < n; b0 += QB) {
+        vsb::RowsView q;
+        q.n = std::min(QB, n - b0);
+        q.rows = x.rows + (size_t)b0 * row_bytes;
+        q.sq = x.sq + b0;
+        q.nrm = x.nrm + b0;
+        q.row_bytes = row_bytes;
+        ST(exact_block(q, x, 0, n, deny_bm, keys.as<uint64_t>(), nullptr, 0, kin, nullptr, nullptr, nullptr,
+                       knn.as<uint64_t>() + (size_t)b0 * kin, (int64_t)b0, stream));
+    }
+    CU(fwd.ensure((size_t)n * R * 4));
+    CU(rev.ensure((size_t)n * R * 4));
+    CU(rev_cnt.ensure((size_t)n * 4));
+    vsb::launch_prune_detour(knn.as<uint64_t>(), n, kin, R, deny_bm, fwd.as<uint32_t>(), stream);
+    CU(cudaGetLastError());
+    const size_t sb = vsb::reverse_edges_scratch_bytes(n, R);
+    CU(scratch.ensure(sb));
+    vsb::launch_reverse_edges(fwd.as<uint32_t>(), n, R, rev.as<uint32_t>(), rev_cnt.as<uint32_t>(), scratch.p,
+                              scratch.bytes, stream);
+    CU(cudaGetLastError());
+    DevBuf new_graph;
+    CU(new_graph.ensure((size_t)n * graph_stride * 4));
+    vsb::launch_merge_graph(fwd.as<uint32_t>(), rev.as<uint32_t>(), rev_cnt.as<uint32_t>(), n, R,
+                            new_graph.as<uint32_t>(), graph_stride, stream);
+    CU(cudaGetLastError());
+
+    // entry-point sample: a stride permutation of the live slots (deterministic, seed-shifted)
+    uint32_t S = 256;
+    const double target = 4.0 * std::sqrt((double)live);
+    while (S < target && S < 8192) S <<= 1;
+    if (S > live / 4) S = (uint32_t)std::max<uint64_t>(32, live / 4);
+    std::vector<uint32_t> h_seeds;
+    h_seeds.reserve(S);
+    {
+        uint64_t step = (uint64_t)((double)n * 0.6180339887498949) | 1ull;
+        auto gcd = [](uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; };
+        while (gcd(step, n) != 1) step += 2;
+        uint64_t pos = opt.seed % n;
+        for (uint32_t i = 0; i < n && h_seeds.size() < S; ++i) {
+            const uint32_t slot = (uint32_t)pos;
+            pos = (pos + step) % n;
+            if (h_deny[slot >> 5] >> (slot & 31) & 1u) continue;
+            h_seeds.push_back(slot);
+        }
+    }
+    S = (uint32_t)h_seeds.size();
+    CU(seed_slots.ensure((size_t)S * 4));
+    CU(seed_rows.ensure((size_t)S * row_bytes));
+    CU(seed_sq.ensure((size_t)S * 4));
+    CU(seed_nrm.ensure((size_t)S * 4));
+    CU(cudaMemcpyAsync(seed_slots.p, h_seeds.data(), (size_t)S * 4, cudaMemcpyHostToDevice, stream));
+    vsb::launch_gather_rows(x.rows, row_bytes, x.sq, x.nrm, seed_slots.as<uint32_t>(), S, seed_rows.as<uint8_t>(),
+                            seed_sq.as<float>(), seed_nrm.as<float>(), stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(stream));
+    std::swap(graph, new_graph);
+    n_graphed = n;
+    n_seed_rows = S;
+    return VSB_OK;
+}
+
+vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint64_t* d_keys, float* d_dists,
+                                 uint32_t* d_counts, cudaStream_t s, bool exact, const uint32_t* d_allow,
+                                 uint64_t allow_bits) {
+    if (nq == 0) return VSB_OK;
+    if (k == 0) return fail(VSB_EINVAL, "k must be > 0");
+    if (d_q == nullptr || d_keys == nullptr || d_dists == nullptr) return fail(VSB_EINVAL, "null buffer");
+    CU(cudaSetDevice(device));
+    ST(use_stream(s));
+    const uint64_t QCHUNK = 65536;
+    for (uint64_t q0 = 0; q0 < nq; q0 += QCHUNK) {
+        const uint32_t nb = (uint32_t)std::min<uint64_t>(QCHUNK, nq - q0);
+        uint64_t* o_keys = d_keys + q0 * k;
+        float* o_dists = d_dists + q0 * k;
+        uint32_t* o_counts = d_counts ? d_counts + q0 : nullptr;
+        if (n_slots == 0) {
+            vsb::launch_fill_empty(o_keys, o_dists, o_counts, nb, k, s);
+            CU(cudaGetLastError());
+            continue;
+        }
+        CU(q_rows.ensure((size_t)nb * row_bytes));
+        CU(q_sq.ensure((size_t)nb * 4));
+        CU(q_nrm.ensure((size_t)nb * 4));
+        vsb::launch_convert_rows(storage, d_q + q0 * dim, nb, dim, q_rows.as<uint8_t>(), row_bytes, q_sq.as<float>(),
+                                 q_nrm.as<float>(), s);
+        CU(cudaGetLastError());
+        vsb::RowsView qv;
+        qv.rows = q_rows.as<uint8_t>();
+        qv.sq = q_sq.as<float>();
+        qv.nrm = q_nrm.as<float>();
+        qv.row_bytes = row_bytes;
+        qv.n = nb;
+        const vsb::RowsView x = corpus_view();
+        const uint32_t* deny_bm = any_tombstone ? deny.as<uint32_t>() : nullptr;
+        const bool use_graph = !exact && d_allow == nullptr && n_graphed > 0 && k <= 512;
+        const uint32_t tail_lo = use_graph ? n_graphed : 0, tail_hi = n_slots;
+        const bool have_tail = tail_hi > tail_lo;
+        uint64_t* g_keys = o_keys;
+        float* g_dists = o_dists;
+        uint64_t* t_keys = o_keys;
+        float* t_dists = o_dists;
+        if (use_graph && have_tail) {
+            CU(tmp_keys.ensure((size_t)2 * nb * k * 8));
+            CU(tmp_dists.ensure((size_t)2 * nb * k * 4));
+            g_keys = tmp_keys.as<uint64_t>();
+            g_dists = tmp_dists.as<float>();
+            t_keys = g_keys + (size_t)nb * k;
+            t_dists = g_dists + (size_t)nb * k;
+        }
+        if (use_graph) {
+            // seed layer: exact candidates against the contiguous entry-point sample
+            vsb::ExactParams sp;
+            sp.storage = storage;
+            sp.metric = metric;
+            sp.q = qv;
+            sp.x.rows = seed_rows.as<uint8_t>();
+            sp.x.sq = seed_sq.as<float>();
+            sp.x.nrm = seed_nrm.as<float>();
+            sp.x.row_bytes = row_bytes;
+            sp.x.n = n_seed_rows;
+            sp.x_lo = 0;
+            sp.x_hi = n_seed_rows;
+            sp.keys = nullptr;  // ties by seed index: LessByKey is never asked (see below)
+            sp.kp = 32;
+            sp.n_splits = vsb::exact_pick_splits(nb, n_seed_rows, sm_count);
+            CU(seed_part.ensure(vsb::exact_part_elems(nb, sp.n_splits, 32) * 8));
+            sp.part = seed_part.as<uint64_t>();
+            // identity "keys" so that equal distances fall back to the seed index
+            sp.keys = nullptr;
+            vsb::launch_exact_candidates(sp, s);
+            CU(cudaGetLastError());
+            vsb::SearchParams gp;
+            gp.storage = storage;
+            gp.metric = metric;
+            gp.q = qv;
+            gp.x = x;
+            gp.graph = graph.as<uint32_t>();
+            gp.graph_stride = graph_stride;
+            gp.degree = degree;
+            gp.n_graphed = n_graphed;
+            gp.seed_lists = seed_part.as<uint64_t>();
+            gp.seed_stride = sp.n_splits * 32;
+            gp.n_seeds = n_seeds;
+            gp.seed_slots = seed_slots.as<uint32_t>();
+            gp.deny = deny_bm;
+            gp.keys = keys.as<uint64_t>();
+            gp.itopk = std::max(itopk, k);
+            gp.max_iters = max_iters;
+            gp.k = k;
+            gp.out_keys = g_keys;
+            gp.out_dists = g_dists;
+            gp.out_counts = have_tail ? nullptr : o_counts;
+            if (instrumented) {
+                CU(counters.ensure(16));
+                CU(cudaMemsetAsync(counters.p, 0, 16, s));
+                gp.counters = counters.as<unsigned long long>();
+            }
+            vsb::launch_graph_search(gp, s);
+            CU(cudaGetLastError());
+            if (instrumented) {
+                unsigned long long h[2];
+                CU(cudaMemcpyAsync(h, counters.p, 16, cudaMemcpyDeviceToHost, s));
+                CU(cudaStreamSynchronize(s));
+                last_evals = h[0];
+                last_parents = h[1];
+                last_queries = nb;
+            }
+        }
+        if (have_tail) {
+            ST(exact_block(qv, x, tail_lo, tail_hi, deny_bm, keys.as<uint64_t>(), d_allow, allow_bits, k, t_keys,
+                           t_dists, use_graph ? nullptr : o_counts, nullptr, -1, s));
+        }
+        if (use_graph && have_tail) {
+            vsb::launch_merge_topk(g_keys, g_dists, 2, nb, k, o_keys, o_dists, o_counts, s);
+            CU(cudaGetLastError());
+        }
+    }
+    return VSB_OK;
+}
+
+vsb_status vsb_index::search_host(const float* queries, uint64_t nq, uint32_t k, uint64_t* keys_out,
+                                  float* dists_out, uint32_t* counts_out, bool exact, const uint32_t* allow_bitmap,
+                                  uint64_t allow_bits) {
+    if (nq == 0) return VSB_OK;
+    if (k == 0) return fail(VSB_EINVAL, "k must be > 0");
+    if (queries == nullptr || keys_out == nullptr || dists_out == nullptr) return fail(VSB_EINVAL, "null buffer");
+    CU(cudaSetDevice(device));
+    ST(use_stream(stream));
+    DevBuf& d_in = q_in;
+    const size_t in_bytes = (size_t)nq * dim * 4;
+    const size_t keys_bytes = (size_t)nq * k * 8, dists_bytes = (size_t)nq * k * 4, counts_bytes = (size_t)nq * 4;
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    CU(d_in.ensure(al(in_bytes) + al(keys_bytes) + al(dists_bytes) + al(counts_bytes)));
+    uint8_t* base = d_in.as<uint8_t>();
+    float* dq = reinterpret_cast<float*>(base);
+    uint64_t* dk = reinterpret_cast<uint64_t*>(base + al(in_bytes));
+    float* dd = reinterpret_cast<float*>(base + al(in_bytes) + al(keys_bytes));
+    uint32_t* dc = reinterpret_cast<uint32_t*>(base + al(in_bytes) + al(keys_bytes) + al(dists_bytes));
+    CU(cudaMemcpyAsync(dq, queries, in_bytes, cudaMemcpyHostToDevice, stream));
+    const uint32_t* d_allow = nullptr;
+    if (allow_bitmap != nullptr) {
+        const size_t words = (size_t)((allow_bits + 31) / 32);
+        CU(allow.ensure(std::max<size_t>(words * 4, 16)));
+        CU(cudaMemcpyAsync(allow.p, allow_bitmap, words * 4, cudaMemcpyHostToDevice, stream));
+        d_allow = allow.as<uint32_t>();
+    }
+    ST(search_dev(dq, nq, k, dk, dd, dc, stream, exact || allow_bitmap != nullptr, d_allow, allow_bits));
+    CU(cudaMemcpyAsync(keys_out, dk, keys_bytes, cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(dists_out, dd, dists_bytes, cudaMemcpyDeviceToHost, stream));
+    if (counts_out) CU(cudaMemcpyAsync(counts_out, dc, counts_bytes, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return VSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+vsb_status vsb_create(const vsb_options* o, vsb_index** out) {
+    if (o == nullptr || out == nullptr) return fail(VSB_EINVAL, "null options/out");
+    *out = nullptr;
+    if (o->dimensions == 0) return fail(VSB_EINVAL, "dimensions must be > 0");
+    if (o->storage < VSB_F32 || o->storage > VSB_B1) return fail(VSB_EINVAL, "unknown storage scalar %d", o->storage);
+    if (o->metric < VSB_L2SQ || o->metric > VSB_HAMMING) return fail(VSB_EINVAL, "unknown metric %d", o->metric);
+    int metric = o->metric;
+    // usearch.rs:450-464: B1 always uses Hamming; Hamming without B1 is rejected (usearch.rs:480-485)
+    if (o->storage == VSB_B1) metric = VSB_HAMMING;
+    else if (metric == VSB_HAMMING) return fail(VSB_EINVAL, "Binary space type requires B1 quantization.");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(VSB_ECUDA, "no usable CUDA device (%s): vsb200 has no CPU fallback", cudaGetErrorString(e));
+    int dev = o->device;
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(VSB_EINVAL, "device %d out of range (%d devices)", dev, ndev);
+    CU(cudaSetDevice(dev));
+    vsb_index* ix = new (std::nothrow) vsb_index();
+    if (!ix) return fail(VSB_EOOM, "host allocation failed");
+    ix->opt = *o;
+    ix->dim = o->dimensions;
+    ix->metric = metric;
+    ix->storage = o->storage;
+    ix->device = dev;
+    ix->row_bytes = storage_row_bytes(o->storage, o->dimensions);
+    const uint32_t M = o->connectivity ? o->connectivity : 16;
+    const uint32_t ef_add = o->expansion_add ? o->expansion_add : 128;
+    const uint32_t ef_search = o->expansion_search ? o->expansion_search : 64;
+    ix->degree = std::min<uint32_t>(std::max<uint32_t>(2 * M, 8), 64);
+    ix->graph_stride = round_up(ix->degree, 32);
+    ix->k_init = std::min<uint32_t>(std::max<uint32_t>(ef_add / 2, ix->degree), 128);
+    ix->itopk = std::min<uint32_t>(round_up(ef_search, 32), 512);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ix;
+        return fail(VSB_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    *out = ix;
+    return VSB_OK;
+}
+
+void vsb_destroy(vsb_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    cudaDeviceSynchronize();
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+}
+
+vsb_status vsb_reserve(vsb_index* ix, uint64_t capacity) {
+    if (!ix) return fail(VSB_EINVAL, "null index");
+    std::lock_guard<std::mutex> g(ix->mu);
+    return ix->reserve(capacity);
+}
+
+uint64_t vsb_capacity(const vsb_index* ix) { return ix ? ix->capacity_atomic.load() : 0; }
+uint64_t vsb_size(const vsb_index* ix) { return ix ? ix->live_atomic.load() : 0; }
+
+vsb_status vsb_add(vsb_index* ix, const uint64_t* keys, const float* rows, uint64_t n) {
+    if (!ix) return fail(VSB_EINVAL, "null index");
+    std::lock_guard<std::mutex> g(ix->mu);
+    return ix->add(keys, rows, n);
+}
+
+vsb_status vsb_remove(vsb_index* ix, const uint64_t* keys, uint64_t n, uint64_t* n_removed) {
+    if (!ix) return fail(VSB_EINVAL, "null index");
+    if (n_removed) *n_removed = 0;
+    if (n == 0) return VSB_OK;
+    if (!keys) return fail(VSB_EINVAL, "null keys");
+    std::lock_guard<std::mutex> g(ix->mu);
+    return ix->remove(keys, n, n_removed);
+}
+
+int vsb_contains(const vsb_index* ix, uint64_t key) {
+    if (!ix) return 0;
+    std::lock_guard<std::mutex> g(const_cast<vsb_index*>(ix)->mu);
+    return ix->key2slot.count(key) ? 1 : 0;
+}
+
+vsb_status vsb_build(vsb_index* ix) {
+    if (!ix) return fail(VSB_EINVAL, "null index");
+    std::lock_guard<std::mutex> g(ix->mu);
+    return ix->build();
+}
+
+vsb_status vsb_set_search_params(vsb_index* ix, const vsb_search_params* p) {
+    if (!ix || !p) return fail(VSB_EINVAL, "null argument");
+    std::lock_guard<std::mutex> g(ix->mu);
+    if (p->expansion_search) ix->itopk = std::min<uint32_t>(round_up(p->expansion_search, 32), 512);
+    if (p->max_iterations) ix->max_iters = p->max_iterations;
+    if (p->n_seeds) ix->n_seeds = std::min<uint32_t>(p->n_seeds, 32);
+    if (p->min_graph_size) ix->min_graph_size = p->min_graph_size;
+    return VSB_OK;
+}
+
+vsb_status vsb_set_instrumented(vsb_index* ix, int on) {
+    if (!ix) return fail(VSB_EINVAL, "null index");
+    std::lock_guard<std::mutex> g(ix->mu);
+    ix->instrumented = on != 0;
+    return VSB_OK;
+}
+
+vsb_status vsb_get_stats(vsb_index* ix, vsb_stats* out) {
+    if (!ix || !out) return fail(VSB_EINVAL, "null argument");
+    std::lock_guard<std::mutex> g(ix->mu);
+    out->kernel_launches = vsb::g_kernel_launches.load();
+    out->distance_evals = ix->last_evals;
+    out->parent_expansions = ix->last_parents;
+    out->queries = ix->last_queries;
+    out->n_slots = ix->n_slots;
+    out->n_graphed = ix->n_graphed;
+    out->graph_degree = ix->degree;
+    out->row_bytes = ix->row_bytes;
+    out->n_seed_rows = ix->n_seed_rows;
+    out->hbm_bytes = ix->hbm_bytes();
+    return VSB_OK;
+}
+
+vsb_status vsb_search(vsb_index* ix, const float* queries, uint64_t q, uint32_t k, uint64_t* keys, float* distances,
+                      uint32_t* counts) {
+    if (!ix) return fail(VSB_EINVAL, "null index");
+    std::lock_guard<std::mutex> g(ix->mu);
+    return ix->search_host(queries, q, k, keys, distances, counts, false, nullptr, 0);
+}
+
+vsb_status vsb_search_exact(vsb_index* ix, const float* queries, uint64_t q, uint32_t k, uint64_t* keys,
+                            float* distances, uint32_t* counts) {
+    if (!ix) return fail(VSB_EINVAL, "null index");
+    std::lock_guard<std::mutex> g(ix->mu);
+    return ix->search_host(queries, q, k, keys, distances, counts, true, nullptr, 0);
+}
+
+vsb_status vsb_search_filtered(vsb_index* ix, const float* queries, uint64_t q, uint32_t k,
+                               const uint32_t* allow_bitmap, uint64_t bitmap_bits, uint64_t* keys, float* distances,
+                               uint32_t* counts) {
+    if (!ix) return fail(VSB_EINVAL, "null index");
+    if (!allow_bitmap) return fail(VSB_EINVAL, "null bitmap");
+    std::lock_guard<std::mutex> g(ix->mu);
+    return ix->search_host(queries, q, k, keys, distances, counts, true, allow_bitmap, bitmap_bits);
+}
+
+vsb_status vsb_search_dev(vsb_index* ix, const float* d_queries, uint64_t q, uint32_t k, uint64_t* d_keys,
+                          float* d_distances, uint32_t* d_counts, void* stream, int exact) {
+    if (!ix) return fail(VSB_EINVAL, "null index");
+    std::lock_guard<std::mutex> g(ix->mu);
+    return ix->search_dev(d_queries, q, k, d_keys, d_distances, d_counts, static_cast<cudaStream_t>(stream),
+                          exact != 0, nullptr, 0);
+}
+
+vsb_status vsb_merge_topk_dev(const uint64_t* d_keys, const float* d_distances, uint32_t parts, uint64_t q, uint32_t k,
+                              uint64_t* d_out_keys, float* d_out_distances, uint32_t* d_out_counts, int device,
+                              void* stream) {
+    if (!d_keys || !d_distances || !d_out_keys || !d_out_distances) return fail(VSB_EINVAL, "null buffer");
+    if (parts == 0 || k == 0 || (uint64_t)parts * k > 2048) return fail(VSB_EINVAL, "parts*k must be in [1, 2048]");
+    if (device >= 0) CU(cudaSetDevice(device));
+    vsb::launch_merge_topk(d_keys, d_distances, parts, q, k, d_out_keys, d_out_distances, d_out_counts,
+                           static_cast<cudaStream_t>(stream));
+    CU(cudaGetLastError());
+    return VSB_OK;
+}
+
+void vsb_f32_to_b1x8(const float* v, uint64_t n, uint8_t* out) {
+    const uint64_t nb = (n + 7) / 8;
+    for (uint64_t j = 0; j < nb; ++j) {
+        uint8_t b = 0;
+        for (uint64_t i = 0; i < 8 && 8 * j + i < n; ++i)
+            if (v[8 * j + i] > 0.0f) b |= (uint8_t)(1u << i);
+        out[j] = b;
+    }
+}
+
+const char* vsb_last_error(void) { return g_last_error.c_str(); }
+const char* vsb_version(void) { return "vsb200-0.1.0"; }
+
+}  // extern "C"

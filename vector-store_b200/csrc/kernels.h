@@ -1,0 +1,93 @@
+// kernels.h — host-callable launchers of every CUDA kernel in libvsb200 (internal).
+#pragma once
+#include <atomic>
+
+#include "common.cuh"
+
+namespace vsb {
+
+// every launcher adds the number of kernels it enqueued (reported as gpu_launches by bench.py)
+extern std::atomic<uint64_t> g_kernel_launches;
+
+// A block of stored rows: storage-typed bytes + canonical norms.
+struct RowsView {
+    const uint8_t* rows = nullptr;  // [n][row_bytes]
+    const float* sq = nullptr;      // canonical sum of squares (popcount for b1)
+    const float* nrm = nullptr;     // sqrt(sq)
+    uint32_t row_bytes = 0;
+    uint32_t n = 0;
+};
+
+// K0 ------------------------------------------------------------------------------------------
+void launch_convert_rows(int storage, const float* in, uint32_t n_rows, uint32_t dim, uint8_t* out,
+                         uint32_t row_bytes, float* sq, float* nrm, cudaStream_t stream);
+void launch_gather_rows(const uint8_t* rows, uint32_t row_bytes, const float* sq, const float* nrm,
+                        const uint32_t* slots, uint32_t n, uint8_t* out_rows, float* out_sq, float* out_nrm,
+                        cudaStream_t stream);
+
+// K1 + K3 (exact.cu) ----------------------------------------------------------------------------
+struct ExactParams {
+    int storage = 0, metric = 0;
+    RowsView q;                       // converted queries
+    RowsView x;                       // corpus block; candidate slots are x_base + row index
+    uint32_t x_lo = 0, x_hi = 0;      // row range inside x
+    const uint32_t* deny = nullptr;   // tombstone bitmap over rows of x (nullable)
+    const uint64_t* keys = nullptr;   // u64 key per row of x (tie-break + output)
+    const uint32_t* allow = nullptr;  // N1: bitmap over (key & 2^48-1) (nullable)
+    uint64_t allow_bits = 0;
+    uint32_t kp = 32;                 // candidate list length, multiple of 32, <= 256
+    uint32_t n_splits = 1;
+    uint64_t* part = nullptr;         // scratch [q.n][n_splits][kp]
+};
+size_t exact_part_elems(uint32_t nq, uint32_t n_splits, uint32_t kp);
+uint32_t exact_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count);
+// candidates by approximate distance (any summation order), over-fetched to kp
+void launch_exact_candidates(const ExactParams& p, cudaStream_t stream);
+// merge the split lists, re-evaluate the canonical distance, sort by (distance,key), emit top-k.
+//   out_keys/out_dists/out_counts: user-facing result (nullable)
+//   out_packed: [q.n][k] packed (ord(dist)<<32 | slot), kInvalidPacked padded (nullable; used by the build)
+//   self_base: if >= 0 the query i is row (self_base + i) of x and is dropped from its own list
+void launch_exact_rerank(const ExactParams& p, uint32_t k, uint64_t* out_keys, float* out_dists,
+                         uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t stream);
+
+// K6 (graph_build.cu) ---------------------------------------------------------------------------
+// knn: [n][k_init] packed lists (ascending); produces fwd [n][R] pruned by detour count.
+void launch_prune_detour(const uint64_t* knn, uint32_t n, uint32_t k_init, uint32_t R, const uint32_t* deny,
+                         uint32_t* fwd, cudaStream_t stream);
+// deterministic reverse-edge lists: rev [n][R] (sorted by (rank in source list, source slot)), rev_cnt[n]
+size_t reverse_edges_scratch_bytes(uint32_t n, uint32_t R);
+void launch_reverse_edges(const uint32_t* fwd, uint32_t n, uint32_t R, uint32_t* rev, uint32_t* rev_cnt,
+                          void* scratch, size_t scratch_bytes, cudaStream_t stream);
+// final rows: fwd[0:R/2] ++ reverse edges (unique) ++ remaining fwd, padded with kInvalidSlot
+void launch_merge_graph(const uint32_t* fwd, const uint32_t* rev, const uint32_t* rev_cnt, uint32_t n,
+                        uint32_t R, uint32_t* graph, uint32_t graph_stride, cudaStream_t stream);
+
+// K4 (graph_search.cu) ---------------------------------------------------------------------------
+struct SearchParams {
+    int storage = 0, metric = 0;
+    RowsView q;
+    RowsView x;
+    const uint32_t* graph = nullptr;  // [n_graphed][graph_stride]
+    uint32_t graph_stride = 32, degree = 32;
+    uint32_t n_graphed = 0;
+    const uint64_t* seed_lists = nullptr;  // [q.n][seed_stride] packed (approx dist, seed index)
+    uint32_t seed_stride = 32, n_seeds = 32;
+    const uint32_t* seed_slots = nullptr;  // seed index -> slot
+    const uint32_t* deny = nullptr;
+    const uint64_t* keys = nullptr;
+    uint32_t itopk = 64, max_iters = 0, k = 10;
+    uint64_t* out_keys = nullptr;
+    float* out_dists = nullptr;
+    uint32_t* out_counts = nullptr;
+    unsigned long long* counters = nullptr;  // [2]: distance evals, parent expansions (instrumented only)
+};
+void launch_graph_search(const SearchParams& p, cudaStream_t stream);
+bool graph_search_supported(uint32_t row_bytes);  // rows up to 6144 bytes
+
+// K8 (merge.cu) ----------------------------------------------------------------------------------
+void launch_merge_topk(const uint64_t* keys, const float* dists, uint32_t parts, uint64_t q, uint32_t k,
+                       uint64_t* out_keys, float* out_dists, uint32_t* out_counts, cudaStream_t stream);
+// fills [n] key/dist arrays with the padding values
+void launch_fill_empty(uint64_t* keys, float* dists, uint32_t* counts, uint64_t q, uint32_t k, cudaStream_t stream);
+
+}  // namespace vsb
