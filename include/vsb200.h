@@ -117,6 +117,12 @@ int vsb_contains(const vsb_index* index, uint64_t key);
  * over the un-graphed tail, merged with the graph result. */
 vsb_status vsb_build(vsb_index* index);
 
+/* Copies the graph rows [n_graphed][stride] (u32 slot ids, UINT32_MAX padded) and the slot->key
+ * table to host memory; `stride` = 32-rounded degree.  Snapshot/debug hook and the
+ * bit-exact graph parity test.  Either output may be NULL; *n_graphed / *stride are always set. */
+vsb_status vsb_export_graph(vsb_index* index, uint32_t* rows_out, uint64_t* keys_out,
+                            uint64_t* n_graphed, uint32_t* stride);
+
 vsb_status vsb_set_search_params(vsb_index* index, const vsb_search_params* params);
 vsb_status vsb_get_stats(vsb_index* index, vsb_stats* out);
 /* Re-runs nothing: switches the graph-search kernel to its counting build for the

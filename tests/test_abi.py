@@ -1,0 +1,53 @@
+"""The C-ABI library loads and exports every symbol include/vsb200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "vsb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vsb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import vector_store_b200 as v
+    from importlib import import_module
+    native = import_module("vector_store_b200.host.native")
+    lib = ctypes.CDLL(v.lib_path())
+    declared = _header_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in vsb200.h but not exported"
+    bound = sorted(n for n, _, _ in native.SYMBOLS)
+    assert bound == declared, "ctypes binding and header drifted apart"
+
+
+def test_version_and_no_cpu_fallback():
+    import vector_store_b200 as v
+    assert v.version().startswith("vsb200-")
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        # without a device the product must fail loudly, not fall back
+        try:
+            v.GpuIndex(8)
+        except v.VsbError as e:
+            assert e.status == 6  # VSB_ECUDA
+        else:
+            raise AssertionError("GpuIndex was created without a CUDA device")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "vector-store_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(d, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src.replace(
+                    "oracle/exact.c", "").replace("oracle/graph_oracle.py", ""), f"{f} references oracle/"

@@ -1,0 +1,382 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the
+same seeded inputs.  Bit-exact for ids, keys, integer graph rows AND for fp32 distances (the
+kernels and oracle/exact.c share one defined summation order); ANN recall is measured against
+exact ground truth and compared with the USearch-equivalent CPU HNSW at the same M/ef."""
+import threading
+
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import embedding_like, sift_like
+from oracle import graph_oracle
+
+pytestmark = pytest.mark.gpu
+
+INVALID = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def V():
+    import vector_store_b200 as v
+    return v
+
+
+def make_index(x, keys, metric, storage, **kw):
+    v = V()
+    idx = v.GpuIndex(x.shape[1], v.Metric(metric), v.Scalar(storage), **kw)
+    idx.reserve(len(x) + 64)
+    idx.add_batch(keys, x)
+    return idx
+
+
+def assert_bit_equal(gk, gd, gc, ok, od, oc):
+    assert np.array_equal(gc, oc)
+    assert np.array_equal(gk, ok)
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32)), \
+        f"max |diff| = {np.nanmax(np.abs(gd[np.isfinite(od)] - od[np.isfinite(od)]))}"
+
+
+PAIRS = [(s, m) for s in (O.F32, O.F16, O.BF16, O.I8) for m in (O.L2SQ, O.COS, O.IP)] + [(O.B1, O.HAMMING)]
+
+
+@pytest.mark.parametrize("storage,metric", PAIRS)
+def test_exact_bit_parity_ragged(storage, metric):
+    rng = np.random.default_rng(100 + storage * 7 + metric)
+    n, dim, nq, k = 5003, 100, 37, 10  # dim not a multiple of any chunk size, n/nq not tile multiples
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    if storage == O.I8:
+        x = np.clip(x * 0.4, -1.2, 1.2).astype(np.float32)
+    q = rng.standard_normal((nq, dim)).astype(np.float32) * (0.4 if storage == O.I8 else 1.0)
+    keys = rng.permutation(n).astype(np.uint64) + np.uint64(1 << 48)  # epoch bits set, key order != slot order
+    idx = make_index(x, keys, metric, storage)
+    gk, gd, gc = idx.search_batch(q, k, exact=True)
+    ok, od, oc, _ = O.exact_topk(x, q, k, metric, storage, keys=keys)
+    assert_bit_equal(gk, gd, gc, ok, od, oc)
+    # un-built index: the ANN entry point is the brute-force tail => identical
+    gk2, gd2, gc2 = idx.search_batch(q, k)
+    assert_bit_equal(gk2, gd2, gc2, ok, od, oc)
+    space = {O.L2SQ: V().SpaceType.Euclidean, O.COS: V().SpaceType.Cosine, O.IP: V().SpaceType.DotProduct,
+             O.HAMMING: V().SpaceType.Hamming}[metric]
+    for d in gd.ravel():
+        V().Distance.try_from(float(d), space, dim)  # output contract distance.rs:58-105
+
+
+def test_exact_ties_by_key_sift_shaped():
+    n, dim, nq, k = 20000, 128, 64, 10
+    x = sift_like(n, dim)
+    x[5000:5040] = x[4000]  # 41 identical rows straddle any k boundary
+    q = sift_like(nq, dim, seed=4321)
+    q[0] = x[4000]
+    rng = np.random.default_rng(5)
+    keys = rng.permutation(n).astype(np.uint64)
+    idx = make_index(x, keys, O.L2SQ, O.F32)
+    gk, gd, gc = idx.search_batch(q, k, exact=True)
+    ok, od, oc, _ = O.exact_topk(x, q, k, O.L2SQ, O.F32, keys=keys)
+    assert_bit_equal(gk, gd, gc, ok, od, oc)
+    assert np.all(gd[0] == 0.0) and list(gk[0]) == sorted(gk[0])
+
+
+@pytest.mark.parametrize("k", [1, 33, 100, 200])
+def test_exact_k_variants_and_small_index(k):
+    rng = np.random.default_rng(k)
+    x = rng.standard_normal((150, 24)).astype(np.float32)
+    q = rng.standard_normal((5, 24)).astype(np.float32)
+    keys = np.arange(150, dtype=np.uint64) * 3
+    idx = make_index(x, keys, O.COS, O.F32)
+    gk, gd, gc = idx.search_batch(q, k, exact=True)
+    ok, od, oc, _ = O.exact_topk(x, q, k, O.COS, O.F32, keys=keys)
+    assert_bit_equal(gk, gd, gc, ok, od, oc)
+    assert np.all(gc == min(k, 150))
+    assert np.all(np.diff(gd[:, :min(k, 150)], axis=1) >= 0)
+
+
+def test_tombstones_and_filtered_search():
+    rng = np.random.default_rng(11)
+    n, dim = 4000, 48
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    q = rng.standard_normal((20, dim)).astype(np.float32)
+    keys = np.arange(n, dtype=np.uint64) | np.uint64(3 << 48)  # epoch 3, row id = i
+    idx = make_index(x, keys, O.L2SQ, O.BF16)
+    dead = rng.choice(n, 900, replace=False)
+    assert idx.remove_batch(keys[dead]) == 900
+    assert idx.remove_batch(keys[dead[:10]]) == 0  # already gone
+    assert idx.size() == n - 900
+    alive = np.ones(n, np.uint8)
+    alive[dead] = 0
+    gk, gd, gc = idx.search_batch(q, 10, exact=True)
+    ok, od, oc, _ = O.exact_topk(x, q, 10, O.L2SQ, O.BF16, keys=keys, alive=alive)
+    assert_bit_equal(gk, gd, gc, ok, od, oc)
+    # N1: bitmap predicate over row ids (low 48 bits of the key)
+    allow_rows = rng.random(n) < 0.05
+    bm = np.zeros((n + 31) // 32, np.uint32)
+    for r in np.nonzero(allow_rows)[0]:
+        bm[r >> 5] |= np.uint32(1 << (r & 31))
+    alive2 = (alive.astype(bool) & allow_rows).astype(np.uint8)
+    ok2, od2, oc2, _ = O.exact_topk(x, q[:1], 10, O.L2SQ, O.BF16, keys=keys, alive=alive2)
+    hits = idx.filtered_search_bitmap(q[0], 10, bm, n)
+    assert [h[0] for h in hits] == [int(v) for v in ok2[0][:oc2[0]]]
+    assert np.array_equal(np.array([h[1] for h in hits], np.float32).view(np.uint32),
+                          od2[0][:oc2[0]].view(np.uint32))
+
+
+def test_merge_topk_kernel_matches_numpy():
+    import torch
+    from importlib import import_module
+    index_mod = import_module("vector_store_b200.host.index")
+    rng = np.random.default_rng(2)
+    parts, nq, k = 5, 300, 10
+    d = np.sort(rng.integers(0, 50, size=(parts, nq, k)).astype(np.float32), axis=2)  # many ties
+    keys = rng.permutation(parts * nq * k).astype(np.uint64).reshape(parts, nq, k)
+    keys[:, :, 7:] = INVALID
+    d[:, :, 7:] = np.inf
+    order = np.lexsort((keys, d), axis=2) if False else None
+    for p in range(parts):  # make each list ascending by (dist, key)
+        for i in range(nq):
+            o = np.lexsort((keys[p, i], d[p, i]))
+            keys[p, i], d[p, i] = keys[p, i][o], d[p, i][o]
+    tk = torch.from_numpy(keys.view(np.int64)).cuda()
+    td = torch.from_numpy(d).cuda()
+    ok = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    od = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    oc = torch.empty(nq, dtype=torch.int32, device="cuda")
+    index_mod.merge_topk_dev(tk.data_ptr(), td.data_ptr(), parts, nq, k, ok.data_ptr(), od.data_ptr(), oc.data_ptr(),
+                             0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    gk = ok.cpu().numpy().view(np.uint64)
+    gd = od.cpu().numpy()
+    for i in range(nq):
+        ak = keys[:, i, :].ravel()
+        ad = d[:, i, :].ravel()
+        o = np.lexsort((ak, ad))[:k]
+        assert np.array_equal(gk[i], ak[o]) and np.array_equal(gd[i], ad[o])
+    assert np.all(oc.cpu().numpy() == k)
+
+
+# ---- reference golden vectors through the actor mirror (reads like the reference's own tests) ----------
+def cfg(dim, space="Euclidean", quant="F32", **kw):
+    v = V()
+    return v.VsIndexConfiguration("vector.store", dim, space_type=v.SpaceType[space],
+                                  quantization=v.Quantization[quant], **kw)
+
+
+def new_actor(config):
+    a = V().new_index_factory_gpu()(config)
+    a.reserve_increment = 1000
+    return a
+
+
+def test_g1_add_or_replace_size_ann():
+    # vs_index/usearch.rs:1298-1458
+    a = new_actor(cfg(3))
+    a.add_vector(0, 1, [1.0, 1.0, 1.0])
+    a.add_vector(0, 2, [2.0, -2.0, 2.0])
+    a.add_vector(0, 3, [3.0, 3.0, 3.0])
+    assert a.count() == 3
+    keys, dists = a.ann([2.2, -2.2, 2.2], 1)
+    assert keys == [2] and len(dists) == 1
+    a.remove_vector(0, 3)
+    assert a.count() == 2
+    a.add_vector(0, 3, [2.1, -2.1, 2.1])
+    assert a.count() == 3
+    assert a.ann([2.2, -2.2, 2.2], 1)[0] == [3]
+    a.remove_vector(0, 3)
+    assert a.count() == 2
+    assert a.ann([2.2, -2.2, 2.2], 1)[0] == [2]
+    a.stop()
+
+
+def test_g2_similarity_scores_are_decreasing_and_correctly_converted():
+    # tests/integration/vs_index.rs:1746-1887
+    v = V()
+    a = new_actor(cfg(1))
+    for pk, x in ((10, 0.0), (11, 1.0), (13, 3.0)):
+        a.add_vector(0, pk, [x])
+    keys, dists = a.ann([0.0], 3)
+    assert keys == [10, 11, 13] and [float(d) for d in dists] == [0.0, 1.0, 9.0]
+    scores = [v.SimilarityScore.from_distance(d).value for d in dists]
+    assert np.allclose(scores, [1.0, 0.5, 0.1], atol=1e-5) and scores[0] > scores[1] > scores[2]
+
+
+def test_g3_g10_simple_ann_wrong_dim_and_empty():
+    # tests/integration/vs_index.rs:226-311, 441-480, 1889-1951
+    v = V()
+    a = new_actor(cfg(3))
+    assert a.ann([1.0, 2.0, 3.0], 5) == ([], []) and a.count() == 0
+    a.add_vector(0, 1, [1.0, 1.0, 1.0])
+    a.add_vector(0, 2, [2.0, -2.0, 2.0])
+    a.add_vector(0, 3, [3.0, 3.0, 3.0])
+    assert a.ann([2.1, -2.0, 2.0], 1)[0] == [2]
+    with pytest.raises(v.WrongEmbeddingDimension):
+        a.ann([1.0, 2.0], 1)
+    a.add_vector(0, 4, [1.0, 2.0])  # wrong dimension on add: logged and dropped
+    assert a.count() == 3
+    a.add_vector(0, 1, [9.0, 9.0, 9.0])  # duplicate key: logged and swallowed (usearch multi=false)
+    assert a.count() == 3
+    assert a.ann([1.0, 1.0, 1.0], 5)[0] == [1, 2, 3] or len(a.ann([1.0, 1.0, 1.0], 5)[0]) == 3
+    a.can_allocate = False  # memory gate: usearch.rs:1460-1524 allocate_parameter_works
+    a.add_vector(0, 5, [5.0, 5.0, 5.0])
+    assert a.count() == 3
+    a.remove_partition(0)
+    assert a.count() == 0 and a.ann([1.0, 1.0, 1.0], 5) == ([], [])
+
+
+def test_g4_quantization_is_effectively_applied():
+    # tests/integration/quantization.rs:40-124
+    def dist(quant):
+        a = new_actor(cfg(3, quant=quant))
+        a.add_vector(0, 1, [0.9, 0.1, 0.1])
+        return float(a.ann([1.0, 0.0, 0.0], 1)[1][0])
+    assert dist("F32") < 0.1
+    assert dist("I8") > 300 and dist("I8") == 507.0
+
+
+@pytest.mark.parametrize("quant", ["F32", "F16", "BF16", "I8", "B1"])
+def test_g5_g6_self_distance_zero(quant):
+    # tests/integration/quantization.rs:175-259 (dim 1536) and :293-358 (B1, dim 100)
+    for dim in (1536, 100):
+        a = new_actor(cfg(dim, quant=quant))
+        x = np.full(dim, 0.5, np.float32)
+        a.add_vector(0, 1, x)
+        a.add_vector(0, 2, -x)
+        keys, dists = a.ann(x, 1)
+        assert keys == [1] and float(dists[0]) == 0.0
+        keys, dists = a.filtered_ann(x, 2, lambda row: row == 1, max_row_id=2)  # "IN" filter variant
+        assert keys == [1] and float(dists[0]) == 0.0
+
+
+def test_g9_similarity_function_semantics():
+    # crates/validator/src/similarity_functions.rs:113-178
+    rows = {1: [1, 0, 0], 2: [0, 1, 0], 3: [0, 0, 1], 4: [2, 0, 0]}
+    expect_first = {"Euclidean": {1}, "Cosine": {1, 4}, "DotProduct": {4}}
+    for space, first in expect_first.items():
+        a = new_actor(cfg(3, space=space))
+        for pk, x in rows.items():
+            a.add_vector(0, pk, np.array(x, np.float32))
+        keys, dists = a.ann([1.0, 0.0, 0.0], 4)
+        d0 = float(dists[0])
+        assert {k for k, d in zip(keys, dists) if float(d) == d0} == first
+
+
+def test_g11_concurrent_add_and_search():
+    # vs_index/usearch.rs:1526-1607: 2 x cores concurrent adds + searches at dim 1024, exact final count
+    dim, per = 1024, 40
+    a = new_actor(cfg(dim))
+    a.reserve_increment = 4096
+    a.add_vector(0, 10 ** 6, np.ones(dim, np.float32))
+    errors = []
+    lock = threading.Lock()
+
+    def adder(t):
+        rng = np.random.default_rng(t)
+        for i in range(per):
+            with lock:  # the reference's actor loop serialises dispatch; the engine calls run concurrently
+                pass
+            try:
+                a.partitions[0].idx.add(t * 1000 + i, rng.standard_normal(dim).astype(np.float32))
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+    def searcher(t):
+        rng = np.random.default_rng(100 + t)
+        for _ in range(per):
+            try:
+                a.partitions[0].idx.search(rng.standard_normal(dim).astype(np.float32), 5)
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+    a.partitions[0].idx.reserve(8 * per + 64)
+    ts = [threading.Thread(target=adder, args=(t,)) for t in range(8)] + \
+         [threading.Thread(target=searcher, args=(t,)) for t in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors[:3]
+    assert a.partitions[0].idx.size() == 8 * per + 1
+
+
+# ---- graph build + ANN ------------------------------------------------------------------------------
+def test_graph_build_bit_exact_vs_oracle():
+    rng = np.random.default_rng(21)
+    n, dim = 1500, 32
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    keys = rng.permutation(n).astype(np.uint64)
+    idx = make_index(x, keys, O.L2SQ, O.F32, connectivity=8, expansion_add=32)  # R = 16, k_init = 16
+    dead = rng.choice(n, 100, replace=False)
+    idx.remove_batch(keys[dead])
+    idx.set_search_params(min_graph_size=1000)
+    idx.build()
+    rows, gkeys = idx.export_graph()
+    assert rows.shape == (n, 32) and np.array_equal(gkeys, keys)
+    alive = np.ones(n, np.uint8)
+    alive[dead] = 0
+    want = graph_oracle.build_graph(x, k_init=16, R=16, metric=O.L2SQ, storage=O.F32, keys=keys, alive=alive, stride=32)
+    assert np.array_equal(rows, want), f"{(rows != want).any(axis=1).sum()} rows differ"
+
+
+@pytest.mark.parametrize("storage,metric,dim,clusters", [(O.F32, O.COS, 96, 32), (O.BF16, O.COS, 768, 64),
+                                                         (O.F32, O.L2SQ, 128, 0)])
+def test_ann_recall_vs_cpu_hnsw(storage, metric, dim, clusters):
+    n, nq, k = 30000, 500, 10
+    if clusters:
+        x = embedding_like(n, dim, n_clusters=clusters)
+        q = embedding_like(nq, dim, seed=4321, n_clusters=clusters)
+    else:
+        x, q = sift_like(n, dim), sift_like(nq, dim, seed=4321)
+    keys = np.arange(n, dtype=np.uint64)
+    idx = make_index(x, keys, metric, storage)  # defaults M=16 / ef_add=128 / ef_search=64
+    idx.build()
+    st = idx.stats()
+    assert st["n_graphed"] == n and st["graph_degree"] == 32
+    tk, td, tc = idx.search_batch(q, k, exact=True)
+    gk, gd, gc = idx.search_batch(q, k)
+    recall_gpu = O.recall_at_k(gk, tk)
+    h = O.HnswCpu(dim, metric, n, storage=storage)
+    h.add(keys, x)
+    hk, _ = h.search(q, k)
+    recall_cpu = O.recall_at_k(hk, tk)
+    print(f"recall@10 gpu={recall_gpu:.4f} cpu_hnsw={recall_cpu:.4f} (storage={storage} metric={metric} dim={dim})")
+    assert np.all(gc == k)
+    assert np.all(np.diff(gd, axis=1) >= 0)
+    assert recall_gpu >= 0.95
+    assert recall_gpu >= recall_cpu - 0.01
+    # distances of ANN hits are the canonical exact distances of those rows
+    od = O.distance_matrix(x[gk[0].astype(np.int64)], q[:1], metric, storage)[0]
+    assert np.array_equal(gd[0].view(np.uint32), od.view(np.uint32))
+
+
+def test_ann_sees_vectors_added_and_removed_after_build():
+    n, dim = 20000, 64
+    x = embedding_like(n + 200, dim, n_clusters=16)
+    keys = np.arange(n + 200, dtype=np.uint64)
+    idx = make_index(x[:n], keys[:n], O.COS, O.F32)
+    idx.reserve(n + 1000)
+    idx.build()
+    idx.add_batch(keys[n:], x[n:])  # un-graphed tail
+    gk, gd, gc = idx.search_batch(x[n:n + 50], 3)
+    assert np.array_equal(gk[:, 0], keys[n:n + 50]) and np.all(gd[:, 0] <= 1e-6)
+    gk, _, _ = idx.search_batch(x[:50], 1)
+    assert np.array_equal(gk[:, 0], keys[:50])
+    idx.remove_batch(keys[:50])
+    gk, _, gc = idx.search_batch(x[:50], 5)
+    assert not np.isin(gk, keys[:50]).any() and np.all(gc == 5)
+    assert idx.size() == n + 200 - 50
+
+
+def test_c1_full_size_properties():
+    # BASELINE config #1: 100k x 128 f32 L2sq, k=10 — size-independent properties + oracle on a query subset
+    n, dim, k = 100_000, 128, 10
+    x = sift_like(n, dim)
+    q = sift_like(256, dim, seed=4321)
+    keys = np.arange(n, dtype=np.uint64)
+    idx = make_index(x, keys, O.L2SQ, O.F32)
+    gk, gd, gc = idx.search_batch(np.concatenate([q, x[:64]]), k, exact=True)
+    assert np.all(gc == k) and np.all(np.diff(gd, axis=1) >= 0)
+    assert np.all(gd[256:, 0] == 0.0)                        # a stored row is its own nearest neighbour
+    gk2, gd2, _ = idx.search_batch(np.concatenate([q, x[:64]]), k, exact=True)
+    assert np.array_equal(gk, gk2) and np.array_equal(gd, gd2)  # idempotent / deterministic
+    ok, od, oc, _ = O.exact_topk(x, q[:32], k, O.L2SQ, O.F32, keys=keys)
+    assert_bit_equal(gk[:32], gd[:32], gc[:32], ok, od, oc)
+    idx.build()
+    ak, ad, ac = idx.search_batch(q, k)
+    recall = O.recall_at_k(ak, gk[:256])
+    print(f"C1 100k x 128 L2sq recall@10 = {recall:.4f}")
+    assert recall >= 0.95

@@ -621,6 +621,23 @@ vsb_status vsb_build(vsb_index* ix) {
     return ix->build();
 }
 
+vsb_status vsb_export_graph(vsb_index* ix, uint32_t* rows_out, uint64_t* keys_out, uint64_t* n_graphed,
+                            uint32_t* stride) {
+    if (!ix) return fail(VSB_EINVAL, "null index");
+    std::lock_guard<std::mutex> g(ix->mu);
+    if (n_graphed) *n_graphed = ix->n_graphed;
+    if (stride) *stride = ix->graph_stride;
+    CU(cudaSetDevice(ix->device));
+    ST(ix->use_stream(ix->stream));
+    if (rows_out && ix->n_graphed)
+        CU(cudaMemcpyAsync(rows_out, ix->graph.p, (size_t)ix->n_graphed * ix->graph_stride * 4, cudaMemcpyDeviceToHost,
+                           ix->stream));
+    if (keys_out && ix->n_graphed)
+        CU(cudaMemcpyAsync(keys_out, ix->keys.p, (size_t)ix->n_graphed * 8, cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaStreamSynchronize(ix->stream));
+    return VSB_OK;
+}
+
 vsb_status vsb_set_search_params(vsb_index* ix, const vsb_search_params* p) {
     if (!ix || !p) return fail(VSB_EINVAL, "null argument");
     std::lock_guard<std::mutex> g(ix->mu);

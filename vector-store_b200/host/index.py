@@ -1,0 +1,185 @@
+"""`GpuIndex` — host-side mirror of the reference's inner seam, the private trait `UsearchIndex`
+(crates/vector-store/src/vs_index/usearch.rs:142-160: reserve / capacity / add / remove / search /
+filtered_search / stop), implemented over the C ABI of libvsb200.so.  The single-vector methods
+keep the reference's names and error behaviour; the `*_batch` methods expose the batched ABI."""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+
+import numpy as np
+
+from . import native
+from .native import VsbOptions, VsbSearchParams, VsbStats, check, lib
+
+
+class Metric(enum.IntEnum):  # usearch MetricKind as mapped at usearch.rs:480-501
+    L2sq = 0
+    Cos = 1
+    IP = 2
+    Hamming = 3
+
+
+class Scalar(enum.IntEnum):  # usearch ScalarKind, usearch.rs:503-513
+    F32 = 0
+    F16 = 1
+    BF16 = 2
+    I8 = 3
+    B1 = 4
+
+
+INVALID_KEY = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class GpuIndex:
+    def __init__(self, dimensions: int, metric: Metric = Metric.Cos, storage: Scalar = Scalar.F32,
+                 connectivity: int = 0, expansion_add: int = 0, expansion_search: int = 0, device: int = -1,
+                 seed: int = 0):
+        self._lib = lib()
+        opt = VsbOptions(dimensions, int(metric), int(storage), connectivity, expansion_add, expansion_search,
+                         device, 0, seed)
+        h = C.c_void_p()
+        check(self._lib.vsb_create(C.byref(opt), C.byref(h)))
+        self._h = h
+        self.dimensions = dimensions
+        self.metric = Metric.Hamming if storage == Scalar.B1 else Metric(metric)
+        self.storage = Scalar(storage)
+
+    # ---- UsearchIndex trait (usearch.rs:142-160) ----
+    def reserve(self, size: int) -> None:
+        check(self._lib.vsb_reserve(self._h, size))
+
+    def capacity(self) -> int:
+        return int(self._lib.vsb_capacity(self._h))
+
+    def add(self, primary_id: int, vector) -> None:
+        self.add_batch(np.array([primary_id], dtype=np.uint64), np.asarray(vector, dtype=np.float32)[None, :])
+
+    def remove(self, primary_id: int) -> bool:
+        return self.remove_batch(np.array([primary_id], dtype=np.uint64)) != 0
+
+    def search(self, vector, limit: int):
+        """-> list[(primary_id, distance)] ascending; fewer than `limit` when the index is small."""
+        keys, dists, counts = self.search_batch(np.asarray(vector, dtype=np.float32)[None, :], limit)
+        return [(int(keys[0, i]), float(dists[0, i])) for i in range(int(counts[0]))]
+
+    def filtered_search(self, vector, limit: int, predicate):
+        """The reference passes a host closure |PrimaryId| -> bool (usearch.rs:224-248); the device needs a
+        bitmap, so the closure is evaluated once per live row id here (host side) and uploaded."""
+        raise NotImplementedError("use filtered_search_bitmap (the actor mirror builds the bitmap)")
+
+    def filtered_search_bitmap(self, vector, limit: int, allow_bitmap: np.ndarray, bitmap_bits: int):
+        q = np.ascontiguousarray(np.asarray(vector, dtype=np.float32)[None, :])
+        self._check_dim(q)
+        bm = np.ascontiguousarray(allow_bitmap, dtype=np.uint32)
+        keys = np.empty((1, limit), dtype=np.uint64)
+        dists = np.empty((1, limit), dtype=np.float32)
+        counts = np.empty(1, dtype=np.uint32)
+        check(self._lib.vsb_search_filtered(self._h, _ptr(q), 1, limit, _ptr(bm), bitmap_bits, _ptr(keys),
+                                            _ptr(dists), _ptr(counts)))
+        return [(int(keys[0, i]), float(dists[0, i])) for i in range(int(counts[0]))]
+
+    def stop(self) -> None:
+        self.close()
+
+    # ---- batched ABI ----
+    def _check_dim(self, a: np.ndarray) -> None:
+        if a.ndim != 2 or a.shape[1] != self.dimensions:
+            raise native.VsbError(native.VSB_EDIM, f"expected dimension {self.dimensions}, got {a.shape}")
+
+    def size(self) -> int:
+        return int(self._lib.vsb_size(self._h))
+
+    def __len__(self) -> int:
+        return self.size()
+
+    def contains(self, key: int) -> bool:
+        return bool(self._lib.vsb_contains(self._h, key))
+
+    def add_batch(self, keys, rows) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        self._check_dim(rows)
+        if keys.shape[0] != rows.shape[0]:
+            raise native.VsbError(native.VSB_EINVAL, "keys/rows length mismatch")
+        check(self._lib.vsb_add(self._h, _ptr(keys), _ptr(rows), rows.shape[0]))
+
+    def remove_batch(self, keys) -> int:
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        n = C.c_uint64(0)
+        check(self._lib.vsb_remove(self._h, _ptr(keys), keys.shape[0], C.byref(n)))
+        return int(n.value)
+
+    def build(self) -> None:
+        check(self._lib.vsb_build(self._h))
+
+    def export_graph(self):
+        """-> (rows u32 [n_graphed, stride], keys u64 [n_graphed])"""
+        n = C.c_uint64(0)
+        stride = C.c_uint32(0)
+        check(self._lib.vsb_export_graph(self._h, None, None, C.byref(n), C.byref(stride)))
+        rows = np.empty((n.value, stride.value), dtype=np.uint32)
+        keys = np.empty(n.value, dtype=np.uint64)
+        if n.value:
+            check(self._lib.vsb_export_graph(self._h, _ptr(rows), _ptr(keys), C.byref(n), C.byref(stride)))
+        return rows, keys
+
+    def set_search_params(self, expansion_search: int = 0, max_iterations: int = 0, n_seeds: int = 0,
+                          min_graph_size: int = 0) -> None:
+        p = VsbSearchParams(expansion_search, max_iterations, n_seeds, min_graph_size)
+        check(self._lib.vsb_set_search_params(self._h, C.byref(p)))
+
+    def set_instrumented(self, on: bool) -> None:
+        check(self._lib.vsb_set_instrumented(self._h, int(on)))
+
+    def stats(self) -> dict:
+        s = VsbStats()
+        check(self._lib.vsb_get_stats(self._h, C.byref(s)))
+        return {n: int(getattr(s, n)) for n, _ in VsbStats._fields_}
+
+    def search_batch(self, queries, k: int, exact: bool = False, out=None):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        self._check_dim(q)
+        n = q.shape[0]
+        if out is None:
+            keys = np.empty((n, k), dtype=np.uint64)
+            dists = np.empty((n, k), dtype=np.float32)
+            counts = np.empty(n, dtype=np.uint32)
+        else:
+            keys, dists, counts = out
+        fn = self._lib.vsb_search_exact if exact else self._lib.vsb_search
+        check(fn(self._h, _ptr(q), n, k, _ptr(keys), _ptr(dists), _ptr(counts)))
+        return keys, dists, counts
+
+    def search_raw(self, q_ptr: int, n: int, k: int, keys_ptr: int, dists_ptr: int, counts_ptr: int,
+                   exact: bool = False) -> None:
+        """Host-pointer call without NumPy marshalling (bench e2e leg uses pinned torch buffers)."""
+        fn = self._lib.vsb_search_exact if exact else self._lib.vsb_search
+        check(fn(self._h, q_ptr, n, k, keys_ptr, dists_ptr, counts_ptr))
+
+    def search_dev(self, d_queries: int, n: int, k: int, d_keys: int, d_dists: int, d_counts: int, stream: int,
+                   exact: bool = False) -> None:
+        """Device-pointer call (ints = raw CUDA pointers / cudaStream_t), never synchronises."""
+        check(self._lib.vsb_search_dev(self._h, d_queries, n, k, d_keys, d_dists, d_counts or None, stream or None,
+                                       int(exact)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.vsb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def merge_topk_dev(d_keys: int, d_dists: int, parts: int, q: int, k: int, d_out_keys: int, d_out_dists: int,
+                   d_out_counts: int, device: int, stream: int) -> None:
+    check(lib().vsb_merge_topk_dev(d_keys, d_dists, parts, q, k, d_out_keys, d_out_dists, d_out_counts or None,
+                                   device, stream or None))
