@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native index path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm   (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  CPU arm   (USearch-equivalent HNSW restatement)
+
+Workload (config.workload): BASELINE configs[1] — 1M x 768 f32 cosine, embedding-shaped synthetic
+vectors, k = 10, one step = one batch of 10 000 queries through the ANN search path at the smallest
+expansion_search that reaches recall@10 >= 0.95 against exact ground truth.
+  value    queries/s with the query batch already resident in HBM (vsb_search_dev, CUDA events)
+  e2e      the same through the host-pointer C ABI call (vsb_search): pinned H2D of the batch and
+           D2H of keys+distances inside the timed region
+  roofline graph_search_kernel (K4): algorithmic bytes = Q*(E*row_bytes + P*R*4), E/P counted by
+           the instrumented kernel, duration from CUDA events on the launch stream
+Multi-GPU (N > 1): the corpus is split into N row-range shards (strong scaling, fixed global corpus
+and query set); every rank searches every query on its shard; ONE all-gather of the per-shard
+top-k (NCCL) + the K8 merge kernel.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC_NAME = "ann_search_qps_at_recall10_ge_0.95"
+UNIT = "queries/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--batch", type=int, default=10_000)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--storage", default="f32", choices=["f32", "bf16", "f16"])
+    ap.add_argument("--target-recall", type=float, default=0.95)
+    ap.add_argument("--cpu-sample", type=int, default=100_000, help="corpus rows of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-queries", type=int, default=2_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"{a.n}x{a.dim} {a.storage} cosine embedding-shaped synthetic (BASELINE configs[1]), k={a.k}, query batch {a.batch}"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_hnsw_run(a, steps, warmup, full_line):
+    """The CPU arm: USearch-equivalent HNSW (oracle/hnsw_cpu.cpp) on the host cores, bounded sample."""
+    import oracle as O
+    from importlib import import_module
+    ds = import_module("vector_store_b200.host.datasets")
+    threads = os.cpu_count() or 1
+    n = min(a.cpu_sample, a.n)
+    x = ds.embedding_like(n, a.dim, seed=1234)
+    q = ds.embedding_like(a.cpu_queries, a.dim, seed=4321)
+    st = O.BF16 if a.storage == "bf16" else O.F32
+    h = O.HnswCpu(a.dim, O.COS, n, 16, 128, 64, storage=st, threads=threads)
+    t0 = time.perf_counter()
+    h.add(np.arange(n, dtype=np.uint64), x)
+    build_s = time.perf_counter() - t0
+    tk, _, _, _ = O.exact_topk(x, q[:200], a.k, O.COS, st)
+    # smallest ef reaching the target recall (same rule as the GPU arm)
+    ef_used, recall = 64, 0.0
+    for ef in (32, 64, 96, 128, 192, 256, 384, 512):
+        h.set_ef(ef)
+        hk, _ = h.search(q[:200], a.k)
+        recall = O.recall_at_k(hk, tk)
+        ef_used = ef
+        if recall >= a.target_recall:
+            break
+    for _ in range(warmup):
+        h.search(q, a.k)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        h.search(q, a.k)
+    dt = time.perf_counter() - t0
+    qps = steps * len(q) / dt
+    lat = []
+    for i in range(200):
+        t1 = time.perf_counter()
+        h.search_one(q[i], a.k)
+        lat.append(time.perf_counter() - t1)
+    sample = (f"HNSW M=16/ef_add=128 built on the first {n} corpus rows (of {a.n}), {len(q)} queries per step, "
+              f"ef_search={ef_used} (recall@10={recall:.3f} on 200 queries); USearch-equivalent CPU restatement, "
+              f"not USearch 2.22.0")
+    base = {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+            "build_vectors_per_s": n / build_s, "recall_at_10": recall, "ef_search": ef_used,
+            "p50_batch1_ms": float(np.percentile(lat, 50) * 1e3), "p99_batch1_ms": float(np.percentile(lat, 99) * 1e3)}
+    if not full_line:
+        return base
+    return {"metric": METRIC_NAME, "value": qps, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(a), "index": "M=16 ef_add=128", "sample": sample},
+            "cpu_baseline": base,
+            "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        if rank == 0:
+            print(json.dumps(cpu_hnsw_run(a, a.steps, a.warmup, True)), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from importlib import import_module
+
+    import vector_store_b200 as v
+    ds = import_module("vector_store_b200.host.datasets")
+    shard = import_module("vector_store_b200.host.shard")
+    index_mod = import_module("vector_store_b200.host.index")
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: vsb200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    scalar = {"f32": v.Scalar.F32, "bf16": v.Scalar.BF16, "f16": v.Scalar.F16}[a.storage]
+    lo, hi = shard.shard_range(a.n, rank, world)
+    n_local = hi - lo
+
+    # ---- corpus shard: generated and ingested chunk by chunk (host RAM stays bounded) ----
+    idx = v.GpuIndex(a.dim, v.Metric.Cos, scalar, device=local_rank)
+    idx.reserve(n_local)
+    t_gen = 0.0
+    t_add = 0.0
+    CH = 100_000
+    # global row r comes from chunk r // CH of the global stream, so shards of any world size hold the same data
+    for c0 in range((lo // CH) * CH, hi, CH):
+        t0 = time.perf_counter()
+        xc = ds.embedding_like(min(CH, a.n - c0), a.dim, seed=1234 + c0 // CH)
+        s, e = max(lo, c0) - c0, min(hi, c0 + CH) - c0
+        xc = xc[s:e]
+        keys = np.arange(c0 + s, c0 + e, dtype=np.uint64)
+        t_gen += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        idx.add_batch(keys, xc)
+        t_add += time.perf_counter() - t0
+    barrier()
+    t0 = time.perf_counter()
+    idx.build()
+    barrier()
+    t_build = time.perf_counter() - t0
+    build_vps = a.n / (t_add + t_build)  # first H2D to graph ready, whole job
+
+    # ---- query pool: NB distinct batches, pinned on the host and resident on the device ----
+    NB = 4
+    k, B = a.k, a.batch
+    stream = torch.cuda.current_stream().cuda_stream
+    q_host, q_dev = [], []
+    for b in range(NB):
+        qb = torch.from_numpy(ds.embedding_like(B, a.dim, seed=4321 + b)).pin_memory()
+        q_host.append(qb)
+        q_dev.append(qb.to(dev, non_blocking=False))
+    keys_l = torch.empty((B, k), dtype=torch.int64, device=dev)
+    dists_l = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_k = torch.empty((B, k), dtype=torch.int64, device=dev)
+    out_d = torch.empty((B, k), dtype=torch.float32, device=dev)
+    h_keys = torch.empty((B, k), dtype=torch.int64).pin_memory()
+    h_dists = torch.empty((B, k), dtype=torch.float32).pin_memory()
+    h_counts = torch.empty((B,), dtype=torch.int32).pin_memory()
+    gath_k = torch.empty((world, B, k), dtype=torch.int64, device=dev)
+    gath_d = torch.empty((world, B, k), dtype=torch.float32, device=dev)
+
+    def search_step(qd, exact=False):
+        """device-resident step: local shard search [+ all-gather + K8 merge]; result in out_k/out_d"""
+        if world == 1:
+            idx.search_dev(qd.data_ptr(), B, k, out_k.data_ptr(), out_d.data_ptr(), 0, stream, exact)
+            return
+        idx.search_dev(qd.data_ptr(), B, k, keys_l.data_ptr(), dists_l.data_ptr(), 0, stream, exact)
+        dist.all_gather_into_tensor(gath_k, keys_l)
+        dist.all_gather_into_tensor(gath_d, dists_l)
+        index_mod.merge_topk_dev(gath_k.data_ptr(), gath_d.data_ptr(), world, B, k, out_k.data_ptr(), out_d.data_ptr(),
+                                 0, local_rank, stream)
+
+    # ---- exact ground truth (GPU brute force, bit-exact vs the oracle by tests/test_gpu_parity.py) ----
+    gt = []
+    for b in range(NB):
+        search_step(q_dev[b], exact=True)
+        torch.cuda.synchronize()
+        gt.append(out_k.cpu().numpy().copy())
+
+    def recall_of(b):
+        got = out_k.cpu().numpy()
+        hits = 0
+        for i in range(0, B, max(1, B // 2000)):  # 2000-query sample per batch
+            hits += len(np.intersect1d(got[i], gt[b][i]))
+        return hits / (len(range(0, B, max(1, B // 2000))) * k)
+
+    # ---- operating point: smallest expansion_search with recall@10 >= target ----
+    sweep = []
+    ef_used, recall = None, 0.0
+    for ef in (32, 64, 96, 128, 192, 256, 384, 512):
+        idx.set_search_params(expansion_search=ef)
+        search_step(q_dev[0])
+        torch.cuda.synchronize()
+        r = recall_of(0)
+        sweep.append({"ef": ef, "recall_at_10": round(r, 4)})
+        ef_used, recall = ef, r
+        if r >= a.target_recall:
+            break
+
+    # ---- instrumented pass: E (distance evaluations) and P (parent expansions) per query ----
+    idx.set_instrumented(True)
+    idx.search_dev(q_dev[1].data_ptr(), B, k, keys_l.data_ptr(), dists_l.data_ptr(), 0, stream, False)
+    torch.cuda.synchronize()
+    st = idx.stats()
+    idx.set_instrumented(False)
+    E = st["distance_evals"] / max(st["queries"], 1)
+    P = st["parent_expansions"] / max(st["queries"], 1)
+    bytes_per_query = E * (st["row_bytes"] + 4) + P * st["graph_degree"] * 4  # +4: the row's norm (cosine)
+
+    # ---- timed region 1: inputs resident in HBM ----
+    for i in range(a.warmup):
+        search_step(q_dev[i % NB])
+    barrier()
+    launches0 = idx.stats()["kernel_launches"]
+    idx.set_kernel_timing(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(a.steps):
+        search_step(q_dev[i % NB])
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    st = idx.stats()
+    idx.set_kernel_timing(False)
+    launches = st["kernel_launches"] - launches0 + (a.steps if world > 1 else 0)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = a.steps * B / (ms * 1e-3)
+    recall_timed = recall_of((a.steps - 1) % NB)
+
+    k4_ms = st["graph_search_ns"] / 1e6 / max(st["graph_search_launches"], 1)
+    peak, peak_src = load_peaks()
+    achieved = B * bytes_per_query / (k4_ms * 1e-3) / 1e9 if k4_ms > 0 else 0.0
+    phase_ms = {p: st[p + "_ns"] / 1e6 / a.steps for p in ("convert", "seed", "graph_search", "exact", "merge")}
+
+    # ---- timed region 2: end to end through the host-pointer C ABI ----
+    def e2e_step(b):
+        if world == 1:
+            idx.search_raw(q_host[b].data_ptr(), B, k, h_keys.data_ptr(), h_dists.data_ptr(), h_counts.data_ptr())
+            return
+        q_dev[b].copy_(q_host[b], non_blocking=True)
+        search_step(q_dev[b])
+        h_keys.copy_(out_k, non_blocking=True)
+        h_dists.copy_(out_d, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for i in range(a.warmup):
+        e2e_step(i % NB)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        e2e_step(i % NB)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e = {"value": a.steps * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * a.dim * 4,
+           "d2h_bytes_per_step": B * k * 12 + (B * 4 if world == 1 else 0), "ms_per_step": e2e_s / a.steps * 1e3}
+
+    # ---- p99 batch-1 latency through the host ABI (rank 0 shard only when sharded) ----
+    lat = []
+    q1 = q_host[2]
+    if world == 1:
+        for i in range(320):
+            t1 = time.perf_counter()
+            idx.search_raw(q1[i:i + 1].data_ptr(), 1, k, h_keys.data_ptr(), h_dists.data_ptr(), h_counts.data_ptr())
+            lat.append(time.perf_counter() - t1)
+        lat = lat[20:]
+
+    line = {
+        "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": a.storage, "data": "synthetic",
+        "config": {"workload": workload_name(a), "index": "M=16 (degree 32) ef_add=128",
+                   "expansion_search": ef_used, "recall_at_10": round(recall_timed, 4), "ef_sweep": sweep,
+                   "parallelism": f"corpus sharded over {world} GPU(s), all-gather top-k merge" if world > 1 else "1 GPU",
+                   "l2_policy": f"corpus {a.n * st['row_bytes'] / 1e9:.2f} GB >> 126 MB L2; {NB} query batches rotate"},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "graph_search_kernel (K4)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel_ms_per_launch": k4_ms, "distance_evals_per_query": E, "parent_expansions_per_query": P,
+                     "bytes_per_query": bytes_per_query, "phase_ms_per_step": phase_ms},
+        "build_vectors_per_s": build_vps, "build_s": {"add_h2d_convert": t_add, "graph": t_build, "generate": t_gen},
+        "hbm_bytes": st["hbm_bytes"],
+    }
+    if lat:
+        line["p50_batch1_ms"] = float(np.percentile(lat, 50) * 1e3)
+        line["p99_batch1_ms"] = float(np.percentile(lat, 99) * 1e3)
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_hnsw_run(a, 3, 1, False)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    idx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

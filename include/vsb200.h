@@ -88,6 +88,10 @@ typedef struct {
     uint64_t row_bytes;            /* bytes per stored vector (16-byte padded) */
     uint64_t n_seed_rows;          /* rows in the entry-point sample */
     uint64_t hbm_bytes;            /* device bytes held by this handle */
+    /* CUDA-event timing of the search phases on their launch stream (vsb_set_kernel_timing):
+     * summed nanoseconds and launch counts since timing was switched on. */
+    uint64_t convert_ns, seed_ns, graph_search_ns, exact_ns, merge_ns;
+    uint64_t convert_launches, seed_launches, graph_search_launches, exact_launches, merge_launches;
 } vsb_stats;
 
 /* usearch.rs:172  usearch::Index::new(&options) */
@@ -128,6 +132,9 @@ vsb_status vsb_get_stats(vsb_index* index, vsb_stats* out);
 /* Re-runs nothing: switches the graph-search kernel to its counting build for the
  * next searches (identical algorithm; counters off by default for timing runs). */
 vsb_status vsb_set_instrumented(vsb_index* index, int on);
+/* Brackets each search phase with cudaEventRecord on the launch stream and accumulates the
+ * elapsed times into vsb_stats (resolved in vsb_get_stats).  Switching on resets the sums. */
+vsb_status vsb_set_kernel_timing(vsb_index* index, int on);
 
 /* usearch.rs:203-222  search(&[f32], k) -> Matches{keys, distances}; batched over q queries. */
 vsb_status vsb_search(vsb_index* index, const float* queries, uint64_t q, uint32_t k,

@@ -26,7 +26,7 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
     a.max_iters = p.max_iters ? p.max_iters : 2 * a.itopk;
     a.k = p.k;
     // visited hash: room for ~half of the nodes one query can touch before a reset
-    uint32_t want = 8 * a.itopk;
+    uint32_t want = 32 * a.itopk;
     uint32_t bits = 10;
     while ((1u << bits) < want && bits < 13) ++bits;
     a.hash_bits = bits;

@@ -118,6 +118,39 @@ struct vsb_index {
 
     uint64_t last_evals = 0, last_parents = 0, last_queries = 0;
 
+    // optional CUDA-event timing of the search phases
+    enum Phase { PH_CONVERT = 0, PH_SEED, PH_GRAPH, PH_EXACT, PH_MERGE, PH_COUNT };
+    bool timing = false;
+    struct Timed { cudaEvent_t a, b; int phase; };
+    std::vector<Timed> timed;
+    uint64_t phase_ns[PH_COUNT] = {0, 0, 0, 0, 0};
+    uint64_t phase_launches[PH_COUNT] = {0, 0, 0, 0, 0};
+    void t_begin(int phase, cudaStream_t s) {
+        if (!timing) return;
+        Timed t;
+        t.phase = phase;
+        cudaEventCreate(&t.a);
+        cudaEventCreate(&t.b);
+        cudaEventRecord(t.a, s);
+        timed.push_back(t);
+    }
+    void t_end(cudaStream_t s) {
+        if (!timing) return;
+        cudaEventRecord(timed.back().b, s);
+    }
+    void t_resolve() {
+        for (auto& t : timed) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+                phase_ns[t.phase] += (uint64_t)((double)ms * 1e6);
+                phase_launches[t.phase] += 1;
+            }
+            cudaEventDestroy(t.a);
+            cudaEventDestroy(t.b);
+        }
+        timed.clear();
+    }
+
     size_t hbm_bytes() const {
         const DevBuf* all[] = {&rows, &sq, &nrm, &keys, &deny, &graph, &seed_rows, &seed_sq, &seed_nrm, &seed_slots,
                                &q_in, &q_rows, &q_sq, &q_nrm, &part, &seed_part, &tmp_keys, &tmp_dists, &counters,
@@ -399,8 +432,10 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
         CU(q_rows.ensure((size_t)nb * row_bytes));
         CU(q_sq.ensure((size_t)nb * 4));
         CU(q_nrm.ensure((size_t)nb * 4));
+        t_begin(PH_CONVERT, s);
         vsb::launch_convert_rows(storage, d_q + q0 * dim, nb, dim, q_rows.as<uint8_t>(), row_bytes, q_sq.as<float>(),
                                  q_nrm.as<float>(), s);
+        t_end(s);
         CU(cudaGetLastError());
         vsb::RowsView qv;
         qv.rows = q_rows.as<uint8_t>();
@@ -445,7 +480,9 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
             sp.part = seed_part.as<uint64_t>();
             // identity "keys" so that equal distances fall back to the seed index
             sp.keys = nullptr;
+            t_begin(PH_SEED, s);
             vsb::launch_exact_candidates(sp, s);
+            t_end(s);
             CU(cudaGetLastError());
             vsb::SearchParams gp;
             gp.storage = storage;
@@ -473,7 +510,9 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
                 CU(cudaMemsetAsync(counters.p, 0, 16, s));
                 gp.counters = counters.as<unsigned long long>();
             }
+            t_begin(PH_GRAPH, s);
             vsb::launch_graph_search(gp, s);
+            t_end(s);
             CU(cudaGetLastError());
             if (instrumented) {
                 unsigned long long h[2];
@@ -485,11 +524,16 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
             }
         }
         if (have_tail) {
-            ST(exact_block(qv, x, tail_lo, tail_hi, deny_bm, keys.as<uint64_t>(), d_allow, allow_bits, k, t_keys,
-                           t_dists, use_graph ? nullptr : o_counts, nullptr, -1, s));
+            t_begin(PH_EXACT, s);
+            vsb_status est = exact_block(qv, x, tail_lo, tail_hi, deny_bm, keys.as<uint64_t>(), d_allow, allow_bits, k,
+                                         t_keys, t_dists, use_graph ? nullptr : o_counts, nullptr, -1, s);
+            t_end(s);
+            ST(est);
         }
         if (use_graph && have_tail) {
+            t_begin(PH_MERGE, s);
             vsb::launch_merge_topk(g_keys, g_dists, 2, nb, k, o_keys, o_dists, o_counts, s);
+            t_end(s);
             CU(cudaGetLastError());
         }
     }
@@ -581,6 +625,7 @@ void vsb_destroy(vsb_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     cudaDeviceSynchronize();
+    ix->t_resolve();
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
@@ -655,6 +700,18 @@ vsb_status vsb_set_instrumented(vsb_index* ix, int on) {
     return VSB_OK;
 }
 
+vsb_status vsb_set_kernel_timing(vsb_index* ix, int on) {
+    if (!ix) return fail(VSB_EINVAL, "null index");
+    std::lock_guard<std::mutex> g(ix->mu);
+    cudaSetDevice(ix->device);
+    ix->t_resolve();
+    ix->timing = on != 0;
+    if (on) {
+        for (int i = 0; i < vsb_index::PH_COUNT; ++i) ix->phase_ns[i] = ix->phase_launches[i] = 0;
+    }
+    return VSB_OK;
+}
+
 vsb_status vsb_get_stats(vsb_index* ix, vsb_stats* out) {
     if (!ix || !out) return fail(VSB_EINVAL, "null argument");
     std::lock_guard<std::mutex> g(ix->mu);
@@ -668,6 +725,18 @@ vsb_status vsb_get_stats(vsb_index* ix, vsb_stats* out) {
     out->row_bytes = ix->row_bytes;
     out->n_seed_rows = ix->n_seed_rows;
     out->hbm_bytes = ix->hbm_bytes();
+    cudaSetDevice(ix->device);
+    ix->t_resolve();
+    out->convert_ns = ix->phase_ns[vsb_index::PH_CONVERT];
+    out->seed_ns = ix->phase_ns[vsb_index::PH_SEED];
+    out->graph_search_ns = ix->phase_ns[vsb_index::PH_GRAPH];
+    out->exact_ns = ix->phase_ns[vsb_index::PH_EXACT];
+    out->merge_ns = ix->phase_ns[vsb_index::PH_MERGE];
+    out->convert_launches = ix->phase_launches[vsb_index::PH_CONVERT];
+    out->seed_launches = ix->phase_launches[vsb_index::PH_SEED];
+    out->graph_search_launches = ix->phase_launches[vsb_index::PH_GRAPH];
+    out->exact_launches = ix->phase_launches[vsb_index::PH_EXACT];
+    out->merge_launches = ix->phase_launches[vsb_index::PH_MERGE];
     return VSB_OK;
 }
 

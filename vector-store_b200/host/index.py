@@ -136,6 +136,9 @@ class GpuIndex:
     def set_instrumented(self, on: bool) -> None:
         check(self._lib.vsb_set_instrumented(self._h, int(on)))
 
+    def set_kernel_timing(self, on: bool) -> None:
+        check(self._lib.vsb_set_kernel_timing(self._h, int(on)))
+
     def stats(self) -> dict:
         s = VsbStats()
         check(self._lib.vsb_get_stats(self._h, C.byref(s)))

@@ -31,7 +31,9 @@ class VsbSearchParams(C.Structure):
 class VsbStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("kernel_launches", "distance_evals", "parent_expansions", "queries",
                                           "n_slots", "n_graphed", "graph_degree", "row_bytes", "n_seed_rows",
-                                          "hbm_bytes")]
+                                          "hbm_bytes", "convert_ns", "seed_ns", "graph_search_ns", "exact_ns",
+                                          "merge_ns", "convert_launches", "seed_launches", "graph_search_launches",
+                                          "exact_launches", "merge_launches")]
 
 
 # every symbol include/vsb200.h declares: (name, restype, argtypes)
@@ -50,6 +52,7 @@ SYMBOLS = [
     ("vsb_set_search_params", C.c_int, [_P, C.POINTER(VsbSearchParams)]),
     ("vsb_get_stats", C.c_int, [_P, C.POINTER(VsbStats)]),
     ("vsb_set_instrumented", C.c_int, [_P, C.c_int]),
+    ("vsb_set_kernel_timing", C.c_int, [_P, C.c_int]),
     ("vsb_search", C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P, _P, _P]),
     ("vsb_search_exact", C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P, _P, _P]),
     ("vsb_search_filtered", C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P, C.c_uint64, _P, _P, _P]),
