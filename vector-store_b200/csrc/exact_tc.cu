@@ -1,0 +1,449 @@
+// exact_tc.cu — K1 on the 5th-generation tensor cores: Q x N distance tiles with tcgen05.mma,
+// operands staged by TMA into 128B-swizzled shared memory, accumulators in TMEM, and the top-k'
+// selection (K2) fused into the TMEM epilogue so the Q x N matrix never exists.
+//
+// Used for the dense parts of the path: the seed layer of every ANN search,
+// exact search on 16-bit storage, and the all-pairs kNN lists of the bulk graph build — the work
+// `usearch::Index::add` / `search` spend in SimSIMD distance loops in the reference
+// (vs_index/usearch.rs:191-222).  Output format is identical to exact.cu's K1 (per-split sorted
+// candidate lists), so K3 (exact_rerank_kernel) finishes both the same way.
+//
+// CTA = 192 threads, one CTA per SM (TMEM 512 columns, ~213 KB smem):
+//   warp 0      TMA producer: A = 128 queries x 128 B of K, B = 256 corpus rows x 128 B of K,
+//               3-stage mbarrier ring (full/empty)
+//   warp 1      tcgen05.mma issuer (one elected lane): D[128 x 256] fp32 in TMEM, double buffered
+//               (2 x 256 columns) so the epilogue of tile t overlaps the MMAs of tile t+1
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time; thread = one query row;
+//               distance from the dot product and per-column norms; compare with the row's
+//               current k'-th best (register); survivors go to a per-row smem buffer that is
+//               sorted with the shuffle bitonic network and folded into the row's list.
+// kind::f16 (bf16 / f16 storage, exact products) or kind::tf32 (f32 storage, candidate grade).
+#include <cuda.h>
+
+#include "kernels.h"
+#include "select.cuh"
+
+namespace vsb {
+
+namespace {
+
+constexpr int TC_M = 128;
+constexpr int TC_N = 256;
+constexpr int TC_KBYTES = 128;
+constexpr int TC_STAGES = 3;
+constexpr int TC_BUFCAP = 64;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TC_A_BYTES = TC_M * TC_KBYTES;   // 16 KB
+constexpr uint32_t TC_B_BYTES = TC_N * TC_KBYTES;   // 32 KB
+constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr uint32_t TC_OFF_BUF = TC_STAGES * TC_STAGE_BYTES;
+constexpr uint32_t TC_OFF_COLP = TC_OFF_BUF + TC_M * TC_BUFCAP * 8;
+constexpr uint32_t TC_OFF_BAR = TC_OFF_COLP + 2 * TC_N * 4;
+constexpr uint32_t TC_SMEM_BYTES = TC_OFF_BAR + 128 + 1024;  // + alignment slack
+
+enum { KIND_BF16 = 0, KIND_F16 = 1, KIND_TF32 = 2 };
+
+struct TcArgs {
+    const float* q_sq;
+    const float* q_nrm;
+    uint32_t nq;
+    const float* x_sq;
+    const float* x_nrm;
+    uint32_t x_lo, x_hi, row_bytes;
+    const uint32_t* deny;
+    const uint64_t* keys;
+    const uint32_t* allow;
+    uint64_t allow_bits;
+    uint32_t kp, n_splits, rows_per_split;
+    uint64_t* part;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if constexpr (KIND == KIND_TF32) {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address
+    d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+
+template <int KIND, int METRIC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    exact_candidates_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
+                               TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* buf = reinterpret_cast<uint64_t*>(smem + TC_OFF_BUF);
+    float* colp = reinterpret_cast<float*>(smem + TC_OFF_COLP);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
+    uint64_t* full = bars;                    // [TC_STAGES]
+    uint64_t* empty = bars + TC_STAGES;       // [TC_STAGES]
+    uint64_t* tmem_full = bars + 2 * TC_STAGES;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;         // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = __shfl_sync(kFullMask, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t q0 = blockIdx.x * TC_M;
+    const uint32_t split = blockIdx.y;
+    const uint32_t r_lo = a.x_lo + split * a.rows_per_split;
+    const uint32_t r_hi = min(a.x_hi, r_lo + a.rows_per_split);
+    const uint32_t n_tiles = r_hi > r_lo ? (r_hi - r_lo + TC_N - 1) / TC_N : 0;
+    const uint32_t n_slabs = (a.row_bytes + TC_KBYTES - 1) / TC_KBYTES;
+    constexpr int ELEMS_PER_SLAB = KIND == KIND_TF32 ? 32 : 64;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                     "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = 0; t < n_tiles; ++t) {
+                const int n0 = (int)(r_lo + t * TC_N);
+                for (uint32_t slab = 0; slab < n_slabs; ++slab) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * TC_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
+                    tma_load_2d(sa, &tmap_q, &full[stage], (int)(slab * ELEMS_PER_SLAB), (int)q0);
+                    tma_load_2d(sa + TC_A_BYTES, &tmap_x, &full[stage], (int)(slab * ELEMS_PER_SLAB), n0);
+                    if (++stage == TC_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t fmt = KIND == KIND_BF16 ? 1u : (KIND == KIND_F16 ? 0u : 2u);
+            constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_N >> 3) << 17) |
+                                       ((uint32_t)(TC_M >> 4) << 24);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = 0; t < n_tiles; ++t) {
+                const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * TC_N;
+                for (uint32_t slab = 0; slab < n_slabs; ++slab) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
+                    const uint64_t adesc = make_smem_desc(sa);
+                    const uint64_t bdesc = make_smem_desc(sa + TC_A_BYTES);
+#pragma unroll
+                    for (uint32_t k = 0; k < TC_KBYTES / 32; ++k) {
+                        // +32 bytes of K inside the swizzle atom = +2 in the (addr >> 4) field
+                        tc_mma<KIND>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (slab | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(&empty[stage]);
+                    if (++stage == TC_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(&tmem_full[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue: one thread per query row =====
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may read
+        const int row = quarter * 32 + lane;         // row inside the CTA tile
+        const int etid = (warp - 2) * 32 + lane;     // 0..127 among epilogue threads
+        const uint32_t q = q0 + row;
+        const bool q_valid = q < a.nq;
+        const LessByKey less{a.keys};
+        uint64_t* my_buf = buf + (size_t)row * TC_BUFCAP;
+        float qsq = 0.f, inv_qn = 0.f;
+        if (q_valid) {
+            qsq = a.q_sq[q];
+            const float qn = a.q_nrm[q];
+            inv_qn = qn > 0.f ? 1.0f / qn : 0.f;
+        }
+        // this warp's 32 lists live in global memory (L2 resident); initialise them
+        for (int r = 0; r < 32; ++r) {
+            const uint32_t qq = q0 + quarter * 32 + r;
+            if (qq >= a.nq) break;
+            uint64_t* list = a.part + ((size_t)qq * a.n_splits + split) * a.kp;
+            for (uint32_t i = lane; i < a.kp; i += 32) list[i] = kInvalidPacked;
+        }
+        __syncwarp();
+        float thr = q_valid ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
+        int cnt = 0;
+
+        auto flush = [&](uint32_t need_mask) {
+            __syncwarp();  // make every lane's buffered candidates visible to the warp
+            while (need_mask) {
+                const int r = __ffs(need_mask) - 1;
+                need_mask &= need_mask - 1;
+                const int c = __shfl_sync(kFullMask, cnt, r);
+                const uint32_t qq = q0 + quarter * 32 + r;
+                uint64_t* list = a.part + ((size_t)qq * a.n_splits + split) * a.kp;
+                const uint64_t* rb = buf + (size_t)(quarter * 32 + r) * TC_BUFCAP;
+                for (int base = 0; base < c; base += 32) {
+                    uint64_t v = (base + lane < c) ? rb[base + lane] : kInvalidPacked;
+                    v = warp_sort32(v, lane, less);
+                    warp_list_merge(list, (int)a.kp, v, lane, less);
+                }
+                const uint64_t worst = list[a.kp - 1];
+                if (lane == r) {
+                    cnt = 0;
+                    if (worst != kInvalidPacked) thr = ord_to_f32(packed_hi(worst));
+                }
+                __syncwarp();
+            }
+        };
+
+        for (uint32_t t = 0; t < n_tiles; ++t) {
+            const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
+            const uint32_t n0 = r_lo + t * TC_N;
+            // per-column parameter of this tile (NaN marks columns outside the split)
+            float* cp = colp + acc * TC_N;
+            for (int c = etid; c < TC_N; c += 128) {
+                const uint32_t n = n0 + c;
+                float p = __int_as_float(0x7FC00000);
+                if (n < r_hi) {
+                    if constexpr (METRIC == VSB_METRIC_L2SQ) p = a.x_sq[n];
+                    else if constexpr (METRIC == VSB_METRIC_COS) {
+                        const float xn = a.x_nrm[n];
+                        p = xn > 0.f ? 1.0f / xn : 0.f;
+                    } else p = 1.0f;
+                }
+                cp[c] = p;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_N;
+#pragma unroll 1
+            for (int ch = 0; ch < TC_N / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(taddr + ch * 32, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float dot = __uint_as_float(v[j]);
+                    const float p = cp[ch * 32 + j];
+                    float d;
+                    if constexpr (METRIC == VSB_METRIC_L2SQ) d = fmaf(dot, -2.0f, p) + qsq;
+                    else if constexpr (METRIC == VSB_METRIC_COS) d = fmaf(dot * p, -inv_qn, 1.0f);
+                    else d = fmaf(dot, -1.0f, p);
+                    if (d <= thr) {
+                        const uint32_t n = n0 + ch * 32 + j;
+                        bool ok = true;
+                        if (a.deny != nullptr && bit_test(a.deny, n)) ok = false;
+                        if (ok && a.allow != nullptr) {
+                            const uint64_t rid = a.keys[n] & kRowMask48;
+                            ok = rid < a.allow_bits && bit_test(a.allow, (uint32_t)rid);
+                        }
+                        if (ok) {
+                            if constexpr (METRIC == VSB_METRIC_L2SQ) d = fmaxf(d, 0.0f);
+                            if constexpr (METRIC == VSB_METRIC_COS) d = fminf(fmaxf(d, 0.0f), 2.0f);
+                            my_buf[cnt++] = pack_ds(d, n);
+                        }
+                    }
+                }
+                const uint32_t need = __ballot_sync(kFullMask, cnt > TC_BUFCAP - 32);
+                if (need) flush(need);
+            }
+            // accumulator drained: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        const uint32_t rest = __ballot_sync(kFullMask, cnt > 0);
+        if (rest) flush(rest);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+bool make_map(CUtensorMap* map, int kind, const void* base, uint32_t rows, uint32_t row_bytes, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr || rows == 0) return false;
+    const uint32_t esz = kind == KIND_TF32 ? 4 : 2;
+    const CUtensorMapDataType dt = kind == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                   : kind == KIND_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                       : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    cuuint64_t dims[2] = {row_bytes / esz, rows};
+    cuuint64_t strides[1] = {row_bytes};
+    cuuint32_t box[2] = {TC_KBYTES / esz, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int KIND, int METRIC>
+void launch_tc_inst(const CUtensorMap& mq, const CUtensorMap& mx, const TcArgs& a, dim3 grid, cudaStream_t stream) {
+    cudaFuncSetAttribute(exact_candidates_tc_kernel<KIND, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)TC_SMEM_BYTES);
+    exact_candidates_tc_kernel<KIND, METRIC><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mq, mx, a);
+}
+
+template <int KIND>
+void launch_tc_kind(int metric, const CUtensorMap& mq, const CUtensorMap& mx, const TcArgs& a, dim3 grid,
+                    cudaStream_t stream) {
+    switch (metric) {
+        case VSB_METRIC_L2SQ: launch_tc_inst<KIND, VSB_METRIC_L2SQ>(mq, mx, a, grid, stream); break;
+        case VSB_METRIC_COS: launch_tc_inst<KIND, VSB_METRIC_COS>(mq, mx, a, grid, stream); break;
+        default: launch_tc_inst<KIND, VSB_METRIC_IP>(mq, mx, a, grid, stream); break;
+    }
+}
+
+}  // namespace
+
+bool exact_tc_supported(int storage, int metric) {
+    if (metric == VSB_METRIC_HAMMING) return false;
+    return storage == VSB_ST_F32 || storage == VSB_ST_BF16 || storage == VSB_ST_F16;
+}
+
+uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count) {
+    const uint32_t q_tiles = (nq + TC_M - 1) / TC_M;
+    uint32_t want = ((uint32_t)sm_count + q_tiles - 1) / q_tiles;   // >= one CTA per SM
+    const uint32_t max_by_rows = (n_rows + 2 * TC_N - 1) / (2 * TC_N);  // >= 2 tiles per split
+    uint32_t s = want < max_by_rows ? want : max_by_rows;
+    if (s < 1) s = 1;
+    if (s > 1024) s = 1024;
+    return s;
+}
+
+// Same contract as launch_exact_candidates (exact.cu); returns false if the TMA descriptors could
+// not be encoded (caller falls back to the SIMT K1, which is still the CUDA path).
+bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream) {
+    if (p.q.n == 0 || p.x_hi <= p.x_lo) return true;
+    const int kind = p.storage == VSB_ST_F32 ? KIND_TF32 : (p.storage == VSB_ST_BF16 ? KIND_BF16 : KIND_F16);
+    CUtensorMap mq, mx;
+    if (!make_map(&mq, kind, p.q.rows, p.q.n, p.q.row_bytes, TC_M)) return false;
+    if (!make_map(&mx, kind, p.x.rows, p.x_hi, p.x.row_bytes, TC_N)) return false;
+    TcArgs a;
+    a.q_sq = p.q.sq; a.q_nrm = p.q.nrm; a.nq = p.q.n;
+    a.x_sq = p.x.sq; a.x_nrm = p.x.nrm; a.x_lo = p.x_lo; a.x_hi = p.x_hi; a.row_bytes = p.x.row_bytes;
+    a.deny = p.deny; a.keys = p.keys; a.allow = p.allow; a.allow_bits = p.allow_bits;
+    a.kp = p.kp; a.n_splits = p.n_splits;
+    const uint32_t rows = p.x_hi - p.x_lo;
+    const uint32_t rps = (rows + p.n_splits - 1) / p.n_splits;
+    a.rows_per_split = ((rps + TC_N - 1) / TC_N) * TC_N;
+    a.part = p.part;
+    dim3 grid((p.q.n + TC_M - 1) / TC_M, p.n_splits);
+    switch (kind) {
+        case KIND_BF16: launch_tc_kind<KIND_BF16>(p.metric, mq, mx, a, grid, stream); break;
+        case KIND_F16: launch_tc_kind<KIND_F16>(p.metric, mq, mx, a, grid, stream); break;
+        default: launch_tc_kind<KIND_TF32>(p.metric, mq, mx, a, grid, stream); break;
+    }
+    g_kernel_launches += 1;
+    return true;
+}
+
+}  // namespace vsb

@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -183,7 +184,10 @@ struct vsb_index {
     vsb_status exact_block(const vsb::RowsView& q, const vsb::RowsView& x, uint32_t x_lo, uint32_t x_hi,
                            const uint32_t* deny_bm, const uint64_t* key_arr, const uint32_t* allow_bm,
                            uint64_t allow_bits, uint32_t k, uint64_t* out_keys, float* out_dists,
-                           uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t s);
+                           uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t s,
+                           bool approx_ok);
+    bool tc_enabled = true;       // tcgen05 path for the dense distance tiles (VSB_DISABLE_TC=1 turns it off)
+    uint32_t tc_min_rows = 8192;  // below this the SIMT K1 is used (launch + pipeline fill dominate)
     vsb_status search_dev(const float* d_q, uint64_t nq, uint32_t k, uint64_t* d_keys, float* d_dists,
                           uint32_t* d_counts, cudaStream_t s, bool exact, const uint32_t* d_allow,
                           uint64_t allow_bits);
@@ -308,7 +312,8 @@ vsb_status vsb_index::remove(const uint64_t* k, uint64_t n, uint64_t* removed) {
 vsb_status vsb_index::exact_block(const vsb::RowsView& q, const vsb::RowsView& x, uint32_t x_lo, uint32_t x_hi,
                                   const uint32_t* deny_bm, const uint64_t* key_arr, const uint32_t* allow_bm,
                                   uint64_t allow_bits, uint32_t k, uint64_t* out_keys, float* out_dists,
-                                  uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t s) {
+                                  uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t s,
+                                  bool approx_ok) {
     vsb::ExactParams p;
     p.storage = storage;
     p.metric = metric;
@@ -323,10 +328,16 @@ vsb_status vsb_index::exact_block(const vsb::RowsView& q, const vsb::RowsView& x
     const uint32_t extra = std::max<uint32_t>(16, k / 4) + (self_base >= 0 ? 1 : 0);
     p.kp = round_up(k + extra, 32);
     if (p.kp > 256) return fail(VSB_EINVAL, "k=%u too large for the exact path (max 200)", k);
-    p.n_splits = vsb::exact_pick_splits(q.n, x_hi - x_lo, sm_count);
+    // tensor-core tiles: 16-bit storages multiply exactly (only the fp32 accumulation order differs, covered
+    // by the over-fetch); f32 storage runs as TF32 and is used only where candidate-grade lists suffice
+    bool tc = tc_enabled && vsb::exact_tc_supported(storage, metric) && (x_hi - x_lo) >= tc_min_rows &&
+              (approx_ok || storage != VSB_F32);
+    p.n_splits = tc ? vsb::exact_tc_pick_splits(q.n, x_hi - x_lo, sm_count)
+                    : vsb::exact_pick_splits(q.n, x_hi - x_lo, sm_count);
     CU(part.ensure(vsb::exact_part_elems(q.n, p.n_splits, p.kp) * 8));
     p.part = part.as<uint64_t>();
-    vsb::launch_exact_candidates(p, s);
+    if (tc) tc = vsb::launch_exact_candidates_tc(p, s);
+    if (!tc) vsb::launch_exact_candidates(p, s);
     CU(cudaGetLastError());
     vsb::launch_exact_rerank(p, k, out_keys, out_dists, out_counts, out_packed, self_base, s);
     CU(cudaGetLastError());
@@ -357,7 +368,7 @@ vsb_status vsb_index::build() {
         q.nrm = x.nrm + b0;
         q.row_bytes = row_bytes;
         ST(exact_block(q, x, 0, n, deny_bm, keys.as<uint64_t>(), nullptr, 0, kin, nullptr, nullptr, nullptr,
-                       knn.as<uint64_t>() + (size_t)b0 * kin, (int64_t)b0, stream));
+                       knn.as<uint64_t>() + (size_t)b0 * kin, (int64_t)b0, stream, true));
     }
     CU(fwd.ensure((size_t)n * R * 4));
     CU(rev.ensure((size_t)n * R * 4));
@@ -475,13 +486,14 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
             sp.x_hi = n_seed_rows;
             sp.keys = nullptr;  // ties by seed index: LessByKey is never asked (see below)
             sp.kp = 32;
-            sp.n_splits = vsb::exact_pick_splits(nb, n_seed_rows, sm_count);
+            bool seed_tc = tc_enabled && vsb::exact_tc_supported(storage, metric) && nb >= 16;
+            sp.n_splits = seed_tc ? vsb::exact_tc_pick_splits(nb, n_seed_rows, sm_count)
+                                  : vsb::exact_pick_splits(nb, n_seed_rows, sm_count);
             CU(seed_part.ensure(vsb::exact_part_elems(nb, sp.n_splits, 32) * 8));
             sp.part = seed_part.as<uint64_t>();
-            // identity "keys" so that equal distances fall back to the seed index
-            sp.keys = nullptr;
             t_begin(PH_SEED, s);
-            vsb::launch_exact_candidates(sp, s);
+            if (seed_tc) seed_tc = vsb::launch_exact_candidates_tc(sp, s);
+            if (!seed_tc) vsb::launch_exact_candidates(sp, s);
             t_end(s);
             CU(cudaGetLastError());
             vsb::SearchParams gp;
@@ -526,7 +538,7 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
         if (have_tail) {
             t_begin(PH_EXACT, s);
             vsb_status est = exact_block(qv, x, tail_lo, tail_hi, deny_bm, keys.as<uint64_t>(), d_allow, allow_bits, k,
-                                         t_keys, t_dists, use_graph ? nullptr : o_counts, nullptr, -1, s);
+                                         t_keys, t_dists, use_graph ? nullptr : o_counts, nullptr, -1, s, false);
             t_end(s);
             ST(est);
         }
@@ -610,6 +622,8 @@ vsb_status vsb_create(const vsb_options* o, vsb_index** out) {
     ix->graph_stride = round_up(ix->degree, 32);
     ix->k_init = std::min<uint32_t>(std::max<uint32_t>(ef_add / 2, ix->degree), 128);
     ix->itopk = std::min<uint32_t>(round_up(ef_search, 32), 512);
+    if (const char* e = getenv("VSB_DISABLE_TC")) ix->tc_enabled = !(e[0] == '1');
+    if (const char* e = getenv("VSB_TC_MIN_ROWS")) ix->tc_min_rows = (uint32_t)strtoul(e, nullptr, 10);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);

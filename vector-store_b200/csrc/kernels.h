@@ -50,6 +50,11 @@ void launch_exact_candidates(const ExactParams& p, cudaStream_t stream);
 void launch_exact_rerank(const ExactParams& p, uint32_t k, uint64_t* out_keys, float* out_dists,
                          uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t stream);
 
+// K1 on tcgen05 tensor cores (exact_tc.cu): same contract as launch_exact_candidates.
+bool exact_tc_supported(int storage, int metric);
+uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count);
+bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream);
+
 // K6 (graph_build.cu) ---------------------------------------------------------------------------
 // knn: [n][k_init] packed lists (ascending); produces fwd [n][R] pruned by detour count.
 void launch_prune_detour(const uint64_t* knn, uint32_t n, uint32_t k_init, uint32_t R, const uint32_t* deny,
