@@ -48,7 +48,8 @@ def parse_args():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--storage", default="f32", choices=["f32", "bf16", "f16"])
     ap.add_argument("--target-recall", type=float, default=0.95)
-    ap.add_argument("--cpu-sample", type=int, default=100_000, help="corpus rows of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="corpus rows of the bounded CPU-baseline sample")
+    ap.add_argument("--search-width", type=int, default=1)
     ap.add_argument("--cpu-queries", type=int, default=2_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -123,14 +124,18 @@ def cpu_hnsw_run(a, steps, warmup, full_line):
     ds = import_module("vector_store_b200.host.datasets")
     threads = os.cpu_count() or 1
     n = min(a.cpu_sample, a.n)
-    x = ds.embedding_like(n, a.dim, seed=1234)
+    CH = 100_000  # same chunked stream as the GPU arm: row r comes from chunk r // CH
+    x = np.concatenate([ds.embedding_like(min(CH, n - c0), a.dim, seed=1234 + c0 // CH) for c0 in range(0, n, CH)])
     q = ds.embedding_like(a.cpu_queries, a.dim, seed=4321)
     st = O.BF16 if a.storage == "bf16" else O.F32
     h = O.HnswCpu(a.dim, O.COS, n, 16, 128, 64, storage=st, threads=threads)
     t0 = time.perf_counter()
     h.add(np.arange(n, dtype=np.uint64), x)
     build_s = time.perf_counter() - t0
-    tk, _, _, _ = O.exact_topk(x, q[:200], a.k, O.COS, st)
+    # ground truth for the operating-point search: sgemm on the (unit-norm) vectors
+    sims = q[:200] @ x.T
+    tk = np.argsort(-sims, axis=1, kind="stable")[:, :a.k].astype(np.uint64)
+    del sims
     # smallest ef reaching the target recall (same rule as the GPU arm)
     ef_used, recall = 64, 0.0
     for ef in (32, 64, 96, 128, 192, 256, 384, 512):
@@ -152,7 +157,7 @@ def cpu_hnsw_run(a, steps, warmup, full_line):
         t1 = time.perf_counter()
         h.search_one(q[i], a.k)
         lat.append(time.perf_counter() - t1)
-    sample = (f"HNSW M=16/ef_add=128 built on the first {n} corpus rows (of {a.n}), {len(q)} queries per step, "
+    sample = (f"HNSW M=16/ef_add=128 built on {'all' if n == a.n else 'the first'} {n} corpus rows (of {a.n}), {len(q)} queries per step, "
               f"ef_search={ef_used} (recall@10={recall:.3f} on 200 queries); USearch-equivalent CPU restatement, "
               f"not USearch 2.22.0")
     base = {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
@@ -279,7 +284,7 @@ def main():
     sweep = []
     ef_used, recall = None, 0.0
     for ef in (32, 64, 96, 128, 192, 256, 384, 512):
-        idx.set_search_params(expansion_search=ef)
+        idx.set_search_params(expansion_search=ef, search_width=a.search_width)
         search_step(q_dev[0])
         torch.cuda.synchronize()
         r = recall_of(0)
@@ -308,11 +313,13 @@ def main():
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    torch.cuda.profiler.start()  # ncu --profile-from-start off captures exactly the timed region
     ev0.record()
     for i in range(a.steps):
         search_step(q_dev[i % NB])
     ev1.record()
     barrier()
+    torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
     st = idx.stats()
@@ -371,7 +378,8 @@ def main():
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": a.storage, "data": "synthetic",
         "config": {"workload": workload_name(a), "index": "M=16 (degree 32) ef_add=128",
-                   "expansion_search": ef_used, "recall_at_10": round(recall_timed, 4), "ef_sweep": sweep,
+                   "expansion_search": ef_used, "search_width": a.search_width,
+                   "recall_at_10": round(recall_timed, 4), "ef_sweep": sweep,
                    "parallelism": f"corpus sharded over {world} GPU(s), all-gather top-k merge" if world > 1 else "1 GPU",
                    "l2_policy": f"corpus {a.n * st['row_bytes'] / 1e9:.2f} GB >> 126 MB L2; {NB} query batches rotate"},
         "clocks": clocks,

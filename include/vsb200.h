@@ -74,6 +74,7 @@ typedef struct {
     uint32_t max_iterations;   /* parent expansions per query; 0 = auto */
     uint32_t n_seeds;          /* entry points taken from the seed layer, <= 32 */
     uint32_t min_graph_size;   /* below this many live vectors search is brute force */
+    uint32_t search_width;     /* parents expanded per iteration, 1..4 */
 } vsb_search_params;
 
 /* Counters the roofline arithmetic is computed from. */
@@ -92,6 +93,7 @@ typedef struct {
      * summed nanoseconds and launch counts since timing was switched on. */
     uint64_t convert_ns, seed_ns, graph_search_ns, exact_ns, merge_ns;
     uint64_t convert_launches, seed_launches, graph_search_launches, exact_launches, merge_launches;
+    uint64_t tc_launches;          /* distance-tile launches that ran on tcgen05 (exact_tc.cu), process-wide */
 } vsb_stats;
 
 /* usearch.rs:172  usearch::Index::new(&options) */

@@ -24,7 +24,11 @@ def run_exact(x, keys, q, k, metric, storage, dead=None):
     idx.add_batch(keys, x)
     if dead is not None:
         idx.remove_batch(keys[dead])
+    tc0 = idx.stats()["tc_launches"]
     out = idx.search_batch(q, k, exact=True)
+    tc_used = idx.stats()["tc_launches"] - tc0
+    expect_tc = os.environ.get("VSB_DISABLE_TC") != "1" and storage in (O.BF16, O.F16) and len(x) >= 8192
+    assert (tc_used > 0) == expect_tc, f"tcgen05 launches: {tc_used}, expected the TC path: {expect_tc}"
     idx.close()
     return out
 

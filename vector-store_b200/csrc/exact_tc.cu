@@ -443,6 +443,7 @@ bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream) {
         default: launch_tc_kind<KIND_TF32>(p.metric, mq, mx, a, grid, stream); break;
     }
     g_kernel_launches += 1;
+    g_tc_launches += 1;
     return true;
 }
 

@@ -23,18 +23,20 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
     a.seed_slots = p.seed_slots; a.deny = p.deny; a.keys = p.keys;
     a.itopk = ((p.itopk + 31) / 32) * 32;
     if (a.itopk < ((p.k + 31) / 32) * 32) a.itopk = ((p.k + 31) / 32) * 32;
-    a.max_iters = p.max_iters ? p.max_iters : 2 * a.itopk;
+    a.search_width = p.search_width < 1 ? 1 : (p.search_width > 4 ? 4 : p.search_width);
+    a.max_iters = p.max_iters ? p.max_iters : (2 * a.itopk) / a.search_width + 8;
     a.k = p.k;
-    // visited hash: room for ~half of the nodes one query can touch before a reset
-    uint32_t want = 32 * a.itopk;
-    uint32_t bits = 10;
-    while ((1u << bits) < want && bits < 13) ++bits;
+    // Visited hash: 8 KB (16 KB for wide beams) per warp keeps >= 12 query warps resident per SM; it is
+    // reset to "what is still in the list" when 3/4 full (forgotten nodes cost a re-evaluation, never a duplicate).
+    const uint32_t bits = a.itopk <= 256 ? 11 : 12;
     a.hash_bits = bits;
+    const uint32_t deg_pad = ((p.degree + 31) / 32) * 32;
+    a.queue_cap = a.search_width * deg_pad < 32 ? 32 : a.search_width * deg_pad;
     a.metric = p.metric;
     a.out_keys = p.out_keys; a.out_dists = p.out_dists; a.out_counts = p.out_counts; a.counters = p.counters;
     const int cpl = pick_cpl((int)(p.x.row_bytes / 16));
     dim3 grid((p.q.n + K4_WARPS - 1) / K4_WARPS);
-    const size_t smem = (size_t)K4_WARPS * ((size_t)a.itopk * 8 + ((size_t)4 << bits));
+    const size_t smem = (size_t)K4_WARPS * ((size_t)a.itopk * 8 + ((size_t)4 << bits) + (size_t)a.queue_cap * 8);
     switch (p.storage) {
         case VSB_ST_F32: launch_k4_f32(a, cpl, grid, smem, stream); break;
         case VSB_ST_F16: launch_k4_f16(a, cpl, grid, smem, stream); break;

@@ -34,7 +34,7 @@ struct K4Args {
     const uint32_t* seed_slots;
     const uint32_t* deny;
     const uint64_t* keys;
-    uint32_t itopk, max_iters, k, hash_bits;
+    uint32_t itopk, max_iters, k, hash_bits, search_width, queue_cap;
     int metric;
     uint64_t* out_keys;
     float* out_dists;
@@ -54,11 +54,13 @@ __device__ __forceinline__ bool hash_insert(uint32_t* tab, uint32_t mask, uint32
     return false;  // saturated neighbourhood: treat as visited
 }
 
+constexpr int K4_MAX_WIDTH = 4;  // parents expanded per iteration (search_width)
+
 template <int ST, int CPL>
-__global__ void __launch_bounds__(K4_WARPS * 32) graph_search_kernel(K4Args a) {
+__global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a) {
     constexpr int E = Storage<ST>::ELEMS;
     constexpr bool kFloat = Storage<ST>::kFloat;
-    constexpr int U = CPL <= 3 ? 4 : (CPL <= 6 ? 2 : 1);
+    constexpr int U = CPL <= 3 ? 4 : (CPL <= 6 ? 2 : 1);  // vectors per load group
     constexpr int QF = kFloat ? CPL * E : 1;
 
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -67,11 +69,15 @@ __global__ void __launch_bounds__(K4_WARPS * 32) graph_search_kernel(K4Args a) {
     if (q >= a.nq) return;
 
     const uint32_t hsize = 1u << a.hash_bits, hmask = hsize - 1;
-    const size_t per_warp = (size_t)a.itopk * 8 + (size_t)hsize * 4;
+    const uint32_t qcap = a.queue_cap;
+    const size_t per_warp = (size_t)a.itopk * 8 + (size_t)hsize * 4 + (size_t)qcap * 8;
     uint64_t* list = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warp * per_warp);
     uint32_t* hash = reinterpret_cast<uint32_t*>(list + a.itopk);
+    uint32_t* newq = hash + hsize;                           // [qcap] un-visited neighbour slots of this iteration
+    float* newd = reinterpret_cast<float*>(newq + qcap);     // [qcap] their distances
     const LessBySlot less;
     const bool is_l2 = a.metric == VSB_METRIC_L2SQ;
+    const bool is_cos = a.metric == VSB_METRIC_COS;
     const int n_chunks = a.x_row_bytes / 16;
 
     for (uint32_t i = lane; i < a.itopk; i += 32) list[i] = kInvalidPacked;
@@ -94,97 +100,121 @@ __global__ void __launch_bounds__(K4_WARPS * 32) graph_search_kernel(K4Args a) {
     const float qn = a.q_nrm[q];
     __syncwarp();
 
-    uint32_t n_hashed = 0;
+    uint32_t n_hashed = 0, n_new = 0;
     unsigned long long n_evals = 0, n_parents = 0;
 
-    // Evaluates the canonical distance of every lane's candidate `nb` (kInvalidSlot = none),
-    // folds the results into the list.
-    auto process_batch = [&](uint32_t nb) {
+    // visited filter + compaction of one candidate per lane into the iteration queue
+    auto enqueue = [&](uint32_t nb) {
         bool is_new = false;
         if (nb != kInvalidSlot) is_new = hash_insert(hash, hmask, a.hash_bits, nb);
-        uint32_t m = __ballot_sync(kFullMask, is_new);
-        if (m == 0) return;
+        const uint32_t m = __ballot_sync(kFullMask, is_new);
+        if (is_new) newq[n_new + __popc(m & ((1u << lane) - 1))] = nb;
+        n_new += __popc(m);
         n_hashed += __popc(m);
-        n_evals += __popc(m);
-        float my_d = 0.0f;
-        uint32_t todo = m;
-        while (todo) {
-            int src[U];
-            uint32_t slot[U];
+    };
+
+    struct Group {
+        uint4 x[U][CPL];
+        float xn[U];
+    };
+    auto load_group = [&](Group& g, uint32_t base) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                src[u] = todo ? (__ffs(todo) - 1) : -1;
-                if (todo) todo &= todo - 1;
-                slot[u] = __shfl_sync(kFullMask, nb, src[u] < 0 ? 0 : src[u]);
+        for (int u = 0; u < U; ++u) {
+            const uint32_t idx = base + u;
+            const bool on = idx < n_new;
+            const uint32_t slot = on ? newq[idx] : 0u;
+            const uint4* xrow = reinterpret_cast<const uint4*>(a.x_rows + (size_t)slot * a.x_row_bytes);
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const int c = j * 32 + lane;
+                g.x[u][j] = make_uint4(0, 0, 0, 0);
+                if (on && c < n_chunks) g.x[u][j] = ldg_nc_v4(xrow + c);
             }
-            uint4 x[U][CPL];
+            g.xn[u] = (on && is_cos) ? __ldg(a.x_nrm + slot) : 0.0f;
+        }
+    };
+    auto compute_group = [&](const Group& g, uint32_t base) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint4* xrow = reinterpret_cast<const uint4*>(a.x_rows + (size_t)slot[u] * a.x_row_bytes);
+        for (int u = 0; u < U; ++u) {
+            const uint32_t idx = base + u;
+            if (idx >= n_new) continue;  // warp-uniform
+            float facc = 0.0f;
+            int iacc = 0;
+            if constexpr (kFloat) {
+                if (is_l2) {
+                    ChunkAcc<ST, VSB_METRIC_L2SQ> acc;
 #pragma unroll
-                for (int j = 0; j < CPL; ++j) {
-                    const int c = j * 32 + lane;
-                    x[u][j] = make_uint4(0, 0, 0, 0);
-                    if (src[u] >= 0 && c < n_chunks) x[u][j] = ldg_nc_v4(xrow + c);
+                    for (int j = 0; j < CPL; ++j) {
+                        float xf[E];
+                        Storage<ST>::unpack(g.x[u][j], xf);
+                        acc.add_f(&qf[j * E], xf);
+                    }
+                    facc = acc.f;
+                } else {
+                    ChunkAcc<ST, VSB_METRIC_IP> acc;
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) {
+                        float xf[E];
+                        Storage<ST>::unpack(g.x[u][j], xf);
+                        acc.add_f(&qf[j * E], xf);
+                    }
+                    facc = acc.f;
                 }
+                facc = butterfly_sum(facc);
+            } else {
+                if (is_l2) {
+                    ChunkAcc<ST, VSB_METRIC_L2SQ> acc;
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) acc.add(qc[j], g.x[u][j]);
+                    iacc = acc.i;
+                } else {
+                    ChunkAcc<ST, VSB_METRIC_IP> acc;
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) acc.add(qc[j], g.x[u][j]);
+                    iacc = acc.i;
+                }
+                iacc = butterfly_sum_i(iacc);
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (src[u] < 0) continue;  // warp-uniform
-                float facc = 0.0f;
-                int iacc = 0;
-                if constexpr (kFloat) {
-                    if (is_l2) {
-                        ChunkAcc<ST, VSB_METRIC_L2SQ> acc;
-#pragma unroll
-                        for (int j = 0; j < CPL; ++j) {
-                            float xf[E];
-                            Storage<ST>::unpack(x[u][j], xf);
-                            acc.add_f(&qf[j * E], xf);
-                        }
-                        facc = acc.f;
-                    } else {
-                        ChunkAcc<ST, VSB_METRIC_IP> acc;
-#pragma unroll
-                        for (int j = 0; j < CPL; ++j) {
-                            float xf[E];
-                            Storage<ST>::unpack(x[u][j], xf);
-                            acc.add_f(&qf[j * E], xf);
-                        }
-                        facc = acc.f;
-                    }
-                    facc = butterfly_sum(facc);
-                } else {
-                    if (is_l2) {
-                        ChunkAcc<ST, VSB_METRIC_L2SQ> acc;
-#pragma unroll
-                        for (int j = 0; j < CPL; ++j) acc.add(qc[j], x[u][j]);
-                        iacc = acc.i;
-                    } else {
-                        ChunkAcc<ST, VSB_METRIC_IP> acc;
-#pragma unroll
-                        for (int j = 0; j < CPL; ++j) acc.add(qc[j], x[u][j]);
-                        iacc = acc.i;
-                    }
-                    iacc = butterfly_sum_i(iacc);
-                }
-                float d;
-                if constexpr (ST == VSB_ST_B1) {
-                    d = finish_distance<ST, VSB_METRIC_HAMMING>(facc, iacc, 0.0f, 0.0f);
-                } else {
-                    if (is_l2)
-                        d = finish_distance<ST, VSB_METRIC_L2SQ>(facc, iacc, 0.0f, 0.0f);
-                    else if (a.metric == VSB_METRIC_IP)
-                        d = finish_distance<ST, VSB_METRIC_IP>(facc, iacc, 0.0f, 0.0f);
-                    else
-                        d = finish_distance<ST, VSB_METRIC_COS>(facc, iacc, qn, a.x_nrm[slot[u]]);
-                }
-                if (lane == src[u]) my_d = d;
+            float d;
+            if constexpr (ST == VSB_ST_B1) {
+                d = finish_distance<ST, VSB_METRIC_HAMMING>(facc, iacc, 0.0f, 0.0f);
+            } else {
+                if (is_l2)
+                    d = finish_distance<ST, VSB_METRIC_L2SQ>(facc, iacc, 0.0f, 0.0f);
+                else if (is_cos)
+                    d = finish_distance<ST, VSB_METRIC_COS>(facc, iacc, qn, g.xn[u]);
+                else
+                    d = finish_distance<ST, VSB_METRIC_IP>(facc, iacc, 0.0f, 0.0f);
+            }
+            if (lane == 0) newd[idx] = d;
+        }
+    };
+
+    // distances of everything queued (double-buffered: the loads of group g+1 fly while group g is reduced),
+    // then fold the results into the candidate list 32 at a time
+    auto evaluate_queue = [&]() {
+        __syncwarp();
+        if (n_new == 0) return;
+        n_evals += n_new;
+        Group ga, gb;
+        load_group(ga, 0);
+        for (uint32_t base = 0; base < n_new; base += 2 * U) {
+            const bool has_b = base + U < n_new;
+            if (has_b) load_group(gb, base + U);
+            compute_group(ga, base);
+            if (has_b) {
+                if (base + 2 * U < n_new) load_group(ga, base + 2 * U);
+                compute_group(gb, base + U);
             }
         }
-        uint64_t res = is_new ? pack_ds(my_d, nb) : kInvalidPacked;
-        res = warp_sort32(res, lane, less);
-        warp_list_merge(list, (int)a.itopk, res, lane, less);
+        __syncwarp();
+        for (uint32_t base = 0; base < n_new; base += 32) {
+            uint64_t res = kInvalidPacked;
+            if (base + lane < n_new) res = pack_ds(newd[base + lane], newq[base + lane]);
+            res = warp_sort32(res, lane, less);
+            warp_list_merge(list, (int)a.itopk, res, lane, less);
+        }
+        n_new = 0;
     };
 
     // ---- seeds: merge the seed layer's split lists (32 each, ascending), map to slots ----
@@ -197,14 +227,15 @@ __global__ void __launch_bounds__(K4_WARPS * 32) graph_search_kernel(K4Args a) {
         }
         uint32_t nb = kInvalidSlot;
         if (lane < (int)a.n_seeds && sv != kInvalidPacked) nb = a.seed_slots[packed_lo(sv)];
-        process_batch(nb);
+        enqueue(nb);
+        evaluate_queue();
     }
 
     // ---- main loop ----
-    const uint32_t max_iters = a.max_iters;
-    for (uint32_t it = 0; it < max_iters; ++it) {
+    const uint32_t width = a.search_width;
+    for (uint32_t it = 0; it < a.max_iters; ++it) {
         // visited hash getting crowded: forget everything except what is still in the list
-        if (n_hashed > hsize / 2) {
+        if (n_hashed > (hsize >> 2) * 3) {
             for (uint32_t i = lane; i < hsize; i += 32) hash[i] = kHashEmpty;
             __syncwarp();
             n_hashed = 0;
@@ -215,28 +246,50 @@ __global__ void __launch_bounds__(K4_WARPS * 32) graph_search_kernel(K4Args a) {
             }
             __syncwarp();
         }
-        // best un-expanded candidate
-        uint32_t parent = kInvalidSlot;
-        for (uint32_t b = 0; b < a.itopk; b += 32) {
+        // best un-expanded candidates (up to `width`)
+        uint32_t par[K4_MAX_WIDTH];
+        uint32_t np = 0;
+#pragma unroll
+        for (int i = 0; i < K4_MAX_WIDTH; ++i) par[i] = kInvalidSlot;
+        for (uint32_t b = 0; b < a.itopk && np < width; b += 32) {
             const uint64_t e = list[b + lane];
             const bool unexp = e != kInvalidPacked && !(packed_lo(e) & kExpandedBit);
-            const uint32_t m = __ballot_sync(kFullMask, unexp);
-            if (m) {
+            uint32_t m = __ballot_sync(kFullMask, unexp);
+            bool mine = false;
+            while (m && np < width) {
                 const int src = __ffs(m) - 1;
-                parent = __shfl_sync(kFullMask, packed_lo(e), src);
-                if (lane == src) list[b + lane] = e | kExpandedBit;
-                break;
+                m &= m - 1;
+                const uint32_t pslot = __shfl_sync(kFullMask, packed_lo(e), src);
+#pragma unroll
+                for (int i = 0; i < K4_MAX_WIDTH; ++i)
+                    if (i == (int)np) par[i] = pslot;
+                if (lane == src) mine = true;
+                ++np;
             }
+            if (mine) list[b + lane] = e | kExpandedBit;
         }
         __syncwarp();
-        if (parent == kInvalidSlot) break;
-        ++n_parents;
-        const uint32_t* grow = a.graph + (size_t)parent * a.graph_stride;
-        for (uint32_t r0 = 0; r0 < a.degree; r0 += 32) {
-            uint32_t nb = kInvalidSlot;
-            if (r0 + lane < a.degree) nb = __ldg(grow + r0 + lane);
-            process_batch(nb);
+        if (np == 0) break;
+        n_parents += np;
+        // all graph rows of this iteration in flight together, then filter + queue
+        uint32_t nbs[K4_MAX_WIDTH][2];
+#pragma unroll
+        for (int i = 0; i < K4_MAX_WIDTH; ++i) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                nbs[i][h] = kInvalidSlot;
+                const uint32_t r = h * 32 + lane;
+                if (i < (int)np && r < a.degree) nbs[i][h] = __ldg(a.graph + (size_t)par[i] * a.graph_stride + r);
+            }
         }
+#pragma unroll
+        for (int i = 0; i < K4_MAX_WIDTH; ++i) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (i < (int)np && h * 32 < (int)a.degree) enqueue(nbs[i][h]);
+            }
+        }
+        evaluate_queue();
     }
 
     // ---- emit the first k live entries ----

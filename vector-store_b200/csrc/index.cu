@@ -32,6 +32,7 @@
 
 namespace vsb {
 std::atomic<uint64_t> g_kernel_launches{0};
+std::atomic<uint64_t> g_tc_launches{0};
 }
 
 namespace {
@@ -98,7 +99,7 @@ struct vsb_index {
     uint32_t dim = 0, row_bytes = 0;
     int metric = 0, storage = 0, device = 0, sm_count = 148;
     uint32_t degree = 32, graph_stride = 32, k_init = 64;
-    uint32_t itopk = 64, max_iters = 0, n_seeds = 32, min_graph_size = 4096;
+    uint32_t itopk = 64, max_iters = 0, n_seeds = 32, min_graph_size = 4096, search_width = 1;
     bool instrumented = false;
 
     cudaStream_t stream = nullptr;
@@ -513,6 +514,7 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
             gp.keys = keys.as<uint64_t>();
             gp.itopk = std::max(itopk, k);
             gp.max_iters = max_iters;
+            gp.search_width = search_width;
             gp.k = k;
             gp.out_keys = g_keys;
             gp.out_dists = g_dists;
@@ -704,6 +706,7 @@ vsb_status vsb_set_search_params(vsb_index* ix, const vsb_search_params* p) {
     if (p->max_iterations) ix->max_iters = p->max_iterations;
     if (p->n_seeds) ix->n_seeds = std::min<uint32_t>(p->n_seeds, 32);
     if (p->min_graph_size) ix->min_graph_size = p->min_graph_size;
+    if (p->search_width) ix->search_width = std::min<uint32_t>(p->search_width, 4);
     return VSB_OK;
 }
 
@@ -751,6 +754,7 @@ vsb_status vsb_get_stats(vsb_index* ix, vsb_stats* out) {
     out->graph_search_launches = ix->phase_launches[vsb_index::PH_GRAPH];
     out->exact_launches = ix->phase_launches[vsb_index::PH_EXACT];
     out->merge_launches = ix->phase_launches[vsb_index::PH_MERGE];
+    out->tc_launches = vsb::g_tc_launches.load();
     return VSB_OK;
 }
 

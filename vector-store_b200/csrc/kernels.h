@@ -8,6 +8,7 @@ namespace vsb {
 
 // every launcher adds the number of kernels it enqueued (reported as gpu_launches by bench.py)
 extern std::atomic<uint64_t> g_kernel_launches;
+extern std::atomic<uint64_t> g_tc_launches;
 
 // A block of stored rows: storage-typed bytes + canonical norms.
 struct RowsView {
@@ -80,7 +81,7 @@ struct SearchParams {
     const uint32_t* seed_slots = nullptr;  // seed index -> slot
     const uint32_t* deny = nullptr;
     const uint64_t* keys = nullptr;
-    uint32_t itopk = 64, max_iters = 0, k = 10;
+    uint32_t itopk = 64, max_iters = 0, k = 10, search_width = 1;
     uint64_t* out_keys = nullptr;
     float* out_dists = nullptr;
     uint32_t* out_counts = nullptr;

@@ -129,8 +129,8 @@ class GpuIndex:
         return rows, keys
 
     def set_search_params(self, expansion_search: int = 0, max_iterations: int = 0, n_seeds: int = 0,
-                          min_graph_size: int = 0) -> None:
-        p = VsbSearchParams(expansion_search, max_iterations, n_seeds, min_graph_size)
+                          min_graph_size: int = 0, search_width: int = 0) -> None:
+        p = VsbSearchParams(expansion_search, max_iterations, n_seeds, min_graph_size, search_width)
         check(self._lib.vsb_set_search_params(self._h, C.byref(p)))
 
     def set_instrumented(self, on: bool) -> None:

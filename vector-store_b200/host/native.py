@@ -25,7 +25,7 @@ class VsbOptions(C.Structure):
 
 class VsbSearchParams(C.Structure):
     _fields_ = [("expansion_search", C.c_uint32), ("max_iterations", C.c_uint32), ("n_seeds", C.c_uint32),
-                ("min_graph_size", C.c_uint32)]
+                ("min_graph_size", C.c_uint32), ("search_width", C.c_uint32)]
 
 
 class VsbStats(C.Structure):
@@ -33,7 +33,7 @@ class VsbStats(C.Structure):
                                           "n_slots", "n_graphed", "graph_degree", "row_bytes", "n_seed_rows",
                                           "hbm_bytes", "convert_ns", "seed_ns", "graph_search_ns", "exact_ns",
                                           "merge_ns", "convert_launches", "seed_launches", "graph_search_launches",
-                                          "exact_launches", "merge_launches")]
+                                          "exact_launches", "merge_launches", "tc_launches")]
 
 
 # every symbol include/vsb200.h declares: (name, restype, argtypes)
