@@ -261,8 +261,8 @@ def main():
             idx.search_dev(qd.data_ptr(), B, k, out_k.data_ptr(), out_d.data_ptr(), 0, stream, exact)
             return
         idx.search_dev(qd.data_ptr(), B, k, keys_l.data_ptr(), dists_l.data_ptr(), 0, stream, exact)
-        dist.all_gather_into_tensor(gath_k, keys_l)
-        dist.all_gather_into_tensor(gath_d, dists_l)
+        dist.all_gather_into_tensor(gath_k.view(world * B, k), keys_l)
+        dist.all_gather_into_tensor(gath_d.view(world * B, k), dists_l)
         index_mod.merge_topk_dev(gath_k.data_ptr(), gath_d.data_ptr(), world, B, k, out_k.data_ptr(), out_d.data_ptr(),
                                  0, local_rank, stream)
 

@@ -56,6 +56,7 @@ struct TcArgs {
     uint64_t allow_bits;
     uint32_t kp, n_splits, rows_per_split;
     uint64_t* part;
+    int tile_min;  // 1: emit only each tile's best row per query (seed layer), no list maintenance
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -287,6 +288,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (uint32_t t = 0; t < n_tiles; ++t) {
             const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
             const uint32_t n0 = r_lo + t * TC_N;
+            float best_d = __int_as_float(0x7F800000);
+            uint32_t best_n = kInvalidSlot;
             // per-column parameter of this tile (NaN marks columns outside the split)
             float* cp = colp + acc * TC_N;
             for (int c = etid; c < TC_N; c += 128) {
@@ -317,6 +320,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     if constexpr (METRIC == VSB_METRIC_L2SQ) d = fmaf(dot, -2.0f, p) + qsq;
                     else if constexpr (METRIC == VSB_METRIC_COS) d = fmaf(dot * p, -inv_qn, 1.0f);
                     else d = fmaf(dot, -1.0f, p);
+                    if (a.tile_min) {
+                        if (d < best_d) {
+                            best_d = d;
+                            best_n = n0 + ch * 32 + j;
+                        }
+                        continue;
+                    }
                     if (d <= thr) {
                         const uint32_t n = n0 + ch * 32 + j;
                         bool ok = true;
@@ -334,6 +344,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 }
                 const uint32_t need = __ballot_sync(kFullMask, cnt > TC_BUFCAP - 32);
                 if (need) flush(need);
+            }
+            if (a.tile_min && q_valid && best_n != kInvalidSlot && t < a.kp) {
+                if constexpr (METRIC == VSB_METRIC_L2SQ) best_d = fmaxf(best_d, 0.0f);
+                if constexpr (METRIC == VSB_METRIC_COS) best_d = fminf(fmaxf(best_d, 0.0f), 2.0f);
+                a.part[((size_t)q * a.n_splits + split) * a.kp + t] = pack_ds(best_d, best_n);
             }
             // accumulator drained: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
@@ -409,6 +424,12 @@ bool exact_tc_supported(int storage, int metric) {
     return storage == VSB_ST_F32 || storage == VSB_ST_BF16 || storage == VSB_ST_F16;
 }
 
+// tile-min mode keeps one entry per tile: a split may not hold more than kp tiles
+uint32_t exact_tc_min_splits_tile_min(uint32_t n_rows, uint32_t kp) {
+    const uint32_t tiles = (n_rows + TC_N - 1) / TC_N;
+    return (tiles + kp - 1) / kp;
+}
+
 uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count) {
     const uint32_t q_tiles = (nq + TC_M - 1) / TC_M;
     uint32_t want = ((uint32_t)sm_count + q_tiles - 1) / q_tiles;   // >= one CTA per SM
@@ -421,7 +442,7 @@ uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count) {
 
 // Same contract as launch_exact_candidates (exact.cu); returns false if the TMA descriptors could
 // not be encoded (caller falls back to the SIMT K1, which is still the CUDA path).
-bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream) {
+bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream, bool tile_min) {
     if (p.q.n == 0 || p.x_hi <= p.x_lo) return true;
     const int kind = p.storage == VSB_ST_F32 ? KIND_TF32 : (p.storage == VSB_ST_BF16 ? KIND_BF16 : KIND_F16);
     CUtensorMap mq, mx;
@@ -436,6 +457,7 @@ bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream) {
     const uint32_t rps = (rows + p.n_splits - 1) / p.n_splits;
     a.rows_per_split = ((rps + TC_N - 1) / TC_N) * TC_N;
     a.part = p.part;
+    a.tile_min = tile_min ? 1 : 0;
     dim3 grid((p.q.n + TC_M - 1) / TC_M, p.n_splits);
     switch (kind) {
         case KIND_BF16: launch_tc_kind<KIND_BF16>(p.metric, mq, mx, a, grid, stream); break;

@@ -26,9 +26,10 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
     a.search_width = p.search_width < 1 ? 1 : (p.search_width > 4 ? 4 : p.search_width);
     a.max_iters = p.max_iters ? p.max_iters : (2 * a.itopk) / a.search_width + 8;
     a.k = p.k;
-    // Visited hash: 8 KB (16 KB for wide beams) per warp keeps >= 12 query warps resident per SM; it is
-    // reset to "what is still in the list" when 3/4 full (forgotten nodes cost a re-evaluation, never a duplicate).
-    const uint32_t bits = a.itopk <= 256 ? 11 : 12;
+    // Visited hash: 16 KB per warp (4096 slots) = 3 CTAs x 4 query warps per SM, the same residency the
+    // register budget allows; it is reset to "what is still in the list" when 3/4 full (forgotten nodes
+    // cost a re-evaluation, never a duplicate).
+    const uint32_t bits = 12;
     a.hash_bits = bits;
     const uint32_t deg_pad = ((p.degree + 31) / 32) * 32;
     a.queue_cap = a.search_width * deg_pad < 32 ? 32 : a.search_width * deg_pad;

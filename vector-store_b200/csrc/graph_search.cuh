@@ -217,11 +217,13 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
         n_new = 0;
     };
 
-    // ---- seeds: merge the seed layer's split lists (32 each, ascending), map to slots ----
+    // ---- seeds: the seed layer hands over `seed_splits` blocks of 32 packed (distance, seed index)
+    // entries (sorted lists from K1, or unsorted per-tile winners from the tensor-core kernel) ----
     {
-        uint64_t sv = a.seed_lists[((size_t)q * a.seed_splits) * 32 + lane];
-        for (uint32_t s = 1; s < a.seed_splits; ++s) {
-            const uint64_t v = a.seed_lists[((size_t)q * a.seed_splits + s) * 32 + lane];
+        uint64_t sv = kInvalidPacked;
+        for (uint32_t s = 0; s < a.seed_splits; ++s) {
+            uint64_t v = a.seed_lists[((size_t)q * a.seed_splits + s) * 32 + lane];
+            v = warp_sort32(v, lane, less);
             const uint64_t rc = shfl_u64(v, 31 - lane);
             sv = warp_bitonic_merge32(rc < sv ? rc : sv, lane, less);
         }

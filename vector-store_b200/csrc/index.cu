@@ -114,6 +114,8 @@ struct vsb_index {
 
     DevBuf rows, sq, nrm, keys, deny, graph;
     DevBuf seed_rows, seed_sq, seed_nrm, seed_slots;
+    DevBuf seed16_rows, seed16_sq, seed16_nrm;   // bf16 shadow of the seed block (f32 storage only)
+    DevBuf q16_rows, q16_sq, q16_nrm;            // bf16 shadow of the converted queries (f32 storage only)
     DevBuf q_in, q_rows, q_sq, q_nrm, part, seed_part, tmp_keys, tmp_dists, counters, add_in, allow;
     std::unordered_map<uint64_t, uint32_t> key2slot;
     std::vector<uint32_t> h_deny;
@@ -155,6 +157,7 @@ struct vsb_index {
 
     size_t hbm_bytes() const {
         const DevBuf* all[] = {&rows, &sq, &nrm, &keys, &deny, &graph, &seed_rows, &seed_sq, &seed_nrm, &seed_slots,
+                               &seed16_rows, &seed16_sq, &seed16_nrm, &q16_rows, &q16_sq, &q16_nrm,
                                &q_in, &q_rows, &q_sq, &q_nrm, &part, &seed_part, &tmp_keys, &tmp_dists, &counters,
                                &add_in, &allow};
         size_t s = 0;
@@ -186,7 +189,8 @@ struct vsb_index {
                            const uint32_t* deny_bm, const uint64_t* key_arr, const uint32_t* allow_bm,
                            uint64_t allow_bits, uint32_t k, uint64_t* out_keys, float* out_dists,
                            uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t s,
-                           bool approx_ok);
+                           bool approx_ok, const vsb::RowsView* shadow_q = nullptr,
+                           const vsb::RowsView* shadow_x = nullptr);
     bool tc_enabled = true;       // tcgen05 path for the dense distance tiles (VSB_DISABLE_TC=1 turns it off)
     uint32_t tc_min_rows = 8192;  // below this the SIMT K1 is used (launch + pipeline fill dominate)
     vsb_status search_dev(const float* d_q, uint64_t nq, uint32_t k, uint64_t* d_keys, float* d_dists,
@@ -314,7 +318,7 @@ vsb_status vsb_index::exact_block(const vsb::RowsView& q, const vsb::RowsView& x
                                   const uint32_t* deny_bm, const uint64_t* key_arr, const uint32_t* allow_bm,
                                   uint64_t allow_bits, uint32_t k, uint64_t* out_keys, float* out_dists,
                                   uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t s,
-                                  bool approx_ok) {
+                                  bool approx_ok, const vsb::RowsView* shadow_q, const vsb::RowsView* shadow_x) {
     vsb::ExactParams p;
     p.storage = storage;
     p.metric = metric;
@@ -337,7 +341,18 @@ vsb_status vsb_index::exact_block(const vsb::RowsView& q, const vsb::RowsView& x
                     : vsb::exact_pick_splits(q.n, x_hi - x_lo, sm_count);
     CU(part.ensure(vsb::exact_part_elems(q.n, p.n_splits, p.kp) * 8));
     p.part = part.as<uint64_t>();
-    if (tc) tc = vsb::launch_exact_candidates_tc(p, s);
+    if (tc) {
+        if (shadow_q != nullptr && shadow_x != nullptr) {
+            // candidate stage on the bf16 shadow (half the bytes, kind::f16 rate); K3 re-ranks on the real rows
+            vsb::ExactParams pc = p;
+            pc.storage = VSB_BF16;
+            pc.q = *shadow_q;
+            pc.x = *shadow_x;
+            tc = vsb::launch_exact_candidates_tc(pc, s);
+        } else {
+            tc = vsb::launch_exact_candidates_tc(p, s);
+        }
+    }
     if (!tc) vsb::launch_exact_candidates(p, s);
     CU(cudaGetLastError());
     vsb::launch_exact_rerank(p, k, out_keys, out_dists, out_counts, out_packed, self_base, s);
@@ -360,6 +375,25 @@ vsb_status vsb_index::build() {
     CU(knn.ensure((size_t)n * kin * 8));
     const vsb::RowsView x = corpus_view();
     const uint32_t* deny_bm = any_tombstone ? deny.as<uint32_t>() : nullptr;
+    // f32 storage: the all-pairs candidate stage runs on a temporary bf16 copy (kNN lists only need
+    // candidate-grade distances; K3 re-evaluates the survivors on the f32 rows in the canonical order)
+    DevBuf sh_rows, sh_sq, sh_nrm;
+    vsb::RowsView shx;
+    const bool use_shadow = storage == VSB_F32 && tc_enabled && n >= tc_min_rows;
+    if (use_shadow) {
+        const uint32_t dim_pad = row_bytes / 4;
+        shx.row_bytes = ((dim_pad * 2 + 15) / 16) * 16;
+        shx.n = n;
+        CU(sh_rows.ensure((size_t)n * shx.row_bytes));
+        CU(sh_sq.ensure((size_t)n * 4));
+        CU(sh_nrm.ensure((size_t)n * 4));
+        vsb::launch_convert_rows(VSB_BF16, reinterpret_cast<const float*>(x.rows), n, dim_pad, sh_rows.as<uint8_t>(),
+                                 shx.row_bytes, sh_sq.as<float>(), sh_nrm.as<float>(), stream);
+        CU(cudaGetLastError());
+        shx.rows = sh_rows.as<uint8_t>();
+        shx.sq = sh_sq.as<float>();
+        shx.nrm = sh_nrm.as<float>();
+    }
     const uint32_t QB = 16384;
     for (uint32_t b0 = 0; b0 < n; b0 += QB) {
         vsb::RowsView q;
@@ -368,9 +402,20 @@ vsb_status vsb_index::build() {
         q.sq = x.sq + b0;
         q.nrm = x.nrm + b0;
         q.row_bytes = row_bytes;
+        vsb::RowsView shq = shx;
+        if (use_shadow) {
+            shq.n = q.n;
+            shq.rows = shx.rows + (size_t)b0 * shx.row_bytes;
+            shq.sq = shx.sq + b0;
+            shq.nrm = shx.nrm + b0;
+        }
         ST(exact_block(q, x, 0, n, deny_bm, keys.as<uint64_t>(), nullptr, 0, kin, nullptr, nullptr, nullptr,
-                       knn.as<uint64_t>() + (size_t)b0 * kin, (int64_t)b0, stream, true));
+                       knn.as<uint64_t>() + (size_t)b0 * kin, (int64_t)b0, stream, true, use_shadow ? &shq : nullptr,
+                       use_shadow ? &shx : nullptr));
     }
+    sh_rows.release();
+    sh_sq.release();
+    sh_nrm.release();
     CU(fwd.ensure((size_t)n * R * 4));
     CU(rev.ensure((size_t)n * R * 4));
     CU(rev_cnt.ensure((size_t)n * 4));
@@ -415,6 +460,16 @@ vsb_status vsb_index::build() {
     vsb::launch_gather_rows(x.rows, row_bytes, x.sq, x.nrm, seed_slots.as<uint32_t>(), S, seed_rows.as<uint8_t>(),
                             seed_sq.as<float>(), seed_nrm.as<float>(), stream);
     CU(cudaGetLastError());
+    if (storage == VSB_F32) {
+        const uint32_t dim_pad = row_bytes / 4;
+        const uint32_t rb16 = ((dim_pad * 2 + 15) / 16) * 16;
+        CU(seed16_rows.ensure((size_t)S * rb16));
+        CU(seed16_sq.ensure((size_t)S * 4));
+        CU(seed16_nrm.ensure((size_t)S * 4));
+        vsb::launch_convert_rows(VSB_BF16, seed_rows.as<float>(), S, dim_pad, seed16_rows.as<uint8_t>(), rb16,
+                                 seed16_sq.as<float>(), seed16_nrm.as<float>(), stream);
+        CU(cudaGetLastError());
+    }
     CU(cudaStreamSynchronize(stream));
     std::swap(graph, new_graph);
     n_graphed = n;
@@ -488,13 +543,46 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
             sp.keys = nullptr;  // ties by seed index: LessByKey is never asked (see below)
             sp.kp = 32;
             bool seed_tc = tc_enabled && vsb::exact_tc_supported(storage, metric) && nb >= 16;
-            sp.n_splits = seed_tc ? vsb::exact_tc_pick_splits(nb, n_seed_rows, sm_count)
-                                  : vsb::exact_pick_splits(nb, n_seed_rows, sm_count);
+            if (seed_tc) {
+                // tensor-core seed layer: one winner per 256-row tile per query (no list maintenance);
+                // f32 storage multiplies the bf16 shadows of the queries and of the seed block
+                sp.n_splits = std::max(vsb::exact_tc_pick_splits(nb, n_seed_rows, sm_count),
+                                       vsb::exact_tc_min_splits_tile_min(n_seed_rows, 32));
+                if (storage == VSB_F32) {
+                    const uint32_t dim_pad = row_bytes / 4;
+                    const uint32_t rb16 = ((dim_pad * 2 + 15) / 16) * 16;
+                    CU(q16_rows.ensure((size_t)nb * rb16));
+                    CU(q16_sq.ensure((size_t)nb * 4));
+                    CU(q16_nrm.ensure((size_t)nb * 4));
+                    vsb::launch_convert_rows(VSB_BF16, q_rows.as<float>(), nb, dim_pad, q16_rows.as<uint8_t>(), rb16,
+                                             q16_sq.as<float>(), q16_nrm.as<float>(), s);
+                    CU(cudaGetLastError());
+                    sp.storage = VSB_BF16;
+                    sp.q.rows = q16_rows.as<uint8_t>();
+                    sp.q.sq = q16_sq.as<float>();
+                    sp.q.nrm = q16_nrm.as<float>();
+                    sp.q.row_bytes = rb16;
+                    sp.x.rows = seed16_rows.as<uint8_t>();
+                    sp.x.sq = seed16_sq.as<float>();
+                    sp.x.nrm = seed16_nrm.as<float>();
+                    sp.x.row_bytes = rb16;
+                }
+            } else {
+                sp.n_splits = vsb::exact_pick_splits(nb, n_seed_rows, sm_count);
+            }
             CU(seed_part.ensure(vsb::exact_part_elems(nb, sp.n_splits, 32) * 8));
             sp.part = seed_part.as<uint64_t>();
             t_begin(PH_SEED, s);
-            if (seed_tc) seed_tc = vsb::launch_exact_candidates_tc(sp, s);
-            if (!seed_tc) vsb::launch_exact_candidates(sp, s);
+            if (seed_tc) seed_tc = vsb::launch_exact_candidates_tc(sp, s, true);
+            if (!seed_tc) {
+                sp.storage = storage;
+                sp.q = qv;
+                sp.x.rows = seed_rows.as<uint8_t>();
+                sp.x.sq = seed_sq.as<float>();
+                sp.x.nrm = seed_nrm.as<float>();
+                sp.x.row_bytes = row_bytes;
+                vsb::launch_exact_candidates(sp, s);
+            }
             t_end(s);
             CU(cudaGetLastError());
             vsb::SearchParams gp;

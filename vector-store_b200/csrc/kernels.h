@@ -54,7 +54,8 @@ void launch_exact_rerank(const ExactParams& p, uint32_t k, uint64_t* out_keys, f
 // K1 on tcgen05 tensor cores (exact_tc.cu): same contract as launch_exact_candidates.
 bool exact_tc_supported(int storage, int metric);
 uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count);
-bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream);
+bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream, bool tile_min = false);
+uint32_t exact_tc_min_splits_tile_min(uint32_t n_rows, uint32_t kp);
 
 // K6 (graph_build.cu) ---------------------------------------------------------------------------
 // knn: [n][k_init] packed lists (ascending); produces fwd [n][R] pruned by detour count.

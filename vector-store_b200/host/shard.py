@@ -32,8 +32,9 @@ def allgather_topk(keys, dists, world: int):
         gk[0].copy_(keys)
         gd[0].copy_(dists)
         return gk, gd
-    dist.all_gather_into_tensor(gk, keys.contiguous())
-    dist.all_gather_into_tensor(gd, dists.contiguous())
+    # concatenated-along-dim-0 output form: accepted by both NCCL and gloo
+    dist.all_gather_into_tensor(gk.view(-1, *keys.shape[1:]), keys.contiguous())
+    dist.all_gather_into_tensor(gd.view(-1, *dists.shape[1:]), dists.contiguous())
     return gk, gd
 
 
