@@ -384,3 +384,25 @@ def test_c1_full_size_properties():
     recall_hi = O.recall_at_k(ak2, gk[:256])
     print(f"C1 100k x 128 L2sq recall@10: ef=64 {recall:.4f}, ef=512 {recall_hi:.4f}")
     assert recall_hi >= recall and recall_hi >= 0.9
+
+
+@pytest.mark.parametrize("storage,dim", [(O.F32, 96), (O.BF16, 768)])
+def test_small_batch_paths_cta_per_query(storage, dim):
+    # batch <= 256 runs the CTA-per-query kernel (K4b); batch < 16 also uses the seed-scan kernel
+    n, k = 30000, 10
+    x = embedding_like(n, dim, n_clusters=32)
+    q = embedding_like(300, dim, seed=4321, n_clusters=32)
+    keys = np.arange(n, dtype=np.uint64) + np.uint64(5 << 48)
+    idx = make_index(x, keys, O.COS, storage)
+    idx.build()
+    tk, td, _ = idx.search_batch(q, k, exact=True)
+    big_k, big_d, _ = idx.search_batch(q, k)  # warp-per-query kernel (batch 300)
+    for nq in (1, 5, 16, 100, 256):
+        gk, gd, gc = idx.search_batch(q[:nq], k)
+        assert np.all(gc == k) and np.all(np.diff(gd, axis=1) >= 0)
+        r = O.recall_at_k(gk, tk[:nq])
+        print(f"batch {nq}: recall@10 = {r:.4f}")
+        assert r >= 0.9 if nq < 16 else r >= 0.95
+        od = O.distance_matrix(x[(gk[0] - np.uint64(5 << 48)).astype(np.int64)], q[:1], O.COS, storage)[0]
+        assert np.array_equal(gd[0].view(np.uint32), od.view(np.uint32))
+    assert O.recall_at_k(big_k, tk) >= 0.95

@@ -13,6 +13,33 @@ static int pick_cpl(int n_chunks) {
 
 bool graph_search_supported(uint32_t row_bytes) { return pick_cpl((int)(row_bytes / 16)) > 0; }
 
+// batches up to this size use the CTA-per-query kernel (one CTA per SM-slot still fills the GPU)
+uint32_t graph_search_small_batch() { return 256; }
+
+uint32_t seed_scan_blocks(uint32_t n_seed_rows) {
+    const uint32_t ctas = (n_seed_rows + SEED_SCAN_WARPS * SEED_SCAN_ROWS_PER_WARP - 1) /
+                          (SEED_SCAN_WARPS * SEED_SCAN_ROWS_PER_WARP);
+    return (ctas + 31) / 32;
+}
+
+// [q][blocks][32] packed per-CTA winners, kInvalidPacked padded (caller pre-fills the buffer with 0xFF)
+void launch_seed_scan(int storage, int metric, const RowsView& q, const RowsView& seeds, uint64_t* out,
+                      cudaStream_t stream) {
+    if (q.n == 0 || seeds.n == 0) return;
+    SeedScanArgs s;
+    s.q_rows = q.rows; s.q_nrm = q.nrm; s.nq = q.n; s.q_row_bytes = q.row_bytes;
+    s.s_rows = seeds.rows; s.s_nrm = seeds.nrm; s.n_seed_rows = seeds.n; s.row_bytes = seeds.row_bytes;
+    s.metric = metric; s.n_blocks = seed_scan_blocks(seeds.n); s.out = out;
+    switch (storage) {
+        case VSB_ST_F32: launch_seed_scan_f32(s, stream); break;
+        case VSB_ST_F16: launch_seed_scan_f16(s, stream); break;
+        case VSB_ST_BF16: launch_seed_scan_bf16(s, stream); break;
+        case VSB_ST_I8: launch_seed_scan_i8(s, stream); break;
+        default: launch_seed_scan_b1(s, stream); break;
+    }
+    g_kernel_launches += 1;
+}
+
 void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
     if (p.q.n == 0) return;
     K4Args a;
@@ -36,6 +63,23 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
     a.metric = p.metric;
     a.out_keys = p.out_keys; a.out_dists = p.out_dists; a.out_counts = p.out_counts; a.counters = p.counters;
     const int cpl = pick_cpl((int)(p.x.row_bytes / 16));
+    if (p.q.n <= graph_search_small_batch()) {
+        // CTA-per-query kernel: 8 warps and up to 8 parents per iteration for one query
+        a.search_width = a.search_width < 4 ? 8 : (a.search_width > 8 ? 8 : a.search_width);
+        a.max_iters = p.max_iters ? p.max_iters : (2 * a.itopk) / a.search_width + 8;
+        a.queue_cap = a.search_width * deg_pad;
+        dim3 gridb(p.q.n);
+        const size_t smemb = (size_t)a.itopk * 8 + (size_t)a.queue_cap * 16 + ((size_t)4 << bits) + 64;
+        switch (p.storage) {
+            case VSB_ST_F32: launch_k4b_f32(a, cpl, gridb, smemb, stream); break;
+            case VSB_ST_F16: launch_k4b_f16(a, cpl, gridb, smemb, stream); break;
+            case VSB_ST_BF16: launch_k4b_bf16(a, cpl, gridb, smemb, stream); break;
+            case VSB_ST_I8: launch_k4b_i8(a, cpl, gridb, smemb, stream); break;
+            default: launch_k4b_b1(a, cpl, gridb, smemb, stream); break;
+        }
+        g_kernel_launches += 1;
+        return;
+    }
     dim3 grid((p.q.n + K4_WARPS - 1) / K4_WARPS);
     const size_t smem = (size_t)K4_WARPS * ((size_t)a.itopk * 8 + ((size_t)4 << bits) + (size_t)a.queue_cap * 8);
     switch (p.storage) {

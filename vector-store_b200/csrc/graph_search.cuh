@@ -323,10 +323,361 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K4b: CTA-per-query variant for small batches (batch-1 latency, SURVEY §8d "p99 batch-1").
+// Same algorithm and the same canonical distances as the warp kernel, but 8 warps share one candidate
+// list / visited hash and split every iteration's neighbour evaluations, and up to 8 parents are
+// expanded per iteration, so a query needs ~ef/8 dependent memory round trips instead of ~ef.
+constexpr int K4B_WARPS = 8;
+constexpr int K4B_MAX_WIDTH = 8;
+
+template <int ST, int CPL>
+__global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4Args a) {
+    constexpr int E = Storage<ST>::ELEMS;
+    constexpr bool kFloat = Storage<ST>::kFloat;
+    constexpr int U = CPL <= 3 ? 4 : (CPL <= 6 ? 2 : 1);
+    constexpr int QF = kFloat ? CPL * E : 1;
+
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t q = blockIdx.x;
+    const uint32_t hsize = 1u << a.hash_bits, hmask = hsize - 1;
+    const uint32_t qcap = a.queue_cap;
+    uint64_t* list = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* newp = list + a.itopk;                              // [qcap] sorted groups of 32
+    uint32_t* hash = reinterpret_cast<uint32_t*>(newp + qcap);    // [hsize]
+    uint32_t* newq = hash + hsize;                                // [qcap]
+    float* newd = reinterpret_cast<float*>(newq + qcap);          // [qcap]
+    uint32_t* par = reinterpret_cast<uint32_t*>(newd + qcap);     // [K4B_MAX_WIDTH]
+    uint32_t* ctrl = par + K4B_MAX_WIDTH;                         // [0]=n_new [1]=np [2]=n_hashed
+    const LessBySlot less;
+    const bool is_l2 = a.metric == VSB_METRIC_L2SQ;
+    const bool is_cos = a.metric == VSB_METRIC_COS;
+    const int n_chunks = a.x_row_bytes / 16;
+
+    for (uint32_t i = tid; i < a.itopk; i += K4B_WARPS * 32) list[i] = kInvalidPacked;
+    for (uint32_t i = tid; i < hsize; i += K4B_WARPS * 32) hash[i] = kHashEmpty;
+    if (tid < 3) ctrl[tid] = 0;
+
+    const uint4* qrow = reinterpret_cast<const uint4*>(a.q_rows + (size_t)q * a.q_row_bytes);
+    float qf[QF];
+    uint4 qc[kFloat ? 1 : CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        const int c = j * 32 + lane;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (c < n_chunks) v = qrow[c];
+        if constexpr (kFloat)
+            Storage<ST>::unpack(v, &qf[j * E]);
+        else
+            qc[j] = v;
+    }
+    const float qn = a.q_nrm[q];
+    unsigned long long n_evals = 0, n_parents = 0;
+    __syncthreads();
+
+    struct Group {
+        uint4 x[U][CPL];
+        float xn[U];
+    };
+    // this warp's m-th queue entry is index warp + 8*m
+    auto load_group = [&](Group& g, uint32_t m0, uint32_t n_new) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t idx = warp + K4B_WARPS * (m0 + u);
+            const bool on = idx < n_new;
+            const uint32_t slot = on ? newq[idx] : 0u;
+            const uint4* xrow = reinterpret_cast<const uint4*>(a.x_rows + (size_t)slot * a.x_row_bytes);
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const int c = j * 32 + lane;
+                g.x[u][j] = make_uint4(0, 0, 0, 0);
+                if (on && c < n_chunks) g.x[u][j] = ldg_nc_v4(xrow + c);
+            }
+            g.xn[u] = (on && is_cos) ? __ldg(a.x_nrm + slot) : 0.0f;
+        }
+    };
+    auto compute_group = [&](const Group& g, uint32_t m0, uint32_t n_new) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t idx = warp + K4B_WARPS * (m0 + u);
+            if (idx >= n_new) continue;
+            float facc = 0.0f;
+            int iacc = 0;
+            if constexpr (kFloat) {
+                if (is_l2) {
+                    ChunkAcc<ST, VSB_METRIC_L2SQ> acc;
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) {
+                        float xf[E];
+                        Storage<ST>::unpack(g.x[u][j], xf);
+                        acc.add_f(&qf[j * E], xf);
+                    }
+                    facc = acc.f;
+                } else {
+                    ChunkAcc<ST, VSB_METRIC_IP> acc;
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) {
+                        float xf[E];
+                        Storage<ST>::unpack(g.x[u][j], xf);
+                        acc.add_f(&qf[j * E], xf);
+                    }
+                    facc = acc.f;
+                }
+                facc = butterfly_sum(facc);
+            } else {
+                if (is_l2) {
+                    ChunkAcc<ST, VSB_METRIC_L2SQ> acc;
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) acc.add(qc[j], g.x[u][j]);
+                    iacc = acc.i;
+                } else {
+                    ChunkAcc<ST, VSB_METRIC_IP> acc;
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) acc.add(qc[j], g.x[u][j]);
+                    iacc = acc.i;
+                }
+                iacc = butterfly_sum_i(iacc);
+            }
+            float d;
+            if constexpr (ST == VSB_ST_B1) {
+                d = finish_distance<ST, VSB_METRIC_HAMMING>(facc, iacc, 0.0f, 0.0f);
+            } else {
+                if (is_l2)
+                    d = finish_distance<ST, VSB_METRIC_L2SQ>(facc, iacc, 0.0f, 0.0f);
+                else if (is_cos)
+                    d = finish_distance<ST, VSB_METRIC_COS>(facc, iacc, qn, g.xn[u]);
+                else
+                    d = finish_distance<ST, VSB_METRIC_IP>(facc, iacc, 0.0f, 0.0f);
+            }
+            if (lane == 0) newd[idx] = d;
+        }
+    };
+    // all warps: evaluate the queue, sort it in groups of 32, warp 0 folds the groups into the list
+    auto evaluate_queue = [&]() {
+        __syncthreads();
+        const uint32_t n_new = ctrl[0];
+        if (n_new != 0) {
+            const uint32_t mine = n_new > (uint32_t)warp ? (n_new - warp + K4B_WARPS - 1) / K4B_WARPS : 0;
+            if (mine) {
+                Group ga, gb;
+                load_group(ga, 0, n_new);
+                for (uint32_t m0 = 0; m0 < mine; m0 += 2 * U) {
+                    const bool has_b = m0 + U < mine;
+                    if (has_b) load_group(gb, m0 + U, n_new);
+                    compute_group(ga, m0, n_new);
+                    if (has_b) {
+                        if (m0 + 2 * U < mine) load_group(ga, m0 + 2 * U, n_new);
+                        compute_group(gb, m0 + U, n_new);
+                    }
+                }
+            }
+            __syncthreads();
+            for (uint32_t g = warp; g * 32 < n_new; g += K4B_WARPS) {
+                uint64_t res = kInvalidPacked;
+                if (g * 32 + lane < n_new) res = pack_ds(newd[g * 32 + lane], newq[g * 32 + lane]);
+                newp[g * 32 + lane] = warp_sort32(res, lane, less);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                for (uint32_t g = 0; g * 32 < n_new; ++g) warp_list_merge(list, (int)a.itopk, newp[g * 32 + lane], lane, less);
+                if (lane == 0) {
+                    ctrl[2] += n_new;
+                    ctrl[0] = 0;
+                }
+                n_evals += n_new;
+            }
+        }
+        __syncthreads();
+    };
+
+    // ---- seeds (warp 0) ----
+    if (warp == 0) {
+        uint64_t sv = kInvalidPacked;
+        for (uint32_t s = 0; s < a.seed_splits; ++s) {
+            uint64_t v = a.seed_lists[((size_t)q * a.seed_splits + s) * 32 + lane];
+            v = warp_sort32(v, lane, less);
+            const uint64_t rc = shfl_u64(v, 31 - lane);
+            sv = warp_bitonic_merge32(rc < sv ? rc : sv, lane, less);
+        }
+        uint32_t nb = kInvalidSlot;
+        if (lane < (int)a.n_seeds && sv != kInvalidPacked) nb = a.seed_slots[packed_lo(sv)];
+        bool is_new = false;
+        if (nb != kInvalidSlot) is_new = hash_insert(hash, hmask, a.hash_bits, nb);
+        const uint32_t m = __ballot_sync(kFullMask, is_new);
+        if (is_new) newq[__popc(m & ((1u << lane) - 1))] = nb;
+        if (lane == 0) ctrl[0] = __popc(m);
+    }
+    evaluate_queue();
+
+    const uint32_t width = a.search_width;
+    const uint32_t deg_pad = ((a.degree + 31) / 32) * 32;
+    for (uint32_t it = 0; it < a.max_iters; ++it) {
+        if (ctrl[2] > (hsize >> 2) * 3) {  // uniform: written before the last barrier
+            __syncthreads();
+            for (uint32_t i = tid; i < hsize; i += K4B_WARPS * 32) hash[i] = kHashEmpty;
+            __syncthreads();
+            uint32_t cnt = 0;
+            for (uint32_t i = tid; i < a.itopk; i += K4B_WARPS * 32) {
+                const uint64_t e = list[i];
+                if (e != kInvalidPacked) {
+                    hash_insert(hash, hmask, a.hash_bits, packed_lo(e) & ~kExpandedBit);
+                    ++cnt;
+                }
+            }
+            if (tid == 0) ctrl[2] = 0;
+            __syncthreads();
+            if (cnt) atomicAdd(&ctrl[2], cnt);
+            __syncthreads();
+        }
+        if (warp == 0) {
+            uint32_t np = 0;
+            for (uint32_t b = 0; b < a.itopk && np < width; b += 32) {
+                const uint64_t e = list[b + lane];
+                const bool unexp = e != kInvalidPacked && !(packed_lo(e) & kExpandedBit);
+                uint32_t m = __ballot_sync(kFullMask, unexp);
+                bool mine = false;
+                while (m && np < width) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (lane == src) {
+                        par[np] = packed_lo(e);
+                        mine = true;
+                    }
+                    ++np;
+                }
+                if (mine) list[b + lane] = e | kExpandedBit;
+            }
+            if (lane == 0) ctrl[1] = np;
+            n_parents += np;
+        }
+        __syncthreads();
+        const uint32_t np = ctrl[1];
+        if (np == 0) break;
+        for (uint32_t t = tid; t < np * deg_pad; t += K4B_WARPS * 32) {
+            const uint32_t i = t / deg_pad, r = t % deg_pad;
+            if (r < a.degree) {
+                const uint32_t nb = __ldg(a.graph + (size_t)par[i] * a.graph_stride + r);
+                if (nb != kInvalidSlot && hash_insert(hash, hmask, a.hash_bits, nb)) newq[atomicAdd(&ctrl[0], 1u)] = nb;
+            }
+        }
+        evaluate_queue();
+    }
+
+    // ---- emit (warp 0) ----
+    if (warp == 0) {
+        uint32_t count = 0;
+        for (uint32_t b = 0; b < a.itopk; b += 32) {
+            const uint64_t e = list[b + lane];
+            const uint32_t slot = packed_lo(e) & ~kExpandedBit;
+            bool valid = e != kInvalidPacked;
+            if (valid && a.deny != nullptr && bit_test(a.deny, slot)) valid = false;
+            const uint32_t m = __ballot_sync(kFullMask, valid);
+            const uint32_t pos = count + __popc(m & ((1u << lane) - 1));
+            if (valid && pos < a.k) {
+                a.out_keys[(size_t)q * a.k + pos] = a.keys[slot];
+                a.out_dists[(size_t)q * a.k + pos] = ord_to_f32(packed_hi(e));
+            }
+            count += __popc(m);
+        }
+        if (count > a.k) count = a.k;
+        for (uint32_t i = count + lane; i < a.k; i += 32) {
+            a.out_keys[(size_t)q * a.k + i] = 0xFFFFFFFFFFFFFFFFull;
+            a.out_dists[(size_t)q * a.k + i] = __int_as_float(0x7F800000);
+        }
+        if (lane == 0) {
+            if (a.out_counts != nullptr) a.out_counts[q] = count;
+            if (a.counters != nullptr) {
+                atomicAdd(&a.counters[0], n_evals);
+                atomicAdd(&a.counters[1], n_parents);
+            }
+        }
+    }
+}
+
+// Seed layer for tiny batches: every warp scans 4 seed rows with the canonical distance, every CTA
+// emits its best row -> [q][blocks][32] packed winners (the format K4 consumes).
+constexpr int SEED_SCAN_WARPS = 8;
+constexpr int SEED_SCAN_ROWS_PER_WARP = 4;
+
+template <int ST>
+__global__ void __launch_bounds__(SEED_SCAN_WARPS * 32) seed_scan_kernel(const uint8_t* __restrict__ q_rows,
+                                                                          const float* __restrict__ q_nrm,
+                                                                          uint32_t q_row_bytes,
+                                                                          const uint8_t* __restrict__ s_rows,
+                                                                          const float* __restrict__ s_nrm,
+                                                                          uint32_t n_seed_rows, uint32_t row_bytes,
+                                                                          int metric, uint32_t n_blocks,
+                                                                          uint64_t* __restrict__ out) {
+    __shared__ uint64_t best[SEED_SCAN_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.y;
+    const uint4* qrow = reinterpret_cast<const uint4*>(q_rows + (size_t)q * q_row_bytes);
+    const float qn = q_nrm[q];
+    const int n_chunks = row_bytes / 16;
+    const uint32_t r0 = (blockIdx.x * SEED_SCAN_WARPS + warp) * SEED_SCAN_ROWS_PER_WARP;
+    uint64_t mine = kInvalidPacked;
+#pragma unroll
+    for (int i = 0; i < SEED_SCAN_ROWS_PER_WARP; ++i) {
+        const uint32_t r = r0 + i;
+        if (r >= n_seed_rows) break;
+        const uint4* xrow = reinterpret_cast<const uint4*>(s_rows + (size_t)r * row_bytes);
+        float d;
+        if constexpr (ST == VSB_ST_B1) {
+            d = warp_distance<ST, VSB_METRIC_HAMMING>(qrow, xrow, n_chunks, qn, 0.0f, lane);
+        } else {
+            if (metric == VSB_METRIC_L2SQ) d = warp_distance<ST, VSB_METRIC_L2SQ>(qrow, xrow, n_chunks, qn, 0.0f, lane);
+            else if (metric == VSB_METRIC_IP) d = warp_distance<ST, VSB_METRIC_IP>(qrow, xrow, n_chunks, qn, 0.0f, lane);
+            else d = warp_distance<ST, VSB_METRIC_COS>(qrow, xrow, n_chunks, qn, s_nrm[r], lane);
+        }
+        const uint64_t p = pack_ds(d, r);
+        mine = p < mine ? p : mine;
+    }
+    if (lane == 0) best[warp] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t b = best[0];
+        for (int w = 1; w < SEED_SCAN_WARPS; ++w) b = best[w] < b ? best[w] : b;
+        out[(size_t)q * n_blocks * 32 + blockIdx.x] = b;
+    }
+}
+
 template <int ST, int CPL>
 void launch_k4_inst(const K4Args& a, dim3 grid, size_t smem, cudaStream_t stream) {
     cudaFuncSetAttribute(graph_search_kernel<ST, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     graph_search_kernel<ST, CPL><<<grid, K4_WARPS * 32, smem, stream>>>(a);
+}
+
+template <int ST, int CPL>
+void launch_k4b_inst(const K4Args& a, dim3 grid, size_t smem, cudaStream_t stream) {
+    cudaFuncSetAttribute(graph_search_cta_kernel<ST, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    graph_search_cta_kernel<ST, CPL><<<grid, K4B_WARPS * 32, smem, stream>>>(a);
+}
+
+template <int ST>
+void launch_k4b_storage(const K4Args& a, int cpl, dim3 grid, size_t smem, cudaStream_t stream) {
+    switch (cpl) {
+        case 1: launch_k4b_inst<ST, 1>(a, grid, smem, stream); break;
+        case 2: launch_k4b_inst<ST, 2>(a, grid, smem, stream); break;
+        case 3: launch_k4b_inst<ST, 3>(a, grid, smem, stream); break;
+        case 4: launch_k4b_inst<ST, 4>(a, grid, smem, stream); break;
+        case 6: launch_k4b_inst<ST, 6>(a, grid, smem, stream); break;
+        case 8: launch_k4b_inst<ST, 8>(a, grid, smem, stream); break;
+        default: launch_k4b_inst<ST, 12>(a, grid, smem, stream); break;
+    }
+}
+
+struct SeedScanArgs {
+    const uint8_t* q_rows; const float* q_nrm; uint32_t nq, q_row_bytes;
+    const uint8_t* s_rows; const float* s_nrm; uint32_t n_seed_rows, row_bytes;
+    int metric; uint32_t n_blocks; uint64_t* out;
+};
+template <int ST>
+void launch_seed_scan_storage(const SeedScanArgs& s, cudaStream_t stream) {
+    const uint32_t ctas = (s.n_seed_rows + SEED_SCAN_WARPS * SEED_SCAN_ROWS_PER_WARP - 1) /
+                          (SEED_SCAN_WARPS * SEED_SCAN_ROWS_PER_WARP);
+    seed_scan_kernel<ST><<<dim3(ctas, s.nq), SEED_SCAN_WARPS * 32, 0, stream>>>(
+        s.q_rows, s.q_nrm, s.q_row_bytes, s.s_rows, s.s_nrm, s.n_seed_rows, s.row_bytes, s.metric, s.n_blocks, s.out);
 }
 
 // one translation unit per storage scalar instantiates this
@@ -343,6 +694,14 @@ void launch_k4_storage(const K4Args& a, int cpl, dim3 grid, size_t smem, cudaStr
     }
 }
 
+#define VSB_K4_DECL(name)                                                                              \
+    void launch_k4b_##name(const K4Args& a, int cpl, dim3 grid, size_t smem, cudaStream_t stream);     \
+    void launch_seed_scan_##name(const SeedScanArgs& s, cudaStream_t stream);
+VSB_K4_DECL(f32)
+VSB_K4_DECL(f16)
+VSB_K4_DECL(bf16)
+VSB_K4_DECL(i8)
+VSB_K4_DECL(b1)
 void launch_k4_f32(const K4Args& a, int cpl, dim3 grid, size_t smem, cudaStream_t stream);
 void launch_k4_f16(const K4Args& a, int cpl, dim3 grid, size_t smem, cudaStream_t stream);
 void launch_k4_bf16(const K4Args& a, int cpl, dim3 grid, size_t smem, cudaStream_t stream);

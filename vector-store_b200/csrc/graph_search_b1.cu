@@ -1,8 +1,12 @@
-// graph_search_b1.cu — K4 instantiations for the b1 storage scalar (see graph_search.cuh).
+// graph_search_b1.cu — K4 / K4b / seed-scan instantiations for the b1 storage scalar (see graph_search.cuh).
 #include "graph_search.cuh"
 
 namespace vsb {
 void launch_k4_b1(const K4Args& a, int cpl, dim3 grid, size_t smem, cudaStream_t stream) {
     launch_k4_storage<VSB_ST_B1>(a, cpl, grid, smem, stream);
 }
+void launch_k4b_b1(const K4Args& a, int cpl, dim3 grid, size_t smem, cudaStream_t stream) {
+    launch_k4b_storage<VSB_ST_B1>(a, cpl, grid, smem, stream);
+}
+void launch_seed_scan_b1(const SeedScanArgs& s, cudaStream_t stream) { launch_seed_scan_storage<VSB_ST_B1>(s, stream); }
 }  // namespace vsb

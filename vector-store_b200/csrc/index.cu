@@ -394,6 +394,12 @@ vsb_status vsb_index::build() {
         shx.sq = sh_sq.as<float>();
         shx.nrm = sh_nrm.as<float>();
     }
+    const bool btime = getenv("VSB_BUILD_TIMING") != nullptr;
+    cudaEvent_t ev[6];
+    if (btime) {
+        for (auto& e : ev) cudaEventCreate(&e);
+        cudaEventRecord(ev[0], stream);
+    }
     const uint32_t QB = 16384;
     for (uint32_t b0 = 0; b0 < n; b0 += QB) {
         vsb::RowsView q;
@@ -416,22 +422,34 @@ vsb_status vsb_index::build() {
     sh_rows.release();
     sh_sq.release();
     sh_nrm.release();
+    if (btime) cudaEventRecord(ev[1], stream);
     CU(fwd.ensure((size_t)n * R * 4));
     CU(rev.ensure((size_t)n * R * 4));
     CU(rev_cnt.ensure((size_t)n * 4));
     vsb::launch_prune_detour(knn.as<uint64_t>(), n, kin, R, deny_bm, fwd.as<uint32_t>(), stream);
     CU(cudaGetLastError());
+    if (btime) cudaEventRecord(ev[2], stream);
     const size_t sb = vsb::reverse_edges_scratch_bytes(n, R);
     CU(scratch.ensure(sb));
     vsb::launch_reverse_edges(fwd.as<uint32_t>(), n, R, rev.as<uint32_t>(), rev_cnt.as<uint32_t>(), scratch.p,
                               scratch.bytes, stream);
     CU(cudaGetLastError());
+    if (btime) cudaEventRecord(ev[3], stream);
     DevBuf new_graph;
     CU(new_graph.ensure((size_t)n * graph_stride * 4));
     vsb::launch_merge_graph(fwd.as<uint32_t>(), rev.as<uint32_t>(), rev_cnt.as<uint32_t>(), n, R,
                             new_graph.as<uint32_t>(), graph_stride, stream);
     CU(cudaGetLastError());
 
+    if (btime) {
+        cudaEventRecord(ev[4], stream);
+        cudaEventSynchronize(ev[4]);
+        float t[4];
+        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+        fprintf(stderr, "[vsb200 build] n=%u knn(K1+K3)=%.1f ms prune=%.1f ms reverse=%.1f ms merge=%.1f ms\n", n, t[0], t[1],
+                t[2], t[3]);
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
     // entry-point sample: a stride permutation of the live slots (deterministic, seed-shifted)
     uint32_t S = 256;
     const double target = 4.0 * std::sqrt((double)live);
@@ -570,6 +588,8 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
             } else {
                 sp.n_splits = vsb::exact_pick_splits(nb, n_seed_rows, sm_count);
             }
+            const bool seed_scan = !seed_tc && nb <= vsb::graph_search_small_batch();
+            if (seed_scan) sp.n_splits = vsb::seed_scan_blocks(n_seed_rows);
             CU(seed_part.ensure(vsb::exact_part_elems(nb, sp.n_splits, 32) * 8));
             sp.part = seed_part.as<uint64_t>();
             t_begin(PH_SEED, s);
@@ -581,7 +601,13 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
                 sp.x.sq = seed_sq.as<float>();
                 sp.x.nrm = seed_nrm.as<float>();
                 sp.x.row_bytes = row_bytes;
-                vsb::launch_exact_candidates(sp, s);
+                if (seed_scan) {
+                    // tiny batch: one warp per 4 seed rows, one winner per CTA
+                    CU(cudaMemsetAsync(seed_part.p, 0xFF, vsb::exact_part_elems(nb, sp.n_splits, 32) * 8, s));
+                    vsb::launch_seed_scan(storage, metric, qv, sp.x, seed_part.as<uint64_t>(), s);
+                } else {
+                    vsb::launch_exact_candidates(sp, s);
+                }
             }
             t_end(s);
             CU(cudaGetLastError());

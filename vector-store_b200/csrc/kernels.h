@@ -90,6 +90,10 @@ struct SearchParams {
 };
 void launch_graph_search(const SearchParams& p, cudaStream_t stream);
 bool graph_search_supported(uint32_t row_bytes);  // rows up to 6144 bytes
+uint32_t graph_search_small_batch();
+uint32_t seed_scan_blocks(uint32_t n_seed_rows);
+void launch_seed_scan(int storage, int metric, const RowsView& q, const RowsView& seeds, uint64_t* out,
+                      cudaStream_t stream);
 
 // K8 (merge.cu) ----------------------------------------------------------------------------------
 void launch_merge_topk(const uint64_t* keys, const float* dists, uint32_t parts, uint64_t q, uint32_t k,
