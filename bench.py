@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--target-recall", type=float, default=0.95)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="corpus rows of the bounded CPU-baseline sample")
     ap.add_argument("--search-width", type=int, default=1)
+    ap.add_argument("--traversal", default="bf16", choices=["bf16", "native"],
+                    help="f32 storage: traverse a bf16 copy and re-rank the best candidates on the f32 rows")
     ap.add_argument("--cpu-queries", type=int, default=2_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -213,7 +215,8 @@ def main():
     n_local = hi - lo
 
     # ---- corpus shard: generated and ingested chunk by chunk (host RAM stays bounded) ----
-    idx = v.GpuIndex(a.dim, v.Metric.Cos, scalar, device=local_rank)
+    trav16 = a.storage == "f32" and a.traversal == "bf16"
+    idx = v.GpuIndex(a.dim, v.Metric.Cos, scalar, device=local_rank, bf16_traversal=trav16)
     idx.reserve(n_local)
     t_gen = 0.0
     t_add = 0.0
@@ -301,7 +304,8 @@ def main():
     idx.set_instrumented(False)
     E = st["distance_evals"] / max(st["queries"], 1)
     P = st["parent_expansions"] / max(st["queries"], 1)
-    bytes_per_query = E * (st["row_bytes"] + 4) + P * st["graph_degree"] * 4  # +4: the row's norm (cosine)
+    trav_row_bytes = st["row_bytes"] // 2 if trav16 else st["row_bytes"]
+    bytes_per_query = E * (trav_row_bytes + 4) + P * st["graph_degree"] * 4  # +4: the row's norm (cosine)
 
     # ---- timed region 1: inputs resident in HBM ----
     for i in range(a.warmup):
@@ -378,6 +382,8 @@ def main():
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": a.storage, "data": "synthetic",
         "config": {"workload": workload_name(a), "index": "M=16 (degree 32) ef_add=128",
+                   "traversal": ("bf16 copy of the f32 rows for the graph traversal, fp32 re-rank of the best "
+                                 "candidates on the f32 rows" if trav16 else "native storage scalar"),
                    "expansion_search": ef_used, "search_width": a.search_width,
                    "recall_at_10": round(recall_timed, 4), "ef_sweep": sweep,
                    "parallelism": f"corpus sharded over {world} GPU(s), all-gather top-k merge" if world > 1 else "1 GPU",

@@ -67,6 +67,10 @@ typedef struct {
 } vsb_options;
 
 #define VSB_FLAG_NONE 0u
+/* f32 storage only: keep a bf16 copy of every row for the graph traversal (K4 reads half the bytes);
+ * the best candidates are then re-ranked on the f32 rows (K3), so returned distances stay the
+ * canonical fp32 distances of the stored vectors.  Costs +50 % HBM for the rows. */
+#define VSB_FLAG_BF16_TRAVERSAL 1u
 
 /* Runtime tunables of the graph search (all 0 = keep current). */
 typedef struct {

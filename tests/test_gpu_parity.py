@@ -406,3 +406,29 @@ def test_small_batch_paths_cta_per_query(storage, dim):
         od = O.distance_matrix(x[(gk[0] - np.uint64(5 << 48)).astype(np.int64)], q[:1], O.COS, storage)[0]
         assert np.array_equal(gd[0].view(np.uint32), od.view(np.uint32))
     assert O.recall_at_k(big_k, tk) >= 0.95
+
+
+def test_bf16_traversal_flag_keeps_fp32_distances():
+    # VSB_FLAG_BF16_TRAVERSAL: K4 walks a bf16 copy, K3 re-ranks on the f32 rows => canonical f32 distances
+    n, dim, k = 30000, 768, 10
+    x = embedding_like(n, dim, n_clusters=64)
+    q = embedding_like(400, dim, seed=4321, n_clusters=64)
+    keys = np.arange(n, dtype=np.uint64)
+    v = V()
+    idx = v.GpuIndex(dim, v.Metric.Cos, v.Scalar.F32, bf16_traversal=True)
+    idx.reserve(n + 100)
+    idx.add_batch(keys, x)
+    idx.build()
+    tk, td, _ = idx.search_batch(q, k, exact=True)
+    ok, od, _, _ = O.exact_topk(x, q[:8], k, O.COS, O.F32, keys=keys)
+    assert np.array_equal(tk[:8], ok) and np.array_equal(td[:8].view(np.uint32), od.view(np.uint32))
+    for nq in (400, 3):
+        gk, gd, gc = idx.search_batch(q[:nq], k)
+        r = O.recall_at_k(gk, tk[:nq])
+        print(f"bf16 traversal, batch {nq}: recall@10 = {r:.4f}")
+        assert np.all(gc == k) and np.all(np.diff(gd, axis=1) >= 0) and r >= 0.95
+        d0 = O.distance_matrix(x[gk[0].astype(np.int64)], q[:1], O.COS, O.F32)[0]
+        assert np.array_equal(gd[0].view(np.uint32), d0.view(np.uint32))
+    idx.add_batch(np.arange(n, n + 50, dtype=np.uint64), q[:50])  # tail + traversal copy stay in sync
+    gk, gd, _ = idx.search_batch(q[:50], 1)
+    assert np.array_equal(gk[:, 0], np.arange(n, n + 50, dtype=np.uint64))

@@ -137,7 +137,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return d;
 }
 
-template <int KIND, int METRIC>
+template <int KIND, int METRIC, bool TILE_MIN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     exact_candidates_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                                TcArgs a) {
@@ -261,6 +261,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         __syncwarp();
         float thr = q_valid ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
         int cnt = 0;
+        const uint32_t* deny = a.deny;
+        const uint32_t* allow = a.allow;
+        const uint64_t* keys = a.keys;
+        const uint64_t allow_bits = a.allow_bits;
 
         auto flush = [&](uint32_t need_mask) {
             __syncwarp();  // make every lane's buffered candidates visible to the warp
@@ -289,7 +293,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
             const uint32_t n0 = r_lo + t * TC_N;
             float best_d = __int_as_float(0x7F800000);
-            uint32_t best_n = kInvalidSlot;
+            uint32_t best_c = kInvalidSlot;
             // per-column parameter of this tile (NaN marks columns outside the split)
             float* cp = colp + acc * TC_N;
             for (int c = etid; c < TC_N; c += 128) {
@@ -312,43 +316,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             for (int ch = 0; ch < TC_N / 32; ++ch) {
                 uint32_t v[32];
                 tmem_ld32(taddr + ch * 32, v);
+                // fast path: branch-free distance + threshold test of 32 columns (~4 instructions each)
+                const float4* cp4 = reinterpret_cast<const float4*>(cp + ch * 32);
+                float d[32];
+                uint32_t mask = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float dot = __uint_as_float(v[j]);
-                    const float p = cp[ch * 32 + j];
-                    float d;
-                    if constexpr (METRIC == VSB_METRIC_L2SQ) d = fmaf(dot, -2.0f, p) + qsq;
-                    else if constexpr (METRIC == VSB_METRIC_COS) d = fmaf(dot * p, -inv_qn, 1.0f);
-                    else d = fmaf(dot, -1.0f, p);
-                    if (a.tile_min) {
-                        if (d < best_d) {
-                            best_d = d;
-                            best_n = n0 + ch * 32 + j;
-                        }
-                        continue;
-                    }
-                    if (d <= thr) {
-                        const uint32_t n = n0 + ch * 32 + j;
-                        bool ok = true;
-                        if (a.deny != nullptr && bit_test(a.deny, n)) ok = false;
-                        if (ok && a.allow != nullptr) {
-                            const uint64_t rid = a.keys[n] & kRowMask48;
-                            ok = rid < a.allow_bits && bit_test(a.allow, (uint32_t)rid);
-                        }
-                        if (ok) {
-                            if constexpr (METRIC == VSB_METRIC_L2SQ) d = fmaxf(d, 0.0f);
-                            if constexpr (METRIC == VSB_METRIC_COS) d = fminf(fmaxf(d, 0.0f), 2.0f);
-                            my_buf[cnt++] = pack_ds(d, n);
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 p4 = cp4[j4];
+                    const float pj[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = j4 * 4 + jj;
+                        const float dot = __uint_as_float(v[j]);
+                        if constexpr (METRIC == VSB_METRIC_L2SQ) d[j] = fmaf(dot, -2.0f, pj[jj]) + qsq;
+                        else if constexpr (METRIC == VSB_METRIC_COS) d[j] = fmaf(dot * pj[jj], -inv_qn, 1.0f);
+                        else d[j] = fmaf(dot, -1.0f, pj[jj]);
+                        if constexpr (TILE_MIN) {
+                            const bool lt = d[j] < best_d;
+                            best_d = lt ? d[j] : best_d;
+                            best_c = lt ? (uint32_t)(ch * 32 + j) : best_c;
+                        } else {
+                            mask |= (d[j] <= thr) ? (1u << j) : 0u;
                         }
                     }
                 }
-                const uint32_t need = __ballot_sync(kFullMask, cnt > TC_BUFCAP - 32);
-                if (need) flush(need);
+                if constexpr (!TILE_MIN) {
+                    if (mask) {  // rare once the row's threshold has tightened
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (mask & (1u << j)) {
+                                const uint32_t n = n0 + ch * 32 + j;
+                                bool ok = true;
+                                if (deny != nullptr && bit_test(deny, n)) ok = false;
+                                if (ok && allow != nullptr) {
+                                    const uint64_t rid = keys[n] & kRowMask48;
+                                    ok = rid < allow_bits && bit_test(allow, (uint32_t)rid);
+                                }
+                                if (ok) {
+                                    float dd = d[j];
+                                    if constexpr (METRIC == VSB_METRIC_L2SQ) dd = fmaxf(dd, 0.0f);
+                                    if constexpr (METRIC == VSB_METRIC_COS) dd = fminf(fmaxf(dd, 0.0f), 2.0f);
+                                    my_buf[cnt++] = pack_ds(dd, n);
+                                }
+                            }
+                        }
+                    }
+                    const uint32_t need = __ballot_sync(kFullMask, cnt > TC_BUFCAP - 32);
+                    if (need) flush(need);
+                }
             }
-            if (a.tile_min && q_valid && best_n != kInvalidSlot && t < a.kp) {
-                if constexpr (METRIC == VSB_METRIC_L2SQ) best_d = fmaxf(best_d, 0.0f);
-                if constexpr (METRIC == VSB_METRIC_COS) best_d = fminf(fmaxf(best_d, 0.0f), 2.0f);
-                a.part[((size_t)q * a.n_splits + split) * a.kp + t] = pack_ds(best_d, best_n);
+            if constexpr (TILE_MIN) {
+                if (q_valid && best_c != kInvalidSlot && t < a.kp) {
+                    if constexpr (METRIC == VSB_METRIC_L2SQ) best_d = fmaxf(best_d, 0.0f);
+                    if constexpr (METRIC == VSB_METRIC_COS) best_d = fminf(fmaxf(best_d, 0.0f), 2.0f);
+                    a.part[((size_t)q * a.n_splits + split) * a.kp + t] = pack_ds(best_d, n0 + best_c);
+                }
             }
             // accumulator drained: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
@@ -402,9 +424,15 @@ bool make_map(CUtensorMap* map, int kind, const void* base, uint32_t rows, uint3
 
 template <int KIND, int METRIC>
 void launch_tc_inst(const CUtensorMap& mq, const CUtensorMap& mx, const TcArgs& a, dim3 grid, cudaStream_t stream) {
-    cudaFuncSetAttribute(exact_candidates_tc_kernel<KIND, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)TC_SMEM_BYTES);
-    exact_candidates_tc_kernel<KIND, METRIC><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mq, mx, a);
+    if (a.tile_min) {
+        cudaFuncSetAttribute(exact_candidates_tc_kernel<KIND, METRIC, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+        exact_candidates_tc_kernel<KIND, METRIC, true><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mq, mx, a);
+    } else {
+        cudaFuncSetAttribute(exact_candidates_tc_kernel<KIND, METRIC, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+        exact_candidates_tc_kernel<KIND, METRIC, false><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mq, mx, a);
+    }
 }
 
 template <int KIND>

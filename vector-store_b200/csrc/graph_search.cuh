@@ -39,6 +39,7 @@ struct K4Args {
     uint64_t* out_keys;
     float* out_dists;
     uint32_t* out_counts;
+    uint64_t* out_packed;  // if set: emit the first k live entries as packed (ord(dist)<<32 | slot) for K3 instead of keys
     unsigned long long* counters;
 };
 
@@ -304,15 +305,23 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
         const uint32_t m = __ballot_sync(kFullMask, valid);
         const uint32_t pos = count + __popc(m & ((1u << lane) - 1));
         if (valid && pos < a.k) {
-            a.out_keys[(size_t)q * a.k + pos] = a.keys[slot];
-            a.out_dists[(size_t)q * a.k + pos] = ord_to_f32(packed_hi(e));
+            if (a.out_packed != nullptr) {
+                a.out_packed[(size_t)q * a.k + pos] = ((uint64_t)packed_hi(e) << 32) | slot;
+            } else {
+                a.out_keys[(size_t)q * a.k + pos] = a.keys[slot];
+                a.out_dists[(size_t)q * a.k + pos] = ord_to_f32(packed_hi(e));
+            }
         }
         count += __popc(m);
     }
     if (count > a.k) count = a.k;
     for (uint32_t i = count + lane; i < a.k; i += 32) {
-        a.out_keys[(size_t)q * a.k + i] = 0xFFFFFFFFFFFFFFFFull;
-        a.out_dists[(size_t)q * a.k + i] = __int_as_float(0x7F800000);
+        if (a.out_packed != nullptr) {
+            a.out_packed[(size_t)q * a.k + i] = kInvalidPacked;
+        } else {
+            a.out_keys[(size_t)q * a.k + i] = 0xFFFFFFFFFFFFFFFFull;
+            a.out_dists[(size_t)q * a.k + i] = __int_as_float(0x7F800000);
+        }
     }
     if (lane == 0) {
         if (a.out_counts != nullptr) a.out_counts[q] = count;
@@ -575,15 +584,23 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
             const uint32_t m = __ballot_sync(kFullMask, valid);
             const uint32_t pos = count + __popc(m & ((1u << lane) - 1));
             if (valid && pos < a.k) {
-                a.out_keys[(size_t)q * a.k + pos] = a.keys[slot];
-                a.out_dists[(size_t)q * a.k + pos] = ord_to_f32(packed_hi(e));
+                if (a.out_packed != nullptr) {
+                    a.out_packed[(size_t)q * a.k + pos] = ((uint64_t)packed_hi(e) << 32) | slot;
+                } else {
+                    a.out_keys[(size_t)q * a.k + pos] = a.keys[slot];
+                    a.out_dists[(size_t)q * a.k + pos] = ord_to_f32(packed_hi(e));
+                }
             }
             count += __popc(m);
         }
         if (count > a.k) count = a.k;
         for (uint32_t i = count + lane; i < a.k; i += 32) {
-            a.out_keys[(size_t)q * a.k + i] = 0xFFFFFFFFFFFFFFFFull;
-            a.out_dists[(size_t)q * a.k + i] = __int_as_float(0x7F800000);
+            if (a.out_packed != nullptr) {
+                a.out_packed[(size_t)q * a.k + i] = kInvalidPacked;
+            } else {
+                a.out_keys[(size_t)q * a.k + i] = 0xFFFFFFFFFFFFFFFFull;
+                a.out_dists[(size_t)q * a.k + i] = __int_as_float(0x7F800000);
+            }
         }
         if (lane == 0) {
             if (a.out_counts != nullptr) a.out_counts[q] = count;

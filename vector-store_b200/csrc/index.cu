@@ -113,6 +113,10 @@ struct vsb_index {
     bool any_tombstone = false;
 
     DevBuf rows, sq, nrm, keys, deny, graph;
+    DevBuf rows16, sq16, nrm16;   // VSB_FLAG_BF16_TRAVERSAL: bf16 copy of the rows for K4
+    bool trav16 = false;
+    uint32_t row_bytes16 = 0;
+    DevBuf rr_packed;             // K4 -> K3 hand-over of the traversal shadow path
     DevBuf seed_rows, seed_sq, seed_nrm, seed_slots;
     DevBuf seed16_rows, seed16_sq, seed16_nrm;   // bf16 shadow of the seed block (f32 storage only)
     DevBuf q16_rows, q16_sq, q16_nrm;            // bf16 shadow of the converted queries (f32 storage only)
@@ -156,7 +160,7 @@ struct vsb_index {
     }
 
     size_t hbm_bytes() const {
-        const DevBuf* all[] = {&rows, &sq, &nrm, &keys, &deny, &graph, &seed_rows, &seed_sq, &seed_nrm, &seed_slots,
+        const DevBuf* all[] = {&rows, &sq, &nrm, &keys, &deny, &graph, &rows16, &sq16, &nrm16, &rr_packed, &seed_rows, &seed_sq, &seed_nrm, &seed_slots,
                                &seed16_rows, &seed16_sq, &seed16_nrm, &q16_rows, &q16_sq, &q16_nrm,
                                &q_in, &q_rows, &q_sq, &q_nrm, &part, &seed_part, &tmp_keys, &tmp_dists, &counters,
                                &add_in, &allow};
@@ -217,7 +221,7 @@ vsb_status vsb_index::reserve(uint64_t cap) {
     if (cap >= (1ull << 28)) return fail(VSB_EINVAL, "capacity %llu exceeds the 2^28 rows one shard holds", (unsigned long long)cap);
     CU(cudaSetDevice(device));
     const uint64_t words = (cap + 31) / 32;
-    DevBuf n_rows, n_sq, n_nrm, n_keys, n_deny;
+    DevBuf n_rows, n_sq, n_nrm, n_keys, n_deny, n_rows16, n_sq16, n_nrm16;
     auto alloc = [&](DevBuf& b, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(&b.p, bytes ? bytes : 16);
         if (e == cudaSuccess) b.bytes = bytes ? bytes : 16; else b.p = nullptr;
@@ -228,6 +232,11 @@ vsb_status vsb_index::reserve(uint64_t cap) {
     CU(alloc(n_nrm, cap * 4));
     CU(alloc(n_keys, cap * 8));
     CU(alloc(n_deny, words * 4));
+    if (trav16) {
+        CU(alloc(n_rows16, cap * row_bytes16));
+        CU(alloc(n_sq16, cap * 4));
+        CU(alloc(n_nrm16, cap * 4));
+    }
     ST(use_stream(stream));
     CU(cudaMemsetAsync(n_deny.p, 0, words * 4, stream));
     if (n_slots > 0) {
@@ -236,6 +245,11 @@ vsb_status vsb_index::reserve(uint64_t cap) {
         CU(cudaMemcpyAsync(n_nrm.p, nrm.p, (size_t)n_slots * 4, cudaMemcpyDeviceToDevice, stream));
         CU(cudaMemcpyAsync(n_keys.p, keys.p, (size_t)n_slots * 8, cudaMemcpyDeviceToDevice, stream));
         CU(cudaMemcpyAsync(n_deny.p, deny.p, (size_t)((n_slots + 31) / 32) * 4, cudaMemcpyDeviceToDevice, stream));
+        if (trav16) {
+            CU(cudaMemcpyAsync(n_rows16.p, rows16.p, (size_t)n_slots * row_bytes16, cudaMemcpyDeviceToDevice, stream));
+            CU(cudaMemcpyAsync(n_sq16.p, sq16.p, (size_t)n_slots * 4, cudaMemcpyDeviceToDevice, stream));
+            CU(cudaMemcpyAsync(n_nrm16.p, nrm16.p, (size_t)n_slots * 4, cudaMemcpyDeviceToDevice, stream));
+        }
     }
     CU(cudaStreamSynchronize(stream));
     std::swap(rows, n_rows);
@@ -243,6 +257,11 @@ vsb_status vsb_index::reserve(uint64_t cap) {
     std::swap(nrm, n_nrm);
     std::swap(keys, n_keys);
     std::swap(deny, n_deny);
+    if (trav16) {
+        std::swap(rows16, n_rows16);
+        std::swap(sq16, n_sq16);
+        std::swap(nrm16, n_nrm16);
+    }
     h_deny.resize(words, 0u);
     capacity = cap;
     capacity_atomic.store(cap);
@@ -276,6 +295,12 @@ vsb_status vsb_index::add(const uint64_t* k, const float* r, uint64_t n) {
         vsb::launch_convert_rows(storage, add_in.as<float>(), (uint32_t)nb, dim, rows.as<uint8_t>() + (size_t)s0 * row_bytes,
                                  row_bytes, sq.as<float>() + s0, nrm.as<float>() + s0, stream);
         CU(cudaGetLastError());
+        if (trav16) {
+            vsb::launch_convert_rows(VSB_BF16, add_in.as<float>(), (uint32_t)nb, dim,
+                                     rows16.as<uint8_t>() + (size_t)s0 * row_bytes16, row_bytes16, sq16.as<float>() + s0,
+                                     nrm16.as<float>() + s0, stream);
+            CU(cudaGetLastError());
+        }
         CU(cudaMemcpyAsync(keys.as<uint64_t>() + s0, k + b, nb * 8, cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));  // add_in is reused by the next chunk
     }
@@ -546,7 +571,23 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
             t_dists = g_dists + (size_t)nb * k;
         }
         if (use_graph) {
-            // seed layer: exact candidates against the contiguous entry-point sample
+            // ---- bf16 shadow of the queries (f32 storage: tensor-core seed layer and/or bf16 traversal) ----
+            bool seed_tc = tc_enabled && vsb::exact_tc_supported(storage, metric) && nb >= 16;
+            vsb::RowsView q16v;
+            if (storage == VSB_F32 && (seed_tc || trav16)) {
+                CU(q16_rows.ensure((size_t)nb * row_bytes16));
+                CU(q16_sq.ensure((size_t)nb * 4));
+                CU(q16_nrm.ensure((size_t)nb * 4));
+                vsb::launch_convert_rows(VSB_BF16, q_rows.as<float>(), nb, row_bytes / 4, q16_rows.as<uint8_t>(),
+                                         row_bytes16, q16_sq.as<float>(), q16_nrm.as<float>(), s);
+                CU(cudaGetLastError());
+                q16v.rows = q16_rows.as<uint8_t>();
+                q16v.sq = q16_sq.as<float>();
+                q16v.nrm = q16_nrm.as<float>();
+                q16v.row_bytes = row_bytes16;
+                q16v.n = nb;
+            }
+            // ---- seed layer: distances to the contiguous entry-point sample ----
             vsb::ExactParams sp;
             sp.storage = storage;
             sp.metric = metric;
@@ -558,32 +599,21 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
             sp.x.n = n_seed_rows;
             sp.x_lo = 0;
             sp.x_hi = n_seed_rows;
-            sp.keys = nullptr;  // ties by seed index: LessByKey is never asked (see below)
+            sp.keys = nullptr;  // ties fall back to the seed index (LessByKey with null keys)
             sp.kp = 32;
-            bool seed_tc = tc_enabled && vsb::exact_tc_supported(storage, metric) && nb >= 16;
+            const vsb::ExactParams sp_native = sp;
             if (seed_tc) {
-                // tensor-core seed layer: one winner per 256-row tile per query (no list maintenance);
+                // tensor cores: one winner per 256-row tile per query (no list maintenance);
                 // f32 storage multiplies the bf16 shadows of the queries and of the seed block
                 sp.n_splits = std::max(vsb::exact_tc_pick_splits(nb, n_seed_rows, sm_count),
                                        vsb::exact_tc_min_splits_tile_min(n_seed_rows, 32));
                 if (storage == VSB_F32) {
-                    const uint32_t dim_pad = row_bytes / 4;
-                    const uint32_t rb16 = ((dim_pad * 2 + 15) / 16) * 16;
-                    CU(q16_rows.ensure((size_t)nb * rb16));
-                    CU(q16_sq.ensure((size_t)nb * 4));
-                    CU(q16_nrm.ensure((size_t)nb * 4));
-                    vsb::launch_convert_rows(VSB_BF16, q_rows.as<float>(), nb, dim_pad, q16_rows.as<uint8_t>(), rb16,
-                                             q16_sq.as<float>(), q16_nrm.as<float>(), s);
-                    CU(cudaGetLastError());
                     sp.storage = VSB_BF16;
-                    sp.q.rows = q16_rows.as<uint8_t>();
-                    sp.q.sq = q16_sq.as<float>();
-                    sp.q.nrm = q16_nrm.as<float>();
-                    sp.q.row_bytes = rb16;
+                    sp.q = q16v;
                     sp.x.rows = seed16_rows.as<uint8_t>();
                     sp.x.sq = seed16_sq.as<float>();
                     sp.x.nrm = seed16_nrm.as<float>();
-                    sp.x.row_bytes = rb16;
+                    sp.x.row_bytes = row_bytes16;
                 }
             } else {
                 sp.n_splits = vsb::exact_pick_splits(nb, n_seed_rows, sm_count);
@@ -595,12 +625,10 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
             t_begin(PH_SEED, s);
             if (seed_tc) seed_tc = vsb::launch_exact_candidates_tc(sp, s, true);
             if (!seed_tc) {
-                sp.storage = storage;
-                sp.q = qv;
-                sp.x.rows = seed_rows.as<uint8_t>();
-                sp.x.sq = seed_sq.as<float>();
-                sp.x.nrm = seed_nrm.as<float>();
-                sp.x.row_bytes = row_bytes;
+                const uint32_t splits = sp.n_splits;
+                sp = sp_native;
+                sp.n_splits = splits;
+                sp.part = seed_part.as<uint64_t>();
                 if (seed_scan) {
                     // tiny batch: one warp per 4 seed rows, one winner per CTA
                     CU(cudaMemsetAsync(seed_part.p, 0xFF, vsb::exact_part_elems(nb, sp.n_splits, 32) * 8, s));
@@ -611,11 +639,18 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
             }
             t_end(s);
             CU(cudaGetLastError());
+            // ---- K4 beam search (on the bf16 traversal copy when VSB_FLAG_BF16_TRAVERSAL is set) ----
             vsb::SearchParams gp;
-            gp.storage = storage;
+            gp.storage = trav16 ? VSB_BF16 : storage;
             gp.metric = metric;
-            gp.q = qv;
+            gp.q = trav16 ? q16v : qv;
             gp.x = x;
+            if (trav16) {
+                gp.x.rows = rows16.as<uint8_t>();
+                gp.x.sq = sq16.as<float>();
+                gp.x.nrm = nrm16.as<float>();
+                gp.x.row_bytes = row_bytes16;
+            }
             gp.graph = graph.as<uint32_t>();
             gp.graph_stride = graph_stride;
             gp.degree = degree;
@@ -633,6 +668,16 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
             gp.out_keys = g_keys;
             gp.out_dists = g_dists;
             gp.out_counts = have_tail ? nullptr : o_counts;
+            uint32_t kr = 0;
+            if (trav16) {
+                // hand the best kr bf16-ranked candidates to K3 for the canonical fp32 re-rank
+                kr = std::min<uint32_t>(round_up(std::max(2 * k, k + 22), 32), 256);
+                if (kr < k) return fail(VSB_EINVAL, "k=%u too large for the bf16-traversal re-rank (max 256)", k);
+                CU(rr_packed.ensure((size_t)nb * kr * 8));
+                gp.k = kr;
+                gp.out_packed = rr_packed.as<uint64_t>();
+                gp.out_counts = nullptr;
+            }
             if (instrumented) {
                 CU(counters.ensure(16));
                 CU(cudaMemsetAsync(counters.p, 0, 16, s));
@@ -642,6 +687,21 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
             vsb::launch_graph_search(gp, s);
             t_end(s);
             CU(cudaGetLastError());
+            if (trav16) {
+                vsb::ExactParams rp;
+                rp.storage = storage;
+                rp.metric = metric;
+                rp.q = qv;
+                rp.x = x;
+                rp.keys = keys.as<uint64_t>();
+                rp.part = rr_packed.as<uint64_t>();
+                rp.kp = kr;
+                rp.n_splits = 1;
+                t_begin(PH_EXACT, s);
+                vsb::launch_exact_rerank(rp, k, g_keys, g_dists, have_tail ? nullptr : o_counts, nullptr, -1, s);
+                t_end(s);
+                CU(cudaGetLastError());
+            }
             if (instrumented) {
                 unsigned long long h[2];
                 CU(cudaMemcpyAsync(h, counters.p, 16, cudaMemcpyDeviceToHost, s));
@@ -738,6 +798,8 @@ vsb_status vsb_create(const vsb_options* o, vsb_index** out) {
     ix->graph_stride = round_up(ix->degree, 32);
     ix->k_init = std::min<uint32_t>(std::max<uint32_t>(ef_add / 2, ix->degree), 128);
     ix->itopk = std::min<uint32_t>(round_up(ef_search, 32), 512);
+    ix->trav16 = (o->flags & VSB_FLAG_BF16_TRAVERSAL) != 0 && o->storage == VSB_F32;
+    ix->row_bytes16 = storage_row_bytes(VSB_BF16, o->dimensions);
     if (const char* e = getenv("VSB_DISABLE_TC")) ix->tc_enabled = !(e[0] == '1');
     if (const char* e = getenv("VSB_TC_MIN_ROWS")) ix->tc_min_rows = (uint32_t)strtoul(e, nullptr, 10);
     cudaDeviceProp prop;

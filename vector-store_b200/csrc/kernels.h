@@ -86,6 +86,7 @@ struct SearchParams {
     uint64_t* out_keys = nullptr;
     float* out_dists = nullptr;
     uint32_t* out_counts = nullptr;
+    uint64_t* out_packed = nullptr;          // packed (dist, slot) output for a following K3 re-rank
     unsigned long long* counters = nullptr;  // [2]: distance evals, parent expansions (instrumented only)
 };
 void launch_graph_search(const SearchParams& p, cudaStream_t stream);

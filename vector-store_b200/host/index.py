@@ -38,10 +38,10 @@ def _ptr(a):
 class GpuIndex:
     def __init__(self, dimensions: int, metric: Metric = Metric.Cos, storage: Scalar = Scalar.F32,
                  connectivity: int = 0, expansion_add: int = 0, expansion_search: int = 0, device: int = -1,
-                 seed: int = 0):
+                 seed: int = 0, bf16_traversal: bool = False):
         self._lib = lib()
         opt = VsbOptions(dimensions, int(metric), int(storage), connectivity, expansion_add, expansion_search,
-                         device, 0, seed)
+                         device, 1 if bf16_traversal else 0, seed)
         h = C.c_void_p()
         check(self._lib.vsb_create(C.byref(opt), C.byref(h)))
         self._h = h
