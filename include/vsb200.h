@@ -79,6 +79,8 @@ typedef struct {
     uint32_t n_seeds;          /* entry points taken from the seed layer, <= 32 */
     uint32_t min_graph_size;   /* below this many live vectors search is brute force */
     uint32_t search_width;     /* parents expanded per iteration, 1..4 */
+    uint32_t stream_threshold; /* un-graphed rows that make vsb_add link them into the graph (K7);
+                                  default 4096; UINT32_MAX = never (only vsb_insert_pending / vsb_build) */
 } vsb_search_params;
 
 /* Counters the roofline arithmetic is computed from. */
@@ -126,6 +128,11 @@ int vsb_contains(const vsb_index* index, uint64_t key);
  * Until it is called (and for vectors added after it) search is exact brute force
  * over the un-graphed tail, merged with the graph result. */
 vsb_status vsb_build(vsb_index* index);
+
+/* K7 streaming insert: links every vector added since the last build / insert into the existing graph
+ * (the batched equivalent of usearch's per-vector HNSW insert, usearch.rs:191-197).  vsb_add calls
+ * it by itself once `stream_threshold` rows are pending.  No-op before the first vsb_build. */
+vsb_status vsb_insert_pending(vsb_index* index);
 
 /* Copies the graph rows [n_graphed][stride] (u32 slot ids, UINT32_MAX padded) and the slot->key
  * table to host memory; `stride` = 32-rounded degree.  Snapshot/debug hook and the

@@ -214,3 +214,50 @@ void launch_merge_graph(const uint32_t* fwd, const uint32_t* rev, const uint32_t
 }
 
 }  // namespace vsb
+
+// ------------------------------------------------------------------------------------------------
+// K7: streaming insert (SURVEY §8a A5 "HNSW insert", config C5).  The batch of new rows has been
+// searched with K4 (beam = expansion_add) and `cand` holds each new row's best candidates (packed,
+// ascending, kInvalidPacked padded).  One warp per new row u:
+//   forward : row(u) = its R closest candidates
+//   reverse : each of the R/2 closest v gets u written into the reverse half of row(v) — an empty slot
+//             if one is hit, otherwise a pseudo-randomly chosen reverse edge is replaced (atomicExch,
+//             so concurrent inserts into the same row never tear it)
+// Rows of one batch do not link to each other; a periodic vsb_build() re-optimises the graph.
+namespace vsb {
+namespace {
+__global__ void __launch_bounds__(128) stream_link_kernel(const uint64_t* __restrict__ cand, uint32_t n_new,
+                                                          uint32_t cand_stride, uint32_t first_slot, uint32_t R,
+                                                          uint32_t* __restrict__ graph, uint32_t graph_stride) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n_new) return;
+    const uint32_t u = first_slot + i;
+    const uint64_t* c = cand + (size_t)i * cand_stride;
+    uint32_t* row = graph + (size_t)u * graph_stride;
+    const uint32_t half = R / 2;
+    for (uint32_t r = lane; r < graph_stride; r += 32) {
+        uint32_t v = kInvalidSlot;
+        if (r < R && r < cand_stride) {
+            const uint64_t p = c[r];
+            if (p != kInvalidPacked) v = packed_lo(p);
+        }
+        if (v == u) v = kInvalidSlot;
+        row[r] = v;
+        if (v != kInvalidSlot && r < half) {
+            uint32_t* vrow = graph + (size_t)v * graph_stride;
+            const uint32_t pos = half + ((u * 0x9E3779B1u + r * 0x85EBCA6Bu) >> 16) % (R - half);
+            const uint32_t old = atomicCAS(&vrow[pos], kInvalidSlot, u);
+            if (old != kInvalidSlot && old != u) atomicExch(&vrow[pos], u);
+        }
+    }
+}
+}  // namespace
+
+void launch_stream_link(const uint64_t* cand, uint32_t n_new, uint32_t cand_stride, uint32_t first_slot, uint32_t R,
+                        uint32_t* graph, uint32_t graph_stride, cudaStream_t stream) {
+    if (n_new == 0) return;
+    stream_link_kernel<<<(n_new + 3) / 4, 128, 0, stream>>>(cand, n_new, cand_stride, first_slot, R, graph, graph_stride);
+    g_kernel_launches += 1;
+}
+}  // namespace vsb

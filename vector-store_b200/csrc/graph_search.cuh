@@ -55,6 +55,132 @@ __device__ __forceinline__ bool hash_insert(uint32_t* tab, uint32_t mask, uint32
     return false;  // saturated neighbourhood: treat as visited
 }
 
+// ---- shared evaluation helpers (K4 and K4b) -----------------------------------------------------
+// A "group" is U stored rows in flight in registers.  Loads are unpredicated when every lane owns a
+// full set of chunks (`full`), and indices past the end of the queue are clamped to its last entry
+// (the duplicate result is simply not written back), so the hot loop carries no per-chunk predicates.
+template <int CPL, int U>
+struct VecGroup {
+    uint4 x[U][CPL];
+};
+
+template <int CPL, int U>
+__device__ __forceinline__ void group_load(VecGroup<CPL, U>& g, const uint8_t* __restrict__ x_rows, uint32_t row_bytes,
+                                           const uint32_t* newq, uint32_t base, uint32_t stride, uint32_t last,
+                                           int lane, int n_chunks, bool full) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        uint32_t idx = base + u * stride;
+        idx = idx < last ? idx : last;
+        const uint4* xrow = reinterpret_cast<const uint4*>(x_rows + (size_t)newq[idx] * row_bytes) + lane;
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) g.x[u][j] = ldg_nc_v4(xrow + j * 32);
+        } else {
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                g.x[u][j] = make_uint4(0, 0, 0, 0);
+                if (j * 32 + lane < n_chunks) g.x[u][j] = ldg_nc_v4(xrow + j * 32);
+            }
+        }
+    }
+}
+
+// raw = canonical butterfly sum (dot or squared-L2) as float; integer storages convert once at the end
+template <int ST, int CPL, int U>
+__device__ __forceinline__ void group_reduce(const VecGroup<CPL, U>& g, const float* qf, const uint4* qc, bool is_l2,
+                                             float* newd, uint32_t base, uint32_t stride, uint32_t n_new, int lane) {
+    constexpr int E = Storage<ST>::ELEMS;
+    constexpr bool kFloat = Storage<ST>::kFloat;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint32_t idx = base + u * stride;
+        float raw;
+        if constexpr (kFloat) {
+            float f;
+            if (is_l2) {
+                ChunkAcc<ST, VSB_METRIC_L2SQ> acc;
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    float xf[E];
+                    Storage<ST>::unpack(g.x[u][j], xf);
+                    acc.add_f(&qf[j * E], xf);
+                }
+                f = acc.f;
+            } else {
+                ChunkAcc<ST, VSB_METRIC_IP> acc;
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    float xf[E];
+                    Storage<ST>::unpack(g.x[u][j], xf);
+                    acc.add_f(&qf[j * E], xf);
+                }
+                f = acc.f;
+            }
+            raw = butterfly_sum(f);
+        } else {
+            int i;
+            if (is_l2) {
+                ChunkAcc<ST, VSB_METRIC_L2SQ> acc;
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) acc.add(qc[j], g.x[u][j]);
+                i = acc.i;
+            } else {
+                ChunkAcc<ST, VSB_METRIC_IP> acc;
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) acc.add(qc[j], g.x[u][j]);
+                i = acc.i;
+            }
+            raw = (float)butterfly_sum_i(i);
+        }
+        if (lane == 0 && idx < n_new) newd[idx] = raw;
+    }
+}
+
+// raw sum -> distance; the same arithmetic as finish_distance (common.cuh), executed once per candidate
+// by the lane that owns it instead of once per candidate by the whole warp
+template <int ST>
+__device__ __forceinline__ float finish_raw(float raw, int metric, float qn, float xn) {
+    if constexpr (ST == VSB_ST_B1) {
+        return raw;
+    } else {
+        if (metric == VSB_METRIC_L2SQ) return raw;
+        if (metric == VSB_METRIC_IP) {
+            if constexpr (ST == VSB_ST_I8) raw = __fdiv_rn(raw, 16129.0f);
+            return __fsub_rn(1.0f, raw);
+        }
+        if (qn == 0.0f && xn == 0.0f) return 0.0f;
+        if (qn == 0.0f || xn == 0.0f) return 1.0f;
+        float d = __fsub_rn(1.0f, __fdiv_rn(raw, __fmul_rn(qn, xn)));
+        d = d < 0.0f ? 0.0f : d;
+        d = d > 2.0f ? 2.0f : d;
+        return d;
+    }
+}
+
+// all queue entries of this warp: index(m) = first + m * stride, m < mine.  Double buffered: the loads of
+// group m+1 are in flight while group m is reduced.
+template <int ST, int CPL, int U>
+__device__ __forceinline__ void evaluate_entries(const uint8_t* __restrict__ x_rows, uint32_t row_bytes,
+                                                 const uint32_t* newq, float* newd, uint32_t first, uint32_t stride,
+                                                 uint32_t mine, uint32_t n_new, const float* qf, const uint4* qc,
+                                                 bool is_l2, int lane, int n_chunks, bool full) {
+    if (mine == 0) return;
+    const uint32_t last = first + (mine - 1) * stride;
+    VecGroup<CPL, U> ga, gb;
+    group_load<CPL, U>(ga, x_rows, row_bytes, newq, first, stride, last, lane, n_chunks, full);
+    for (uint32_t m0 = 0; m0 < mine; m0 += 2 * U) {
+        const bool has_b = m0 + U < mine;
+        if (has_b) group_load<CPL, U>(gb, x_rows, row_bytes, newq, first + (m0 + U) * stride, stride, last, lane, n_chunks, full);
+        group_reduce<ST, CPL, U>(ga, qf, qc, is_l2, newd, first + m0 * stride, stride, n_new, lane);
+        if (has_b) {
+            if (m0 + 2 * U < mine)
+                group_load<CPL, U>(ga, x_rows, row_bytes, newq, first + (m0 + 2 * U) * stride, stride, last, lane, n_chunks, full);
+            group_reduce<ST, CPL, U>(gb, qf, qc, is_l2, newd, first + (m0 + U) * stride, stride, n_new, lane);
+        }
+    }
+}
+
 constexpr int K4_MAX_WIDTH = 4;  // parents expanded per iteration (search_width)
 
 template <int ST, int CPL>
@@ -75,11 +201,12 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
     uint64_t* list = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warp * per_warp);
     uint32_t* hash = reinterpret_cast<uint32_t*>(list + a.itopk);
     uint32_t* newq = hash + hsize;                           // [qcap] un-visited neighbour slots of this iteration
-    float* newd = reinterpret_cast<float*>(newq + qcap);     // [qcap] their distances
+    float* newd = reinterpret_cast<float*>(newq + qcap);     // [qcap] their raw sums
     const LessBySlot less;
     const bool is_l2 = a.metric == VSB_METRIC_L2SQ;
     const bool is_cos = a.metric == VSB_METRIC_COS;
     const int n_chunks = a.x_row_bytes / 16;
+    const bool full = n_chunks == CPL * 32;
 
     for (uint32_t i = lane; i < a.itopk; i += 32) list[i] = kInvalidPacked;
     for (uint32_t i = lane; i < hsize; i += 32) hash[i] = kHashEmpty;
@@ -114,104 +241,23 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
         n_hashed += __popc(m);
     };
 
-    struct Group {
-        uint4 x[U][CPL];
-        float xn[U];
-    };
-    auto load_group = [&](Group& g, uint32_t base) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t idx = base + u;
-            const bool on = idx < n_new;
-            const uint32_t slot = on ? newq[idx] : 0u;
-            const uint4* xrow = reinterpret_cast<const uint4*>(a.x_rows + (size_t)slot * a.x_row_bytes);
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) {
-                const int c = j * 32 + lane;
-                g.x[u][j] = make_uint4(0, 0, 0, 0);
-                if (on && c < n_chunks) g.x[u][j] = ldg_nc_v4(xrow + c);
-            }
-            g.xn[u] = (on && is_cos) ? __ldg(a.x_nrm + slot) : 0.0f;
-        }
-    };
-    auto compute_group = [&](const Group& g, uint32_t base) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t idx = base + u;
-            if (idx >= n_new) continue;  // warp-uniform
-            float facc = 0.0f;
-            int iacc = 0;
-            if constexpr (kFloat) {
-                if (is_l2) {
-                    ChunkAcc<ST, VSB_METRIC_L2SQ> acc;
-#pragma unroll
-                    for (int j = 0; j < CPL; ++j) {
-                        float xf[E];
-                        Storage<ST>::unpack(g.x[u][j], xf);
-                        acc.add_f(&qf[j * E], xf);
-                    }
-                    facc = acc.f;
-                } else {
-                    ChunkAcc<ST, VSB_METRIC_IP> acc;
-#pragma unroll
-                    for (int j = 0; j < CPL; ++j) {
-                        float xf[E];
-                        Storage<ST>::unpack(g.x[u][j], xf);
-                        acc.add_f(&qf[j * E], xf);
-                    }
-                    facc = acc.f;
-                }
-                facc = butterfly_sum(facc);
-            } else {
-                if (is_l2) {
-                    ChunkAcc<ST, VSB_METRIC_L2SQ> acc;
-#pragma unroll
-                    for (int j = 0; j < CPL; ++j) acc.add(qc[j], g.x[u][j]);
-                    iacc = acc.i;
-                } else {
-                    ChunkAcc<ST, VSB_METRIC_IP> acc;
-#pragma unroll
-                    for (int j = 0; j < CPL; ++j) acc.add(qc[j], g.x[u][j]);
-                    iacc = acc.i;
-                }
-                iacc = butterfly_sum_i(iacc);
-            }
-            float d;
-            if constexpr (ST == VSB_ST_B1) {
-                d = finish_distance<ST, VSB_METRIC_HAMMING>(facc, iacc, 0.0f, 0.0f);
-            } else {
-                if (is_l2)
-                    d = finish_distance<ST, VSB_METRIC_L2SQ>(facc, iacc, 0.0f, 0.0f);
-                else if (is_cos)
-                    d = finish_distance<ST, VSB_METRIC_COS>(facc, iacc, qn, g.xn[u]);
-                else
-                    d = finish_distance<ST, VSB_METRIC_IP>(facc, iacc, 0.0f, 0.0f);
-            }
-            if (lane == 0) newd[idx] = d;
-        }
-    };
-
-    // distances of everything queued (double-buffered: the loads of group g+1 fly while group g is reduced),
-    // then fold the results into the candidate list 32 at a time
+    // distances of everything queued, then fold the candidates that can still enter the list
     auto evaluate_queue = [&]() {
         __syncwarp();
         if (n_new == 0) return;
         n_evals += n_new;
-        Group ga, gb;
-        load_group(ga, 0);
-        for (uint32_t base = 0; base < n_new; base += 2 * U) {
-            const bool has_b = base + U < n_new;
-            if (has_b) load_group(gb, base + U);
-            compute_group(ga, base);
-            if (has_b) {
-                if (base + 2 * U < n_new) load_group(ga, base + 2 * U);
-                compute_group(gb, base + U);
-            }
-        }
+        evaluate_entries<ST, CPL, U>(a.x_rows, a.x_row_bytes, newq, newd, 0, 1, n_new, n_new, qf, qc, is_l2, lane,
+                                     n_chunks, full);
         __syncwarp();
+        const uint64_t worst = list[a.itopk - 1];
         for (uint32_t base = 0; base < n_new; base += 32) {
             uint64_t res = kInvalidPacked;
-            if (base + lane < n_new) res = pack_ds(newd[base + lane], newq[base + lane]);
+            if (base + lane < n_new) {
+                const uint32_t slot = newq[base + lane];
+                const float xn = is_cos ? __ldg(a.x_nrm + slot) : 0.0f;
+                res = pack_ds(finish_raw<ST>(newd[base + lane], a.metric, qn, xn), slot);
+            }
+            if (__ballot_sync(kFullMask, res < worst) == 0) continue;  // nothing here can enter the list
             res = warp_sort32(res, lane, less);
             warp_list_merge(list, (int)a.itopk, res, lane, less);
         }
@@ -363,6 +409,7 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
     const bool is_l2 = a.metric == VSB_METRIC_L2SQ;
     const bool is_cos = a.metric == VSB_METRIC_COS;
     const int n_chunks = a.x_row_bytes / 16;
+    const bool full = n_chunks == CPL * 32;
 
     for (uint32_t i = tid; i < a.itopk; i += K4B_WARPS * 32) list[i] = kInvalidPacked;
     for (uint32_t i = tid; i < hsize; i += K4B_WARPS * 32) hash[i] = kHashEmpty;
@@ -385,106 +432,23 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
     unsigned long long n_evals = 0, n_parents = 0;
     __syncthreads();
 
-    struct Group {
-        uint4 x[U][CPL];
-        float xn[U];
-    };
-    // this warp's m-th queue entry is index warp + 8*m
-    auto load_group = [&](Group& g, uint32_t m0, uint32_t n_new) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t idx = warp + K4B_WARPS * (m0 + u);
-            const bool on = idx < n_new;
-            const uint32_t slot = on ? newq[idx] : 0u;
-            const uint4* xrow = reinterpret_cast<const uint4*>(a.x_rows + (size_t)slot * a.x_row_bytes);
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) {
-                const int c = j * 32 + lane;
-                g.x[u][j] = make_uint4(0, 0, 0, 0);
-                if (on && c < n_chunks) g.x[u][j] = ldg_nc_v4(xrow + c);
-            }
-            g.xn[u] = (on && is_cos) ? __ldg(a.x_nrm + slot) : 0.0f;
-        }
-    };
-    auto compute_group = [&](const Group& g, uint32_t m0, uint32_t n_new) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t idx = warp + K4B_WARPS * (m0 + u);
-            if (idx >= n_new) continue;
-            float facc = 0.0f;
-            int iacc = 0;
-            if constexpr (kFloat) {
-                if (is_l2) {
-                    ChunkAcc<ST, VSB_METRIC_L2SQ> acc;
-#pragma unroll
-                    for (int j = 0; j < CPL; ++j) {
-                        float xf[E];
-                        Storage<ST>::unpack(g.x[u][j], xf);
-                        acc.add_f(&qf[j * E], xf);
-                    }
-                    facc = acc.f;
-                } else {
-                    ChunkAcc<ST, VSB_METRIC_IP> acc;
-#pragma unroll
-                    for (int j = 0; j < CPL; ++j) {
-                        float xf[E];
-                        Storage<ST>::unpack(g.x[u][j], xf);
-                        acc.add_f(&qf[j * E], xf);
-                    }
-                    facc = acc.f;
-                }
-                facc = butterfly_sum(facc);
-            } else {
-                if (is_l2) {
-                    ChunkAcc<ST, VSB_METRIC_L2SQ> acc;
-#pragma unroll
-                    for (int j = 0; j < CPL; ++j) acc.add(qc[j], g.x[u][j]);
-                    iacc = acc.i;
-                } else {
-                    ChunkAcc<ST, VSB_METRIC_IP> acc;
-#pragma unroll
-                    for (int j = 0; j < CPL; ++j) acc.add(qc[j], g.x[u][j]);
-                    iacc = acc.i;
-                }
-                iacc = butterfly_sum_i(iacc);
-            }
-            float d;
-            if constexpr (ST == VSB_ST_B1) {
-                d = finish_distance<ST, VSB_METRIC_HAMMING>(facc, iacc, 0.0f, 0.0f);
-            } else {
-                if (is_l2)
-                    d = finish_distance<ST, VSB_METRIC_L2SQ>(facc, iacc, 0.0f, 0.0f);
-                else if (is_cos)
-                    d = finish_distance<ST, VSB_METRIC_COS>(facc, iacc, qn, g.xn[u]);
-                else
-                    d = finish_distance<ST, VSB_METRIC_IP>(facc, iacc, 0.0f, 0.0f);
-            }
-            if (lane == 0) newd[idx] = d;
-        }
-    };
-    // all warps: evaluate the queue, sort it in groups of 32, warp 0 folds the groups into the list
+    // all warps: evaluate the queue (warp w takes entries w, w+8, ...), sort it in groups of 32,
+    // warp 0 folds the groups into the list
     auto evaluate_queue = [&]() {
         __syncthreads();
         const uint32_t n_new = ctrl[0];
         if (n_new != 0) {
             const uint32_t mine = n_new > (uint32_t)warp ? (n_new - warp + K4B_WARPS - 1) / K4B_WARPS : 0;
-            if (mine) {
-                Group ga, gb;
-                load_group(ga, 0, n_new);
-                for (uint32_t m0 = 0; m0 < mine; m0 += 2 * U) {
-                    const bool has_b = m0 + U < mine;
-                    if (has_b) load_group(gb, m0 + U, n_new);
-                    compute_group(ga, m0, n_new);
-                    if (has_b) {
-                        if (m0 + 2 * U < mine) load_group(ga, m0 + 2 * U, n_new);
-                        compute_group(gb, m0 + U, n_new);
-                    }
-                }
-            }
+            evaluate_entries<ST, CPL, U>(a.x_rows, a.x_row_bytes, newq, newd, (uint32_t)warp, K4B_WARPS, mine, n_new, qf, qc,
+                                         is_l2, lane, n_chunks, full);
             __syncthreads();
             for (uint32_t g = warp; g * 32 < n_new; g += K4B_WARPS) {
                 uint64_t res = kInvalidPacked;
-                if (g * 32 + lane < n_new) res = pack_ds(newd[g * 32 + lane], newq[g * 32 + lane]);
+                if (g * 32 + lane < n_new) {
+                    const uint32_t slot = newq[g * 32 + lane];
+                    const float xn = is_cos ? __ldg(a.x_nrm + slot) : 0.0f;
+                    res = pack_ds(finish_raw<ST>(newd[g * 32 + lane], a.metric, qn, xn), slot);
+                }
                 newp[g * 32 + lane] = warp_sort32(res, lane, less);
             }
             __syncthreads();

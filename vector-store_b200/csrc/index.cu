@@ -66,6 +66,23 @@ vsb_status fail(vsb_status st, const char* fmt, ...) {
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) {
+        o.p = nullptr;
+        o.bytes = 0;
+    }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p;
+            bytes = o.bytes;
+            o.p = nullptr;
+            o.bytes = 0;
+        }
+        return *this;
+    }
     ~DevBuf() { release(); }
     void release() {
         if (p) cudaFree(p);
@@ -197,6 +214,11 @@ struct vsb_index {
                            const vsb::RowsView* shadow_x = nullptr);
     bool tc_enabled = true;       // tcgen05 path for the dense distance tiles (VSB_DISABLE_TC=1 turns it off)
     uint32_t tc_min_rows = 8192;  // below this the SIMT K1 is used (launch + pipeline fill dominate)
+    vsb_status graph_block(const vsb::RowsView& qv, uint32_t nb, uint32_t k, uint32_t itopk_eff, uint64_t* g_keys,
+                           float* g_dists, uint32_t* counts_out, uint64_t* packed_out, const vsb::RowsView* q16_in,
+                           cudaStream_t s);
+    vsb_status stream_insert();
+    uint32_t stream_threshold = 4096;  // un-graphed tail rows that trigger an automatic streaming insert
     vsb_status search_dev(const float* d_q, uint64_t nq, uint32_t k, uint64_t* d_keys, float* d_dists,
                           uint32_t* d_counts, cudaStream_t s, bool exact, const uint32_t* d_allow,
                           uint64_t allow_bits);
@@ -308,6 +330,7 @@ vsb_status vsb_index::add(const uint64_t* k, const float* r, uint64_t n) {
     n_slots += (uint32_t)n;
     live += n;
     live_atomic.store(live);
+    if (n_graphed > 0 && stream_threshold > 0 && n_slots - n_graphed >= stream_threshold) ST(stream_insert());
     return VSB_OK;
 }
 
@@ -461,7 +484,7 @@ vsb_status vsb_index::build() {
     CU(cudaGetLastError());
     if (btime) cudaEventRecord(ev[3], stream);
     DevBuf new_graph;
-    CU(new_graph.ensure((size_t)n * graph_stride * 4));
+    CU(new_graph.ensure((size_t)std::max<uint64_t>(capacity, n) * graph_stride * 4));  // room for streamed rows
     vsb::launch_merge_graph(fwd.as<uint32_t>(), rev.as<uint32_t>(), rev_cnt.as<uint32_t>(), n, R,
                             new_graph.as<uint32_t>(), graph_stride, stream);
     CU(cudaGetLastError());
@@ -520,6 +543,212 @@ vsb_status vsb_index::build() {
     return VSB_OK;
 }
 
+// Seeds + K4 (+ K3 re-rank on the bf16-traversal path) for `nb` converted queries `qv`.
+//   out_keys/out_dists/out_counts : user-facing top-k (nullable when packed_out is used)
+//   packed_out                    : raw K4 list (packed ord(dist)<<32|slot, [nb][k]) — used by the streaming insert
+//   q16_in                        : bf16 copy of the queries if the caller already has one (corpus rows), else built here
+vsb_status vsb_index::graph_block(const vsb::RowsView& qv, uint32_t nb, uint32_t k, uint32_t itopk_eff,
+                                  uint64_t* g_keys, float* g_dists, uint32_t* counts_out, uint64_t* packed_out,
+                                  const vsb::RowsView* q16_in, cudaStream_t s) {
+    const vsb::RowsView x = corpus_view();
+    const uint32_t* deny_bm = any_tombstone ? deny.as<uint32_t>() : nullptr;
+    const bool have_tail = counts_out == nullptr;  // the caller merges and counts later
+    uint32_t* o_counts = counts_out;
+    const bool rerank = trav16 && packed_out == nullptr;
+    // ---- bf16 shadow of the queries (f32 storage: tensor-core seed layer and/or bf16 traversal) ----
+    bool seed_tc = tc_enabled && vsb::exact_tc_supported(storage, metric) && nb >= 16;
+    vsb::RowsView q16v;
+    if (q16_in != nullptr) {
+        q16v = *q16_in;
+    } else if (storage == VSB_F32 && (seed_tc || trav16)) {
+        CU(q16_rows.ensure((size_t)nb * row_bytes16));
+        CU(q16_sq.ensure((size_t)nb * 4));
+        CU(q16_nrm.ensure((size_t)nb * 4));
+        vsb::launch_convert_rows(VSB_BF16, reinterpret_cast<const float*>(qv.rows), nb, row_bytes / 4, q16_rows.as<uint8_t>(),
+                                 row_bytes16, q16_sq.as<float>(), q16_nrm.as<float>(), s);
+        CU(cudaGetLastError());
+        q16v.rows = q16_rows.as<uint8_t>();
+        q16v.sq = q16_sq.as<float>();
+        q16v.nrm = q16_nrm.as<float>();
+        q16v.row_bytes = row_bytes16;
+        q16v.n = nb;
+    }
+    // ---- seed layer: distances to the contiguous entry-point sample ----
+    vsb::ExactParams sp;
+    sp.storage = storage;
+    sp.metric = metric;
+    sp.q = qv;
+    sp.x.rows = seed_rows.as<uint8_t>();
+    sp.x.sq = seed_sq.as<float>();
+    sp.x.nrm = seed_nrm.as<float>();
+    sp.x.row_bytes = row_bytes;
+    sp.x.n = n_seed_rows;
+    sp.x_lo = 0;
+    sp.x_hi = n_seed_rows;
+    sp.keys = nullptr;  // ties fall back to the seed index (LessByKey with null keys)
+    sp.kp = 32;
+    const vsb::ExactParams sp_native = sp;
+    if (seed_tc) {
+        // tensor cores: one winner per 256-row tile per query (no list maintenance);
+        // f32 storage multiplies the bf16 shadows of the queries and of the seed block
+        sp.n_splits = std::max(vsb::exact_tc_pick_splits(nb, n_seed_rows, sm_count),
+                               vsb::exact_tc_min_splits_tile_min(n_seed_rows, 32));
+        if (storage == VSB_F32) {
+            sp.storage = VSB_BF16;
+            sp.q = q16v;
+            sp.x.rows = seed16_rows.as<uint8_t>();
+            sp.x.sq = seed16_sq.as<float>();
+            sp.x.nrm = seed16_nrm.as<float>();
+            sp.x.row_bytes = row_bytes16;
+        }
+    } else {
+        sp.n_splits = vsb::exact_pick_splits(nb, n_seed_rows, sm_count);
+    }
+    const bool seed_scan = !seed_tc && nb <= vsb::graph_search_small_batch();
+    if (seed_scan) sp.n_splits = vsb::seed_scan_blocks(n_seed_rows);
+    CU(seed_part.ensure(vsb::exact_part_elems(nb, sp.n_splits, 32) * 8));
+    sp.part = seed_part.as<uint64_t>();
+    t_begin(PH_SEED, s);
+    if (seed_tc) seed_tc = vsb::launch_exact_candidates_tc(sp, s, true);
+    if (!seed_tc) {
+        const uint32_t splits = sp.n_splits;
+        sp = sp_native;
+        sp.n_splits = splits;
+        sp.part = seed_part.as<uint64_t>();
+        if (seed_scan) {
+            // tiny batch: one warp per 4 seed rows, one winner per CTA
+            CU(cudaMemsetAsync(seed_part.p, 0xFF, vsb::exact_part_elems(nb, sp.n_splits, 32) * 8, s));
+            vsb::launch_seed_scan(storage, metric, qv, sp.x, seed_part.as<uint64_t>(), s);
+        } else {
+            vsb::launch_exact_candidates(sp, s);
+        }
+    }
+    t_end(s);
+    CU(cudaGetLastError());
+    // ---- K4 beam search (on the bf16 traversal copy when VSB_FLAG_BF16_TRAVERSAL is set) ----
+    vsb::SearchParams gp;
+    gp.storage = trav16 ? VSB_BF16 : storage;
+    gp.metric = metric;
+    gp.q = trav16 ? q16v : qv;
+    gp.x = x;
+    if (trav16) {
+        gp.x.rows = rows16.as<uint8_t>();
+        gp.x.sq = sq16.as<float>();
+        gp.x.nrm = nrm16.as<float>();
+        gp.x.row_bytes = row_bytes16;
+    }
+    gp.graph = graph.as<uint32_t>();
+    gp.graph_stride = graph_stride;
+    gp.degree = degree;
+    gp.n_graphed = n_graphed;
+    gp.seed_lists = seed_part.as<uint64_t>();
+    gp.seed_stride = sp.n_splits * 32;
+    gp.n_seeds = n_seeds;
+    gp.seed_slots = seed_slots.as<uint32_t>();
+    gp.deny = deny_bm;
+    gp.keys = keys.as<uint64_t>();
+    gp.itopk = std::max(itopk_eff, k);
+    gp.max_iters = max_iters;
+    gp.search_width = search_width;
+    gp.k = k;
+    gp.out_keys = g_keys;
+    gp.out_dists = g_dists;
+    gp.out_counts = have_tail ? nullptr : o_counts;
+    uint32_t kr = 0;
+    if (packed_out != nullptr) {
+        gp.out_packed = packed_out;
+        gp.out_counts = nullptr;
+    }
+    if (rerank) {
+        // hand the best kr bf16-ranked candidates to K3 for the canonical fp32 re-rank
+        kr = std::min<uint32_t>(round_up(std::max(2 * k, k + 22), 32), 256);
+        if (kr < k) return fail(VSB_EINVAL, "k=%u too large for the bf16-traversal re-rank (max 256)", k);
+        CU(rr_packed.ensure((size_t)nb * kr * 8));
+        gp.k = kr;
+        gp.out_packed = rr_packed.as<uint64_t>();
+        gp.out_counts = nullptr;
+    }
+    if (instrumented) {
+        CU(counters.ensure(16));
+        CU(cudaMemsetAsync(counters.p, 0, 16, s));
+        gp.counters = counters.as<unsigned long long>();
+    }
+    t_begin(PH_GRAPH, s);
+    vsb::launch_graph_search(gp, s);
+    t_end(s);
+    CU(cudaGetLastError());
+    if (rerank) {
+        vsb::ExactParams rp;
+        rp.storage = storage;
+        rp.metric = metric;
+        rp.q = qv;
+        rp.x = x;
+        rp.keys = keys.as<uint64_t>();
+        rp.part = rr_packed.as<uint64_t>();
+        rp.kp = kr;
+        rp.n_splits = 1;
+        t_begin(PH_EXACT, s);
+        vsb::launch_exact_rerank(rp, k, g_keys, g_dists, have_tail ? nullptr : o_counts, nullptr, -1, s);
+        t_end(s);
+        CU(cudaGetLastError());
+    }
+    if (instrumented) {
+        unsigned long long h[2];
+        CU(cudaMemcpyAsync(h, counters.p, 16, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        last_evals = h[0];
+        last_parents = h[1];
+        last_queries = nb;
+    }
+    return VSB_OK;
+}
+
+// K7: link every un-graphed tail row into the existing graph (batched HNSW-style insert:
+// search with beam = expansion_add, connect to the R closest, add reverse edges).
+vsb_status vsb_index::stream_insert() {
+    if (n_graphed == 0 || n_graphed >= n_slots) return VSB_OK;
+    CU(cudaSetDevice(device));
+    ST(use_stream(stream));
+    const size_t need = (size_t)capacity * graph_stride * 4;
+    if (graph.bytes < need) {
+        DevBuf g2;
+        CU(g2.ensure(need));
+        CU(cudaMemcpyAsync(g2.p, graph.p, (size_t)n_graphed * graph_stride * 4, cudaMemcpyDeviceToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+        graph = std::move(g2);
+    }
+    const uint32_t R = degree;
+    const uint32_t ef_add = opt.expansion_add ? opt.expansion_add : 128;
+    const uint32_t ef = std::min<uint32_t>(round_up(std::max(ef_add, R), 32), 512);
+    DevBuf cand;
+    const uint32_t QB = 8192;
+    while (n_graphed < n_slots) {
+        const uint32_t t0 = n_graphed;
+        const uint32_t nb = std::min(QB, n_slots - t0);
+        vsb::RowsView qv;
+        qv.rows = rows.as<uint8_t>() + (size_t)t0 * row_bytes;
+        qv.sq = sq.as<float>() + t0;
+        qv.nrm = nrm.as<float>() + t0;
+        qv.row_bytes = row_bytes;
+        qv.n = nb;
+        vsb::RowsView q16;
+        if (trav16) {
+            q16.rows = rows16.as<uint8_t>() + (size_t)t0 * row_bytes16;
+            q16.sq = sq16.as<float>() + t0;
+            q16.nrm = nrm16.as<float>() + t0;
+            q16.row_bytes = row_bytes16;
+            q16.n = nb;
+        }
+        CU(cand.ensure((size_t)nb * R * 8));
+        ST(graph_block(qv, nb, R, ef, nullptr, nullptr, nullptr, cand.as<uint64_t>(), trav16 ? &q16 : nullptr, stream));
+        vsb::launch_stream_link(cand.as<uint64_t>(), nb, R, t0, R, graph.as<uint32_t>(), graph_stride, stream);
+        CU(cudaGetLastError());
+        n_graphed = t0 + nb;  // later batches may link to these rows (stream order)
+    }
+    CU(cudaStreamSynchronize(stream));
+    return VSB_OK;
+}
+
 vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint64_t* d_keys, float* d_dists,
                                  uint32_t* d_counts, cudaStream_t s, bool exact, const uint32_t* d_allow,
                                  uint64_t allow_bits) {
@@ -571,145 +800,7 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
             t_dists = g_dists + (size_t)nb * k;
         }
         if (use_graph) {
-            // ---- bf16 shadow of the queries (f32 storage: tensor-core seed layer and/or bf16 traversal) ----
-            bool seed_tc = tc_enabled && vsb::exact_tc_supported(storage, metric) && nb >= 16;
-            vsb::RowsView q16v;
-            if (storage == VSB_F32 && (seed_tc || trav16)) {
-                CU(q16_rows.ensure((size_t)nb * row_bytes16));
-                CU(q16_sq.ensure((size_t)nb * 4));
-                CU(q16_nrm.ensure((size_t)nb * 4));
-                vsb::launch_convert_rows(VSB_BF16, q_rows.as<float>(), nb, row_bytes / 4, q16_rows.as<uint8_t>(),
-                                         row_bytes16, q16_sq.as<float>(), q16_nrm.as<float>(), s);
-                CU(cudaGetLastError());
-                q16v.rows = q16_rows.as<uint8_t>();
-                q16v.sq = q16_sq.as<float>();
-                q16v.nrm = q16_nrm.as<float>();
-                q16v.row_bytes = row_bytes16;
-                q16v.n = nb;
-            }
-            // ---- seed layer: distances to the contiguous entry-point sample ----
-            vsb::ExactParams sp;
-            sp.storage = storage;
-            sp.metric = metric;
-            sp.q = qv;
-            sp.x.rows = seed_rows.as<uint8_t>();
-            sp.x.sq = seed_sq.as<float>();
-            sp.x.nrm = seed_nrm.as<float>();
-            sp.x.row_bytes = row_bytes;
-            sp.x.n = n_seed_rows;
-            sp.x_lo = 0;
-            sp.x_hi = n_seed_rows;
-            sp.keys = nullptr;  // ties fall back to the seed index (LessByKey with null keys)
-            sp.kp = 32;
-            const vsb::ExactParams sp_native = sp;
-            if (seed_tc) {
-                // tensor cores: one winner per 256-row tile per query (no list maintenance);
-                // f32 storage multiplies the bf16 shadows of the queries and of the seed block
-                sp.n_splits = std::max(vsb::exact_tc_pick_splits(nb, n_seed_rows, sm_count),
-                                       vsb::exact_tc_min_splits_tile_min(n_seed_rows, 32));
-                if (storage == VSB_F32) {
-                    sp.storage = VSB_BF16;
-                    sp.q = q16v;
-                    sp.x.rows = seed16_rows.as<uint8_t>();
-                    sp.x.sq = seed16_sq.as<float>();
-                    sp.x.nrm = seed16_nrm.as<float>();
-                    sp.x.row_bytes = row_bytes16;
-                }
-            } else {
-                sp.n_splits = vsb::exact_pick_splits(nb, n_seed_rows, sm_count);
-            }
-            const bool seed_scan = !seed_tc && nb <= vsb::graph_search_small_batch();
-            if (seed_scan) sp.n_splits = vsb::seed_scan_blocks(n_seed_rows);
-            CU(seed_part.ensure(vsb::exact_part_elems(nb, sp.n_splits, 32) * 8));
-            sp.part = seed_part.as<uint64_t>();
-            t_begin(PH_SEED, s);
-            if (seed_tc) seed_tc = vsb::launch_exact_candidates_tc(sp, s, true);
-            if (!seed_tc) {
-                const uint32_t splits = sp.n_splits;
-                sp = sp_native;
-                sp.n_splits = splits;
-                sp.part = seed_part.as<uint64_t>();
-                if (seed_scan) {
-                    // tiny batch: one warp per 4 seed rows, one winner per CTA
-                    CU(cudaMemsetAsync(seed_part.p, 0xFF, vsb::exact_part_elems(nb, sp.n_splits, 32) * 8, s));
-                    vsb::launch_seed_scan(storage, metric, qv, sp.x, seed_part.as<uint64_t>(), s);
-                } else {
-                    vsb::launch_exact_candidates(sp, s);
-                }
-            }
-            t_end(s);
-            CU(cudaGetLastError());
-            // ---- K4 beam search (on the bf16 traversal copy when VSB_FLAG_BF16_TRAVERSAL is set) ----
-            vsb::SearchParams gp;
-            gp.storage = trav16 ? VSB_BF16 : storage;
-            gp.metric = metric;
-            gp.q = trav16 ? q16v : qv;
-            gp.x = x;
-            if (trav16) {
-                gp.x.rows = rows16.as<uint8_t>();
-                gp.x.sq = sq16.as<float>();
-                gp.x.nrm = nrm16.as<float>();
-                gp.x.row_bytes = row_bytes16;
-            }
-            gp.graph = graph.as<uint32_t>();
-            gp.graph_stride = graph_stride;
-            gp.degree = degree;
-            gp.n_graphed = n_graphed;
-            gp.seed_lists = seed_part.as<uint64_t>();
-            gp.seed_stride = sp.n_splits * 32;
-            gp.n_seeds = n_seeds;
-            gp.seed_slots = seed_slots.as<uint32_t>();
-            gp.deny = deny_bm;
-            gp.keys = keys.as<uint64_t>();
-            gp.itopk = std::max(itopk, k);
-            gp.max_iters = max_iters;
-            gp.search_width = search_width;
-            gp.k = k;
-            gp.out_keys = g_keys;
-            gp.out_dists = g_dists;
-            gp.out_counts = have_tail ? nullptr : o_counts;
-            uint32_t kr = 0;
-            if (trav16) {
-                // hand the best kr bf16-ranked candidates to K3 for the canonical fp32 re-rank
-                kr = std::min<uint32_t>(round_up(std::max(2 * k, k + 22), 32), 256);
-                if (kr < k) return fail(VSB_EINVAL, "k=%u too large for the bf16-traversal re-rank (max 256)", k);
-                CU(rr_packed.ensure((size_t)nb * kr * 8));
-                gp.k = kr;
-                gp.out_packed = rr_packed.as<uint64_t>();
-                gp.out_counts = nullptr;
-            }
-            if (instrumented) {
-                CU(counters.ensure(16));
-                CU(cudaMemsetAsync(counters.p, 0, 16, s));
-                gp.counters = counters.as<unsigned long long>();
-            }
-            t_begin(PH_GRAPH, s);
-            vsb::launch_graph_search(gp, s);
-            t_end(s);
-            CU(cudaGetLastError());
-            if (trav16) {
-                vsb::ExactParams rp;
-                rp.storage = storage;
-                rp.metric = metric;
-                rp.q = qv;
-                rp.x = x;
-                rp.keys = keys.as<uint64_t>();
-                rp.part = rr_packed.as<uint64_t>();
-                rp.kp = kr;
-                rp.n_splits = 1;
-                t_begin(PH_EXACT, s);
-                vsb::launch_exact_rerank(rp, k, g_keys, g_dists, have_tail ? nullptr : o_counts, nullptr, -1, s);
-                t_end(s);
-                CU(cudaGetLastError());
-            }
-            if (instrumented) {
-                unsigned long long h[2];
-                CU(cudaMemcpyAsync(h, counters.p, 16, cudaMemcpyDeviceToHost, s));
-                CU(cudaStreamSynchronize(s));
-                last_evals = h[0];
-                last_parents = h[1];
-                last_queries = nb;
-            }
+            ST(graph_block(qv, nb, k, itopk, g_keys, g_dists, have_tail ? nullptr : o_counts, nullptr, nullptr, s));
         }
         if (have_tail) {
             t_begin(PH_EXACT, s);
@@ -858,6 +949,12 @@ vsb_status vsb_build(vsb_index* ix) {
     return ix->build();
 }
 
+vsb_status vsb_insert_pending(vsb_index* ix) {
+    if (!ix) return fail(VSB_EINVAL, "null index");
+    std::lock_guard<std::mutex> g(ix->mu);
+    return ix->stream_insert();
+}
+
 vsb_status vsb_export_graph(vsb_index* ix, uint32_t* rows_out, uint64_t* keys_out, uint64_t* n_graphed,
                             uint32_t* stride) {
     if (!ix) return fail(VSB_EINVAL, "null index");
@@ -883,6 +980,7 @@ vsb_status vsb_set_search_params(vsb_index* ix, const vsb_search_params* p) {
     if (p->n_seeds) ix->n_seeds = std::min<uint32_t>(p->n_seeds, 32);
     if (p->min_graph_size) ix->min_graph_size = p->min_graph_size;
     if (p->search_width) ix->search_width = std::min<uint32_t>(p->search_width, 4);
+    if (p->stream_threshold) ix->stream_threshold = p->stream_threshold == 0xFFFFFFFFu ? 0 : p->stream_threshold;
     return VSB_OK;
 }
 

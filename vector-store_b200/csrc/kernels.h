@@ -69,6 +69,10 @@ void launch_reverse_edges(const uint32_t* fwd, uint32_t n, uint32_t R, uint32_t*
 void launch_merge_graph(const uint32_t* fwd, const uint32_t* rev, const uint32_t* rev_cnt, uint32_t n,
                         uint32_t R, uint32_t* graph, uint32_t graph_stride, cudaStream_t stream);
 
+// K7 (graph_build.cu): link a batch of already-searched new rows into the graph
+void launch_stream_link(const uint64_t* cand, uint32_t n_new, uint32_t cand_stride, uint32_t first_slot, uint32_t R,
+                        uint32_t* graph, uint32_t graph_stride, cudaStream_t stream);
+
 // K4 (graph_search.cu) ---------------------------------------------------------------------------
 struct SearchParams {
     int storage = 0, metric = 0;

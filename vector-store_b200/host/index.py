@@ -117,6 +117,9 @@ class GpuIndex:
     def build(self) -> None:
         check(self._lib.vsb_build(self._h))
 
+    def insert_pending(self) -> None:
+        check(self._lib.vsb_insert_pending(self._h))
+
     def export_graph(self):
         """-> (rows u32 [n_graphed, stride], keys u64 [n_graphed])"""
         n = C.c_uint64(0)
@@ -129,8 +132,8 @@ class GpuIndex:
         return rows, keys
 
     def set_search_params(self, expansion_search: int = 0, max_iterations: int = 0, n_seeds: int = 0,
-                          min_graph_size: int = 0, search_width: int = 0) -> None:
-        p = VsbSearchParams(expansion_search, max_iterations, n_seeds, min_graph_size, search_width)
+                          min_graph_size: int = 0, search_width: int = 0, stream_threshold: int = 0) -> None:
+        p = VsbSearchParams(expansion_search, max_iterations, n_seeds, min_graph_size, search_width, stream_threshold)
         check(self._lib.vsb_set_search_params(self._h, C.byref(p)))
 
     def set_instrumented(self, on: bool) -> None:

@@ -25,7 +25,7 @@ class VsbOptions(C.Structure):
 
 class VsbSearchParams(C.Structure):
     _fields_ = [("expansion_search", C.c_uint32), ("max_iterations", C.c_uint32), ("n_seeds", C.c_uint32),
-                ("min_graph_size", C.c_uint32), ("search_width", C.c_uint32)]
+                ("min_graph_size", C.c_uint32), ("search_width", C.c_uint32), ("stream_threshold", C.c_uint32)]
 
 
 class VsbStats(C.Structure):
@@ -48,6 +48,7 @@ SYMBOLS = [
     ("vsb_remove", C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     ("vsb_contains", C.c_int, [_P, C.c_uint64]),
     ("vsb_build", C.c_int, [_P]),
+    ("vsb_insert_pending", C.c_int, [_P]),
     ("vsb_export_graph", C.c_int, [_P, _P, _P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     ("vsb_set_search_params", C.c_int, [_P, C.POINTER(VsbSearchParams)]),
     ("vsb_get_stats", C.c_int, [_P, C.POINTER(VsbStats)]),
