@@ -49,8 +49,8 @@ def parse_args():
     ap.add_argument("--storage", default="f32", choices=["f32", "bf16", "f16"])
     ap.add_argument("--target-recall", type=float, default=0.95)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="corpus rows of the bounded CPU-baseline sample")
-    ap.add_argument("--search-width", type=int, default=1)
-    ap.add_argument("--traversal", default="native", choices=["bf16", "native"],
+    ap.add_argument("--search-width", type=int, default=2)
+    ap.add_argument("--traversal", default="bf16", choices=["bf16", "native"],
                     help="f32 storage: traverse a bf16 copy and re-rank the best candidates on the f32 rows")
     ap.add_argument("--cpu-queries", type=int, default=2_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
