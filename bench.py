@@ -34,6 +34,7 @@ if ROOT not in sys.path:
 
 METRIC_NAME = "ann_search_qps_at_recall10_ge_0.95"
 UNIT = "queries/s"
+EF_SWEEP = (32, 64, 96, 128, 160, 192, 224, 256, 320, 384, 512)  # both arms pick the smallest that reaches the target
 
 
 def parse_args():
@@ -140,7 +141,7 @@ def cpu_hnsw_run(a, steps, warmup, full_line):
     del sims
     # smallest ef reaching the target recall (same rule as the GPU arm)
     ef_used, recall = 64, 0.0
-    for ef in (32, 64, 96, 128, 192, 256, 384, 512):
+    for ef in EF_SWEEP:
         h.set_ef(ef)
         hk, _ = h.search(q[:200], a.k)
         recall = O.recall_at_k(hk, tk)
@@ -286,7 +287,7 @@ def main():
     # ---- operating point: smallest expansion_search with recall@10 >= target ----
     sweep = []
     ef_used, recall = None, 0.0
-    for ef in (32, 64, 96, 128, 192, 256, 384, 512):
+    for ef in EF_SWEEP:
         idx.set_search_params(expansion_search=ef, search_width=a.search_width)
         search_step(q_dev[0])
         torch.cuda.synchronize()

@@ -467,3 +467,25 @@ def test_streaming_insert_k7():
     sk, sd, _ = idx.search_batch(x[n - 100:], 1)
     print(f"streamed rows found as their own top-1: {np.mean(sk[:, 0] == keys[n - 100:]):.3f}")
     assert np.mean(sk[:, 0] == keys[n - 100:]) >= 0.9
+
+
+def test_hybrid_build_allpairs_prefix_plus_streaming():
+    # above VSB_ALLPAIRS_MAX rows vsb_build all-pairs-builds a prefix and streams the rest in (K7)
+    import os
+    n, dim, k = 50000, 96, 10
+    x = embedding_like(n, dim, n_clusters=32)
+    q = embedding_like(500, dim, seed=4321, n_clusters=32)
+    keys = np.arange(n, dtype=np.uint64)
+    os.environ["VSB_ALLPAIRS_MAX"] = "20000"
+    try:
+        idx = make_index(x, keys, O.COS, O.BF16)
+    finally:
+        del os.environ["VSB_ALLPAIRS_MAX"]
+    idx.build()
+    st = idx.stats()
+    assert st["n_graphed"] == n
+    tk, _, _ = idx.search_batch(q, k, exact=True)
+    gk, _, gc = idx.search_batch(q, k)
+    r = O.recall_at_k(gk, tk)
+    print(f"hybrid build (20k all-pairs + 30k streamed): recall@10 = {r:.4f}")
+    assert np.all(gc == k) and r >= 0.93

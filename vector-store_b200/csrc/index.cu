@@ -218,6 +218,8 @@ struct vsb_index {
                            float* g_dists, uint32_t* counts_out, uint64_t* packed_out, const vsb::RowsView* q16_in,
                            cudaStream_t s);
     vsb_status stream_insert();
+    vsb_status sample_seeds(uint32_t n_rows);
+    uint32_t allpairs_max = 2000000;  // rows built by the all-pairs kNN pass; the rest is streamed in (K7)
     uint32_t stream_threshold = 4096;  // un-graphed tail rows that trigger an automatic streaming insert
     vsb_status search_dev(const float* d_q, uint64_t nq, uint32_t k, uint64_t* d_keys, float* d_dists,
                           uint32_t* d_counts, cudaStream_t s, bool exact, const uint32_t* d_allow,
@@ -416,7 +418,9 @@ vsb_status vsb_index::build() {
         n_seed_rows = 0;
         return VSB_OK;
     }
-    const uint32_t n = n_slots;
+    // All-pairs kNN lists cost 2*n^2*D flop: above `allpairs_max` rows only the first `allpairs_max` rows are
+    // built that way and the remaining rows are linked in with the streaming insert (K7, O(n log n)).
+    const uint32_t n = std::min<uint32_t>(n_slots, allpairs_max);
     const uint32_t R = degree;
     const uint32_t kin = std::min<uint32_t>(k_init, 128);
     DevBuf knn, fwd, rev, rev_cnt, scratch;
@@ -498,11 +502,29 @@ vsb_status vsb_index::build() {
                 t[2], t[3]);
         for (auto& e : ev) cudaEventDestroy(e);
     }
+    CU(cudaStreamSynchronize(stream));
+    std::swap(graph, new_graph);
+    n_graphed = n;
+    ST(sample_seeds(n));
+    if (n < n_slots) {
+        ST(stream_insert());
+        ST(sample_seeds(n_slots));  // entry points drawn from every row, not only the all-pairs prefix
+    }
+    return VSB_OK;
+}
+
+// Entry-point sample ("upper layer"): a stride permutation of the live slots below n_rows
+// (deterministic, seed-shifted), gathered into a contiguous block (+ bf16 shadow for f32 storage).
+vsb_status vsb_index::sample_seeds(uint32_t n) {
+    const vsb::RowsView x = corpus_view();
+    uint64_t live_below = 0;
+    for (uint32_t w = 0; w < (n + 31) / 32; ++w) live_below += __builtin_popcount(~h_deny[w]);
+    if (n % 32) live_below -= 32 - (n % 32);
     // entry-point sample: a stride permutation of the live slots (deterministic, seed-shifted)
     uint32_t S = 256;
-    const double target = 4.0 * std::sqrt((double)live);
+    const double target = 4.0 * std::sqrt((double)live_below);
     while (S < target && S < 8192) S <<= 1;
-    if (S > live / 4) S = (uint32_t)std::max<uint64_t>(32, live / 4);
+    if (S > live_below / 4) S = (uint32_t)std::max<uint64_t>(32, live_below / 4);
     std::vector<uint32_t> h_seeds;
     h_seeds.reserve(S);
     {
@@ -537,8 +559,6 @@ vsb_status vsb_index::build() {
         CU(cudaGetLastError());
     }
     CU(cudaStreamSynchronize(stream));
-    std::swap(graph, new_graph);
-    n_graphed = n;
     n_seed_rows = S;
     return VSB_OK;
 }
@@ -893,6 +913,7 @@ vsb_status vsb_create(const vsb_options* o, vsb_index** out) {
     ix->row_bytes16 = storage_row_bytes(VSB_BF16, o->dimensions);
     if (const char* e = getenv("VSB_DISABLE_TC")) ix->tc_enabled = !(e[0] == '1');
     if (const char* e = getenv("VSB_TC_MIN_ROWS")) ix->tc_min_rows = (uint32_t)strtoul(e, nullptr, 10);
+    if (const char* e = getenv("VSB_ALLPAIRS_MAX")) ix->allpairs_max = (uint32_t)strtoul(e, nullptr, 10);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
