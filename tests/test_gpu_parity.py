@@ -477,15 +477,17 @@ def test_hybrid_build_allpairs_prefix_plus_streaming():
     q = embedding_like(500, dim, seed=4321, n_clusters=32)
     keys = np.arange(n, dtype=np.uint64)
     os.environ["VSB_ALLPAIRS_MAX"] = "20000"
+    os.environ["VSB_ALLPAIRS_PREFIX"] = "20000"
     try:
         idx = make_index(x, keys, O.COS, O.BF16)
     finally:
         del os.environ["VSB_ALLPAIRS_MAX"]
+        del os.environ["VSB_ALLPAIRS_PREFIX"]
     idx.build()
     st = idx.stats()
     assert st["n_graphed"] == n
     tk, _, _ = idx.search_batch(q, k, exact=True)
     gk, _, gc = idx.search_batch(q, k)
     r = O.recall_at_k(gk, tk)
-    print(f"hybrid build (20k all-pairs + 30k streamed): recall@10 = {r:.4f}")
+    print(f"hybrid build (20k all-pairs + 30k streamed + refine): recall@10 = {r:.4f}")
     assert np.all(gc == k) and r >= 0.93

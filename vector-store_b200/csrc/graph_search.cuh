@@ -40,6 +40,7 @@ struct K4Args {
     float* out_dists;
     uint32_t* out_counts;
     uint64_t* out_packed;  // if set: emit the first k live entries as packed (ord(dist)<<32 | slot) for K3 instead of keys
+    long long self_base;   // >= 0: query i is row self_base + i of x and is left out of its own result
     unsigned long long* counters;
 };
 
@@ -348,6 +349,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
         const uint32_t slot = packed_lo(e) & ~kExpandedBit;
         bool valid = e != kInvalidPacked;
         if (valid && a.deny != nullptr && bit_test(a.deny, slot)) valid = false;
+        if (valid && a.self_base >= 0 && slot == (uint32_t)(a.self_base + q)) valid = false;
         const uint32_t m = __ballot_sync(kFullMask, valid);
         const uint32_t pos = count + __popc(m & ((1u << lane) - 1));
         if (valid && pos < a.k) {
@@ -545,6 +547,7 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
             const uint32_t slot = packed_lo(e) & ~kExpandedBit;
             bool valid = e != kInvalidPacked;
             if (valid && a.deny != nullptr && bit_test(a.deny, slot)) valid = false;
+            if (valid && a.self_base >= 0 && slot == (uint32_t)(a.self_base + q)) valid = false;
             const uint32_t m = __ballot_sync(kFullMask, valid);
             const uint32_t pos = count + __popc(m & ((1u << lane) - 1));
             if (valid && pos < a.k) {

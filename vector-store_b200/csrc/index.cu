@@ -216,10 +216,14 @@ struct vsb_index {
     uint32_t tc_min_rows = 8192;  // below this the SIMT K1 is used (launch + pipeline fill dominate)
     vsb_status graph_block(const vsb::RowsView& qv, uint32_t nb, uint32_t k, uint32_t itopk_eff, uint64_t* g_keys,
                            float* g_dists, uint32_t* counts_out, uint64_t* packed_out, const vsb::RowsView* q16_in,
-                           cudaStream_t s);
+                           cudaStream_t s, long long self_base = -1);
+    vsb_status graph_from_knn(const uint64_t* knn, uint32_t n, uint32_t kin, const uint32_t* deny_bm);
+    vsb_status refine_graph();
+    uint32_t allpairs_prefix = 131072;  // rows of the exact all-pairs pass when n > allpairs_max
     vsb_status stream_insert();
     vsb_status sample_seeds(uint32_t n_rows);
-    uint32_t allpairs_max = 2000000;  // rows built by the all-pairs kNN pass; the rest is streamed in (K7)
+    uint32_t allpairs_max = 262144;   // up to this many rows the graph comes from exact all-pairs kNN lists
+    uint32_t refine_passes = 1;       // refinement passes after a streamed build
     uint32_t stream_threshold = 4096;  // un-graphed tail rows that trigger an automatic streaming insert
     vsb_status search_dev(const float* d_q, uint64_t nq, uint32_t k, uint64_t* d_keys, float* d_dists,
                           uint32_t* d_counts, cudaStream_t s, bool exact, const uint32_t* d_allow,
@@ -420,10 +424,10 @@ vsb_status vsb_index::build() {
     }
     // All-pairs kNN lists cost 2*n^2*D flop: above `allpairs_max` rows only the first `allpairs_max` rows are
     // built that way and the remaining rows are linked in with the streaming insert (K7, O(n log n)).
-    const uint32_t n = std::min<uint32_t>(n_slots, allpairs_max);
+    const uint32_t n = n_slots <= allpairs_max ? n_slots : std::min<uint32_t>(n_slots, allpairs_prefix);
     const uint32_t R = degree;
     const uint32_t kin = std::min<uint32_t>(k_init, 128);
-    DevBuf knn, fwd, rev, rev_cnt, scratch;
+    DevBuf knn;
     CU(knn.ensure((size_t)n * kin * 8));
     const vsb::RowsView x = corpus_view();
     const uint32_t* deny_bm = any_tombstone ? deny.as<uint32_t>() : nullptr;
@@ -447,7 +451,7 @@ vsb_status vsb_index::build() {
         shx.nrm = sh_nrm.as<float>();
     }
     const bool btime = getenv("VSB_BUILD_TIMING") != nullptr;
-    cudaEvent_t ev[6];
+    cudaEvent_t ev[2];
     if (btime) {
         for (auto& e : ev) cudaEventCreate(&e);
         cudaEventRecord(ev[0], stream);
@@ -474,42 +478,112 @@ vsb_status vsb_index::build() {
     sh_rows.release();
     sh_sq.release();
     sh_nrm.release();
-    if (btime) cudaEventRecord(ev[1], stream);
+    if (btime) {
+        cudaEventRecord(ev[1], stream);
+        cudaEventSynchronize(ev[1]);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ev[0], ev[1]);
+        fprintf(stderr, "[vsb200 build] exact all-pairs kNN lists (K1+K3) over %u rows: %.1f ms\n", n, t);
+        cudaEventRecord(ev[0], stream);
+    }
+    ST(graph_from_knn(knn.as<uint64_t>(), n, kin, deny_bm));
+    knn.release();
+    ST(sample_seeds(n));
+    if (btime) {
+        cudaEventRecord(ev[1], stream);
+        cudaEventSynchronize(ev[1]);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ev[0], ev[1]);
+        fprintf(stderr, "[vsb200 build] prune + reverse + merge + seeds: %.1f ms\n", t);
+        cudaEventRecord(ev[0], stream);
+    }
+    if (n < n_slots) {
+        // large index: link the remaining rows with the streaming insert (K7), then rebuild every row's
+        // list from an ANN search over that navigable graph and prune it exactly like the all-pairs lists
+        ST(stream_insert());
+        ST(sample_seeds(n_slots));  // entry points drawn from every row, not only the all-pairs prefix
+        if (btime) {
+            cudaEventRecord(ev[1], stream);
+            cudaEventSynchronize(ev[1]);
+            float t = 0.f;
+            cudaEventElapsedTime(&t, ev[0], ev[1]);
+            fprintf(stderr, "[vsb200 build] streaming insert of %u rows (K7): %.1f ms\n", n_slots - n, t);
+            cudaEventRecord(ev[0], stream);
+        }
+        if (refine_passes > 0) {
+            for (uint32_t pass = 0; pass < refine_passes; ++pass) ST(refine_graph());
+            if (btime) {
+                cudaEventRecord(ev[1], stream);
+                cudaEventSynchronize(ev[1]);
+                float t = 0.f;
+                cudaEventElapsedTime(&t, ev[0], ev[1]);
+                fprintf(stderr, "[vsb200 build] %u refine pass(es) (K4 kNN lists + K6): %.1f ms\n", refine_passes, t);
+            }
+        }
+    }
+    if (btime)
+        for (auto& e : ev) cudaEventDestroy(e);
+    return VSB_OK;
+}
+
+// K6 pipeline: packed kNN lists [n][kin] -> fixed-degree graph rows (replaces `graph`, sets n_graphed = n)
+vsb_status vsb_index::graph_from_knn(const uint64_t* knn, uint32_t n, uint32_t kin, const uint32_t* deny_bm) {
+    const uint32_t R = degree;
+    DevBuf fwd, rev, rev_cnt, scratch;
     CU(fwd.ensure((size_t)n * R * 4));
     CU(rev.ensure((size_t)n * R * 4));
     CU(rev_cnt.ensure((size_t)n * 4));
-    vsb::launch_prune_detour(knn.as<uint64_t>(), n, kin, R, deny_bm, fwd.as<uint32_t>(), stream);
+    vsb::launch_prune_detour(knn, n, kin, R, deny_bm, fwd.as<uint32_t>(), stream);
     CU(cudaGetLastError());
-    if (btime) cudaEventRecord(ev[2], stream);
     const size_t sb = vsb::reverse_edges_scratch_bytes(n, R);
     CU(scratch.ensure(sb));
     vsb::launch_reverse_edges(fwd.as<uint32_t>(), n, R, rev.as<uint32_t>(), rev_cnt.as<uint32_t>(), scratch.p,
                               scratch.bytes, stream);
     CU(cudaGetLastError());
-    if (btime) cudaEventRecord(ev[3], stream);
+    scratch.release();
     DevBuf new_graph;
     CU(new_graph.ensure((size_t)std::max<uint64_t>(capacity, n) * graph_stride * 4));  // room for streamed rows
     vsb::launch_merge_graph(fwd.as<uint32_t>(), rev.as<uint32_t>(), rev_cnt.as<uint32_t>(), n, R,
                             new_graph.as<uint32_t>(), graph_stride, stream);
     CU(cudaGetLastError());
-
-    if (btime) {
-        cudaEventRecord(ev[4], stream);
-        cudaEventSynchronize(ev[4]);
-        float t[4];
-        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
-        fprintf(stderr, "[vsb200 build] n=%u knn(K1+K3)=%.1f ms prune=%.1f ms reverse=%.1f ms merge=%.1f ms\n", n, t[0], t[1],
-                t[2], t[3]);
-        for (auto& e : ev) cudaEventDestroy(e);
-    }
     CU(cudaStreamSynchronize(stream));
     std::swap(graph, new_graph);
     n_graphed = n;
-    ST(sample_seeds(n));
-    if (n < n_slots) {
-        ST(stream_insert());
-        ST(sample_seeds(n_slots));  // entry points drawn from every row, not only the all-pairs prefix
+    return VSB_OK;
+}
+
+// One refinement pass over a complete (streamed) graph: every row searches the graph for its own
+// k_init nearest rows (K4, beam = expansion_add) and the lists go through the K6 pipeline again.
+vsb_status vsb_index::refine_graph() {
+    const uint32_t n = n_graphed;
+    if (n == 0) return VSB_OK;
+    const uint32_t kin = std::min<uint32_t>(k_init, 128);
+    const uint32_t ef_add = opt.expansion_add ? opt.expansion_add : 128;
+    const uint32_t ef = std::min<uint32_t>(round_up(std::max(ef_add, kin + 1), 32), 512);
+    const uint32_t* deny_bm = any_tombstone ? deny.as<uint32_t>() : nullptr;
+    DevBuf knn;
+    CU(knn.ensure((size_t)n * kin * 8));
+    const uint32_t QB = 16384;
+    for (uint32_t b0 = 0; b0 < n; b0 += QB) {
+        const uint32_t nb = std::min(QB, n - b0);
+        vsb::RowsView qv;
+        qv.rows = rows.as<uint8_t>() + (size_t)b0 * row_bytes;
+        qv.sq = sq.as<float>() + b0;
+        qv.nrm = nrm.as<float>() + b0;
+        qv.row_bytes = row_bytes;
+        qv.n = nb;
+        vsb::RowsView q16;
+        if (trav16) {
+            q16.rows = rows16.as<uint8_t>() + (size_t)b0 * row_bytes16;
+            q16.sq = sq16.as<float>() + b0;
+            q16.nrm = nrm16.as<float>() + b0;
+            q16.row_bytes = row_bytes16;
+            q16.n = nb;
+        }
+        ST(graph_block(qv, nb, kin, ef, nullptr, nullptr, nullptr, knn.as<uint64_t>() + (size_t)b0 * kin,
+                       trav16 ? &q16 : nullptr, stream, (long long)b0));
     }
+    ST(graph_from_knn(knn.as<uint64_t>(), n, kin, deny_bm));
     return VSB_OK;
 }
 
@@ -569,7 +643,7 @@ vsb_status vsb_index::sample_seeds(uint32_t n) {
 //   q16_in                        : bf16 copy of the queries if the caller already has one (corpus rows), else built here
 vsb_status vsb_index::graph_block(const vsb::RowsView& qv, uint32_t nb, uint32_t k, uint32_t itopk_eff,
                                   uint64_t* g_keys, float* g_dists, uint32_t* counts_out, uint64_t* packed_out,
-                                  const vsb::RowsView* q16_in, cudaStream_t s) {
+                                  const vsb::RowsView* q16_in, cudaStream_t s, long long self_base) {
     const vsb::RowsView x = corpus_view();
     const uint32_t* deny_bm = any_tombstone ? deny.as<uint32_t>() : nullptr;
     const bool have_tail = counts_out == nullptr;  // the caller merges and counts later
@@ -674,6 +748,7 @@ vsb_status vsb_index::graph_block(const vsb::RowsView& qv, uint32_t nb, uint32_t
     gp.out_keys = g_keys;
     gp.out_dists = g_dists;
     gp.out_counts = have_tail ? nullptr : o_counts;
+    gp.self_base = self_base;
     uint32_t kr = 0;
     if (packed_out != nullptr) {
         gp.out_packed = packed_out;
@@ -914,6 +989,8 @@ vsb_status vsb_create(const vsb_options* o, vsb_index** out) {
     if (const char* e = getenv("VSB_DISABLE_TC")) ix->tc_enabled = !(e[0] == '1');
     if (const char* e = getenv("VSB_TC_MIN_ROWS")) ix->tc_min_rows = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("VSB_ALLPAIRS_MAX")) ix->allpairs_max = (uint32_t)strtoul(e, nullptr, 10);
+    if (const char* e = getenv("VSB_ALLPAIRS_PREFIX")) ix->allpairs_prefix = (uint32_t)strtoul(e, nullptr, 10);
+    if (const char* e = getenv("VSB_REFINE_PASSES")) ix->refine_passes = (uint32_t)strtoul(e, nullptr, 10);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);

@@ -91,6 +91,7 @@ struct SearchParams {
     float* out_dists = nullptr;
     uint32_t* out_counts = nullptr;
     uint64_t* out_packed = nullptr;          // packed (dist, slot) output for a following K3 re-rank
+    long long self_base = -1;                // >= 0: query i is row self_base + i (excluded from its own list)
     unsigned long long* counters = nullptr;  // [2]: distance evals, parent expansions (instrumented only)
 };
 void launch_graph_search(const SearchParams& p, cudaStream_t stream);
