@@ -217,6 +217,20 @@ def main():
 
     # ---- corpus shard: generated and ingested chunk by chunk (host RAM stays bounded) ----
     trav16 = a.storage == "f32" and a.traversal == "bf16"
+    # ---- process warm-up (untimed): a 40k-row index exercises every kernel once, so CUDA's lazy module
+    # loading and the first cudaMalloc's are not billed to the timed build below ----
+    warm = v.GpuIndex(a.dim, v.Metric.Cos, scalar, device=local_rank, bf16_traversal=trav16)
+    warm.reserve(40_000)
+    wx = ds.embedding_like(40_000, a.dim, seed=7)
+    warm.add_batch(np.arange(40_000, dtype=np.uint64)[:30_000], wx[:30_000])
+    warm.build()
+    warm.add_batch(np.arange(30_000, 40_000, dtype=np.uint64), wx[30_000:])
+    warm.insert_pending()
+    warm.search_batch(wx[:1000], a.k)
+    warm.search_batch(wx[:4], a.k)
+    warm.close()
+    del warm, wx
+
     idx = v.GpuIndex(a.dim, v.Metric.Cos, scalar, device=local_rank, bf16_traversal=trav16)
     idx.reserve(n_local)
     t_gen = 0.0
@@ -382,7 +396,8 @@ def main():
         "metric": METRIC_NAME, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": a.storage, "data": "synthetic",
-        "config": {"workload": workload_name(a), "index": "M=16 (degree 32) ef_add=128",
+        "config": {"workload": workload_name(a), "index": "M=16 (degree 32) ef_add=128; build = exact all-pairs kNN on a 131072-row prefix (tcgen05) + "
+                                                              "K7 streaming insert + one K4/K6 refinement pass",
                    "traversal": ("bf16 copy of the f32 rows for the graph traversal, fp32 re-rank of the best "
                                  "candidates on the f32 rows" if trav16 else "native storage scalar"),
                    "expansion_search": ef_used, "search_width": a.search_width,
