@@ -173,6 +173,24 @@ vsb_status vsb_merge_topk_dev(const uint64_t* d_keys, const float* d_distances, 
                               uint64_t q, uint32_t k, uint64_t* d_out_keys, float* d_out_distances,
                               uint32_t* d_out_counts, int device, void* stream);
 
+/* ---- N2: micro-batcher (what a Rust shim would put into the actor's recv loop, vs_index/mod.rs:30-45).
+ * Many threads call vsb_batcher_search with ONE query each (the reference's VsIndexSearch::Ann message,
+ * vs_index/actor.rs:38-56); a dispatcher thread coalesces up to max_batch requests, or whatever arrived
+ * within max_wait_us of the first, into one vsb_search and hands every caller its own row back. */
+typedef struct vsb_batcher vsb_batcher;
+vsb_status vsb_batcher_create(vsb_index* index, uint32_t dimensions, uint32_t max_batch, uint32_t max_wait_us,
+                              vsb_batcher** out);
+void vsb_batcher_destroy(vsb_batcher* batcher);
+vsb_status vsb_batcher_search(vsb_batcher* batcher, const float* query, uint32_t k, uint64_t* keys,
+                              float* distances, uint32_t* count);
+vsb_status vsb_batcher_stats(vsb_batcher* batcher, uint64_t* n_queries, uint64_t* n_batches);
+
+/* ---- N3: snapshot.  The reference rebuilds its in-memory index from a full table scan on every restart
+ * (db_cdc/checkpoint_saver.rs:103-112); a flat file of keys / tombstones / rows / graph makes
+ * restart O(read).  vsb_load creates a new handle on `device` (-1 = current). */
+vsb_status vsb_save(vsb_index* index, const char* path);
+vsb_status vsb_load(const char* path, int32_t device, vsb_index** out);
+
 /* A11: usearch.rs:1179-1205  f32_to_b1x8 (host utility, same bit order) */
 void vsb_f32_to_b1x8(const float* v, uint64_t n, uint8_t* out /* ceil(n/8) bytes */);
 

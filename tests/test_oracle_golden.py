@@ -184,3 +184,20 @@ def test_hnsw_cpu_recall_and_order():
     tk, _, _, _ = O.exact_topk(x, q, 10, O.COS)
     assert O.recall_at_k(hk, tk) >= 0.9
     assert np.all(np.diff(hd, axis=1) >= 0)
+
+
+def test_n4_fbin_ibin_roundtrip(tmp_path):
+    # crates/benchmark/src/data/fbin.rs:23-148: u32 count, u32 dimension, then row-major payload
+    from importlib import import_module
+    ds = import_module("vector_store_b200.host.datasets")
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((37, 12)).astype(np.float32)
+    gt = rng.integers(0, 37, size=(5, 10)).astype(np.int32)
+    ds.write_fbin(str(tmp_path / "d.fbin"), x)
+    ds.write_ibin(str(tmp_path / "g.ibin"), gt)
+    assert ds.read_bin_header(str(tmp_path / "d.fbin")) == (37, 12)
+    assert np.array_equal(ds.read_fbin(str(tmp_path / "d.fbin")), x)
+    assert np.array_equal(ds.read_fbin(str(tmp_path / "d.fbin"), start=30, count=100), x[30:])
+    assert np.array_equal(ds.read_ibin(str(tmp_path / "g.ibin")), gt)
+    raw = open(tmp_path / "d.fbin", "rb").read()
+    assert raw[:8] == np.array([37, 12], "<u4").tobytes() and len(raw) == 8 + 37 * 12 * 4

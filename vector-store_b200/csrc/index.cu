@@ -1187,3 +1187,135 @@ const char* vsb_last_error(void) { return g_last_error.c_str(); }
 const char* vsb_version(void) { return "vsb200-0.1.0"; }
 
 }  // extern "C"
+
+// ---- N3: snapshot ------------------------------------------------------------------------------
+namespace {
+struct SnapHeader {
+    char magic[8];  // "VSB200S1"
+    vsb_options opt;
+    uint64_t n_slots, n_graphed, capacity;
+    uint32_t row_bytes, graph_stride, degree, reserved;
+};
+
+bool write_dev(FILE* f, const void* dptr, size_t bytes, std::vector<uint8_t>& stage, cudaStream_t s) {
+    const size_t CH = stage.size();
+    for (size_t off = 0; off < bytes; off += CH) {
+        const size_t nb = std::min(CH, bytes - off);
+        if (cudaMemcpyAsync(stage.data(), static_cast<const uint8_t*>(dptr) + off, nb, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+            return false;
+        if (cudaStreamSynchronize(s) != cudaSuccess) return false;
+        if (fwrite(stage.data(), 1, nb, f) != nb) return false;
+    }
+    return true;
+}
+bool read_dev(FILE* f, void* dptr, size_t bytes, std::vector<uint8_t>& stage, cudaStream_t s) {
+    const size_t CH = stage.size();
+    for (size_t off = 0; off < bytes; off += CH) {
+        const size_t nb = std::min(CH, bytes - off);
+        if (fread(stage.data(), 1, nb, f) != nb) return false;
+        if (cudaMemcpyAsync(static_cast<uint8_t*>(dptr) + off, stage.data(), nb, cudaMemcpyHostToDevice, s) != cudaSuccess)
+            return false;
+        if (cudaStreamSynchronize(s) != cudaSuccess) return false;
+    }
+    return true;
+}
+}  // namespace
+
+extern "C" vsb_status vsb_save(vsb_index* ix, const char* path) {
+    if (!ix || !path) return fail(VSB_EINVAL, "null argument");
+    std::lock_guard<std::mutex> g(ix->mu);
+    CU(cudaSetDevice(ix->device));
+    ST(ix->use_stream(ix->stream));
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(VSB_EINVAL, "cannot open %s for writing", path);
+    SnapHeader h{};
+    memcpy(h.magic, "VSB200S1", 8);
+    h.opt = ix->opt;
+    h.n_slots = ix->n_slots;
+    h.n_graphed = ix->n_graphed;
+    h.capacity = ix->capacity;
+    h.row_bytes = ix->row_bytes;
+    h.graph_stride = ix->graph_stride;
+    h.degree = ix->degree;
+    std::vector<uint8_t> stage((size_t)64 << 20);
+    const size_t n = ix->n_slots;
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+    ok = ok && fwrite(ix->h_deny.data(), 4, (n + 31) / 32, f) == (n + 31) / 32;
+    ok = ok && write_dev(f, ix->keys.p, n * 8, stage, ix->stream);
+    ok = ok && write_dev(f, ix->rows.p, n * ix->row_bytes, stage, ix->stream);
+    ok = ok && write_dev(f, ix->sq.p, n * 4, stage, ix->stream);
+    ok = ok && write_dev(f, ix->nrm.p, n * 4, stage, ix->stream);
+    ok = ok && write_dev(f, ix->graph.p, (size_t)ix->n_graphed * ix->graph_stride * 4, stage, ix->stream);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(VSB_ECUDA, "short write or copy failure while saving %s", path);
+    return VSB_OK;
+}
+
+extern "C" vsb_status vsb_load(const char* path, int32_t device, vsb_index** out) {
+    if (!path || !out) return fail(VSB_EINVAL, "null argument");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(VSB_EINVAL, "cannot open %s", path);
+    SnapHeader h{};
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "VSB200S1", 8) != 0) {
+        fclose(f);
+        return fail(VSB_EINVAL, "%s is not a vsb200 snapshot", path);
+    }
+    h.opt.device = device;
+    vsb_index* ix = nullptr;
+    vsb_status st = vsb_create(&h.opt, &ix);
+    if (st != VSB_OK) {
+        fclose(f);
+        return st;
+    }
+    auto bail = [&](vsb_status code, const char* what) {
+        fclose(f);
+        vsb_destroy(ix);
+        return fail(code, "%s while loading %s", what, path);
+    };
+    if (h.row_bytes != ix->row_bytes || h.graph_stride != ix->graph_stride) return bail(VSB_EINVAL, "layout mismatch");
+    const size_t n = h.n_slots;  // nobody else holds this handle yet: no locking needed
+    if (ix->reserve(std::max<uint64_t>(h.capacity, std::max<uint64_t>(n, 1))) != VSB_OK) return bail(VSB_EOOM, "reserve failed");
+    std::vector<uint8_t> stage((size_t)64 << 20);
+    std::vector<uint64_t> h_keys(n);
+    bool ok = fread(ix->h_deny.data(), 4, (n + 31) / 32, f) == (n + 31) / 32;
+    ok = ok && fread(h_keys.data(), 8, n, f) == n;
+    if (!ok) return bail(VSB_EINVAL, "truncated file");
+    if (cudaMemcpy(ix->keys.p, h_keys.data(), n * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(ix->deny.p, ix->h_deny.data(), ((n + 31) / 32) * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail(VSB_ECUDA, "upload failed");
+    ok = read_dev(f, ix->rows.p, n * ix->row_bytes, stage, ix->stream);
+    ok = ok && read_dev(f, ix->sq.p, n * 4, stage, ix->stream);
+    ok = ok && read_dev(f, ix->nrm.p, n * 4, stage, ix->stream);
+    if (ok && h.n_graphed) {
+        if (ix->graph.ensure((size_t)std::max<uint64_t>(ix->capacity, h.n_graphed) * ix->graph_stride * 4) != cudaSuccess)
+            return bail(VSB_EOOM, "graph allocation failed");
+        ok = read_dev(f, ix->graph.p, (size_t)h.n_graphed * ix->graph_stride * 4, stage, ix->stream);
+    }
+    if (!ok) return bail(VSB_EINVAL, "truncated file or copy failure");
+    fclose(f);
+    ix->n_slots = (uint32_t)n;
+    ix->n_graphed = (uint32_t)h.n_graphed;
+    uint64_t live = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (ix->h_deny[i >> 5] >> (i & 31) & 1u) {
+            ix->any_tombstone = true;
+            continue;
+        }
+        ix->key2slot.emplace(h_keys[i], (uint32_t)i);
+        ++live;
+    }
+    ix->live = live;
+    ix->live_atomic.store(live);
+    if (ix->trav16 && n) {  // the bf16 traversal copy is derived data: regenerate instead of storing it
+        vsb::launch_convert_rows(VSB_BF16, ix->rows.as<float>(), (uint32_t)n, ix->row_bytes / 4, ix->rows16.as<uint8_t>(),
+                                 ix->row_bytes16, ix->sq16.as<float>(), ix->nrm16.as<float>(), ix->stream);
+    }
+    if (ix->n_graphed && ix->sample_seeds(ix->n_graphed) != VSB_OK) {
+        vsb_destroy(ix);
+        return VSB_ECUDA;
+    }
+    cudaStreamSynchronize(ix->stream);
+    *out = ix;
+    return VSB_OK;
+}

@@ -88,6 +88,8 @@ class GpuIndex:
 
     # ---- batched ABI ----
     def _check_dim(self, a: np.ndarray) -> None:
+        if self.dimensions is None:  # loaded from a snapshot: the library validates sizes
+            self.dimensions = a.shape[1]
         if a.ndim != 2 or a.shape[1] != self.dimensions:
             raise native.VsbError(native.VSB_EDIM, f"expected dimension {self.dimensions}, got {a.shape}")
 
@@ -173,6 +175,22 @@ class GpuIndex:
         check(self._lib.vsb_search_dev(self._h, d_queries, n, k, d_keys, d_dists, d_counts or None, stream or None,
                                        int(exact)))
 
+    def save(self, path: str) -> None:
+        check(self._lib.vsb_save(self._h, path.encode()))
+
+    @classmethod
+    def load(cls, path: str, device: int = -1) -> "GpuIndex":
+        l = lib()
+        h = C.c_void_p()
+        check(l.vsb_load(path.encode(), device, C.byref(h)))
+        self = cls.__new__(cls)
+        self._lib, self._h = l, h
+        st = VsbStats()
+        check(l.vsb_get_stats(h, C.byref(st)))
+        self.dimensions = None  # filled from the snapshot header by the caller if needed
+        self.metric = self.storage = None
+        return self
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             self._lib.vsb_destroy(self._h)
@@ -189,3 +207,41 @@ def merge_topk_dev(d_keys: int, d_dists: int, parts: int, q: int, k: int, d_out_
                    d_out_counts: int, device: int, stream: int) -> None:
     check(lib().vsb_merge_topk_dev(d_keys, d_dists, parts, q, k, d_out_keys, d_out_dists, d_out_counts or None,
                                    device, stream or None))
+
+
+class Batcher:
+    """N2 micro-batcher: `search(query, k)` may be called from many threads; calls are coalesced on the C++ side."""
+
+    def __init__(self, index: GpuIndex, max_batch: int = 1024, max_wait_us: int = 200):
+        self._lib = lib()
+        self._index = index  # keep the index alive
+        b = C.c_void_p()
+        check(self._lib.vsb_batcher_create(index._h, index.dimensions, max_batch, max_wait_us, C.byref(b)))
+        self._b = b
+        self._dim = index.dimensions
+
+    def search(self, query, k: int):
+        q = np.ascontiguousarray(query, dtype=np.float32).ravel()
+        if q.shape[0] != self._dim:
+            raise native.VsbError(native.VSB_EDIM, f"expected dimension {self._dim}, got {q.shape[0]}")
+        keys = np.empty(k, dtype=np.uint64)
+        dists = np.empty(k, dtype=np.float32)
+        cnt = C.c_uint32(0)
+        check(self._lib.vsb_batcher_search(self._b, _ptr(q), k, _ptr(keys), _ptr(dists), C.byref(cnt)))
+        return keys[:cnt.value], dists[:cnt.value]
+
+    def stats(self):
+        nq, nb = C.c_uint64(0), C.c_uint64(0)
+        check(self._lib.vsb_batcher_stats(self._b, C.byref(nq), C.byref(nb)))
+        return int(nq.value), int(nb.value)
+
+    def close(self) -> None:
+        if getattr(self, "_b", None):
+            self._lib.vsb_batcher_destroy(self._b)
+            self._b = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
