@@ -103,6 +103,18 @@ __global__ void gather_rows_kernel(const uint8_t* __restrict__ rows, uint32_t ro
     }
 }
 
+__global__ void gather_u64_kernel(const uint64_t* __restrict__ in, const uint32_t* __restrict__ slots, uint32_t n,
+                                  uint64_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[slots[i]];
+}
+
+void launch_gather_u64(const uint64_t* in, const uint32_t* slots, uint32_t n, uint64_t* out, cudaStream_t stream) {
+    if (n == 0) return;
+    gather_u64_kernel<<<(n + 255) / 256, 256, 0, stream>>>(in, slots, n, out);
+    g_kernel_launches += 1;
+}
+
 void launch_convert_rows(int storage, const float* in, uint32_t n_rows, uint32_t dim, uint8_t* out,
                          uint32_t row_bytes, float* sq, float* nrm, cudaStream_t stream) {
     if (n_rows == 0) return;

@@ -221,6 +221,7 @@ struct vsb_index {
     vsb_status refine_graph();
     uint32_t allpairs_prefix = 131072;  // rows of the exact all-pairs pass when n > allpairs_max
     vsb_status stream_insert();
+    vsb_status compact();
     vsb_status sample_seeds(uint32_t n_rows);
     uint32_t allpairs_max = 262144;   // up to this many rows the graph comes from exact all-pairs kNN lists
     uint32_t refine_passes = 1;       // refinement passes after a streamed build
@@ -414,9 +415,67 @@ vsb_status vsb_index::exact_block(const vsb::RowsView& q, const vsb::RowsView& x
     return VSB_OK;
 }
 
+// Tombstone compaction (part of vsb_build): live rows are gathered to the front in slot order, the key map is
+// rebuilt and the tombstone bitmap cleared, so a long-running delete/update stream does not leak HBM.
+vsb_status vsb_index::compact() {
+    std::vector<uint32_t> live_slots;
+    live_slots.reserve((size_t)live);
+    for (uint32_t i = 0; i < n_slots; ++i)
+        if (!(h_deny[i >> 5] >> (i & 31) & 1u)) live_slots.push_back(i);
+    const uint32_t m = (uint32_t)live_slots.size();
+    if (m != n_slots) {
+        DevBuf d_slots, n_rows, n_sq, n_nrm, n_keys, n_rows16, n_sq16, n_nrm16;
+        CU(d_slots.ensure(std::max<size_t>((size_t)m * 4, 16)));
+        CU(cudaMemcpyAsync(d_slots.p, live_slots.data(), (size_t)m * 4, cudaMemcpyHostToDevice, stream));
+        auto alloc = [&](DevBuf& b, size_t bytes) -> cudaError_t {
+            cudaError_t e = cudaMalloc(&b.p, bytes ? bytes : 16);
+            if (e == cudaSuccess) b.bytes = bytes ? bytes : 16; else b.p = nullptr;
+            return e;
+        };
+        CU(alloc(n_rows, (size_t)capacity * row_bytes));
+        CU(alloc(n_sq, (size_t)capacity * 4));
+        CU(alloc(n_nrm, (size_t)capacity * 4));
+        CU(alloc(n_keys, (size_t)capacity * 8));
+        vsb::launch_gather_rows(rows.as<uint8_t>(), row_bytes, sq.as<float>(), nrm.as<float>(), d_slots.as<uint32_t>(), m,
+                                n_rows.as<uint8_t>(), n_sq.as<float>(), n_nrm.as<float>(), stream);
+        vsb::launch_gather_u64(keys.as<uint64_t>(), d_slots.as<uint32_t>(), m, n_keys.as<uint64_t>(), stream);
+        if (trav16) {
+            CU(alloc(n_rows16, (size_t)capacity * row_bytes16));
+            CU(alloc(n_sq16, (size_t)capacity * 4));
+            CU(alloc(n_nrm16, (size_t)capacity * 4));
+            vsb::launch_gather_rows(rows16.as<uint8_t>(), row_bytes16, sq16.as<float>(), nrm16.as<float>(),
+                                    d_slots.as<uint32_t>(), m, n_rows16.as<uint8_t>(), n_sq16.as<float>(),
+                                    n_nrm16.as<float>(), stream);
+        }
+        CU(cudaGetLastError());
+        std::vector<uint64_t> h_keys(m);
+        CU(cudaMemcpyAsync(h_keys.data(), n_keys.p, (size_t)m * 8, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemsetAsync(deny.p, 0, deny.bytes, stream));
+        CU(cudaStreamSynchronize(stream));
+        std::swap(rows, n_rows);
+        std::swap(sq, n_sq);
+        std::swap(nrm, n_nrm);
+        std::swap(keys, n_keys);
+        if (trav16) {
+            std::swap(rows16, n_rows16);
+            std::swap(sq16, n_sq16);
+            std::swap(nrm16, n_nrm16);
+        }
+        std::fill(h_deny.begin(), h_deny.end(), 0u);
+        key2slot.clear();
+        for (uint32_t i = 0; i < m; ++i) key2slot.emplace(h_keys[i], i);
+        n_slots = m;
+        n_graphed = 0;
+        n_seed_rows = 0;
+    }
+    any_tombstone = false;
+    return VSB_OK;
+}
+
 vsb_status vsb_index::build() {
     CU(cudaSetDevice(device));
     ST(use_stream(stream));
+    if (any_tombstone) ST(compact());
     if (live < min_graph_size || !vsb::graph_search_supported(row_bytes)) {
         n_graphed = 0;
         n_seed_rows = 0;

@@ -26,6 +26,8 @@ void launch_gather_rows(const uint8_t* rows, uint32_t row_bytes, const float* sq
                         const uint32_t* slots, uint32_t n, uint8_t* out_rows, float* out_sq, float* out_nrm,
                         cudaStream_t stream);
 
+void launch_gather_u64(const uint64_t* in, const uint32_t* slots, uint32_t n, uint64_t* out, cudaStream_t stream);
+
 // K1 + K3 (exact.cu) ----------------------------------------------------------------------------
 struct ExactParams {
     int storage = 0, metric = 0;
