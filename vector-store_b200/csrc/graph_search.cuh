@@ -455,7 +455,12 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
             }
             __syncthreads();
             if (warp == 0) {
-                for (uint32_t g = 0; g * 32 < n_new; ++g) warp_list_merge(list, (int)a.itopk, newp[g * 32 + lane], lane, less);
+                for (uint32_t g = 0; g * 32 < n_new; ++g) {
+                    const uint64_t cand = newp[g * 32 + lane];
+                    const uint64_t worst = list[a.itopk - 1];
+                    if (__ballot_sync(kFullMask, cand < worst) == 0) continue;  // nothing here can enter the list
+                    warp_list_merge(list, (int)a.itopk, cand, lane, less);
+                }
                 if (lane == 0) {
                     ctrl[2] += n_new;
                     ctrl[0] = 0;
