@@ -43,8 +43,10 @@ def main():
     idx.set_search_params(expansion_search=a.ef, search_width=2, stream_threshold=4096)
     pool = ds.embedding_like(extra, a.dim, seed=777)        # vectors for inserts / updates
     queries = ds.embedding_like(20_000, a.dim, seed=4321)
-    live = {int(k): int(k) for k in range(a.n)}             # row id -> current key (epoch in the high bits)
-    live_rows = list(range(a.n))
+    cap_rows = a.n + extra
+    alive = np.zeros(cap_rows, dtype=bool)                  # table row id -> is it live
+    alive[:a.n] = True
+    cur_key = np.arange(cap_rows, dtype=np.uint64)          # row id -> current key (epoch in the high 16 bits)
     next_row, pool_pos = a.n, 0
     tick_ops = max(1, a.rate // 10)
     lat1, q1000, applied = [], [], 0
@@ -59,35 +61,22 @@ def main():
         n_ins = int(tick_ops * 0.7)
         n_del = int(tick_ops * 0.2)
         n_upd = tick_ops - n_ins - n_del
-        sel = rng.choice(len(live_rows), n_del + n_upd, replace=False)
-        victims = [live_rows[i] for i in sel]
-        del_rows, upd_rows = victims[:n_del], victims[n_del:]
-        rm_keys = np.array([live[r] for r in victims], dtype=np.uint64)
+        cand = np.unique(rng.integers(0, next_row, size=4 * (n_del + n_upd)))
+        cand = rng.permutation(cand[alive[cand]])[:n_del + n_upd]
+        del_rows, upd_rows = cand[:n_del], cand[n_del:]
         t1 = time.perf_counter()
-        idx.remove_batch(rm_keys)                                            # RemoveValue / RemoveBeforeAddValue
-        for r in del_rows:
-            del live[r]
-        dead = set(del_rows)
-        if dead:
-            live_rows = [r for r in live_rows if r not in dead] if len(dead) * 50 > len(live_rows) else live_rows
-        new_keys, rows_idx = [], []
-        for r in upd_rows:                                                    # same row id, bumped epoch
-            k = (np.uint64(live[r]) + EPOCH)
-            live[r] = int(k)
-            new_keys.append(int(k))
-        for _ in range(n_ins):
-            live[next_row] = next_row
-            live_rows.append(next_row)
-            new_keys.append(next_row)
-            next_row += 1
+        idx.remove_batch(cur_key[cand])                                      # RemoveValue / RemoveBeforeAddValue
+        alive[del_rows] = False
+        cur_key[upd_rows] += EPOCH                                           # same row id, bumped epoch
+        ins_rows = np.arange(next_row, next_row + n_ins)
+        alive[ins_rows] = True
+        next_row += n_ins
+        new_keys = np.concatenate([cur_key[upd_rows], cur_key[ins_rows]])
         vecs = pool[pool_pos:pool_pos + len(new_keys)]
         pool_pos += len(new_keys)
-        idx.add_batch(np.array(new_keys, dtype=np.uint64), vecs)             # AddVector (K7 links them in batches)
-        applied += tick_ops
+        idx.add_batch(new_keys, vecs)                                        # AddVector (K7 links them in batches)
+        applied += len(cand) + n_ins
         mut_s = time.perf_counter() - t1
-        # lazily drop deleted rows from the sampling list
-        if tick % 20 == 0:
-            live_rows = [r for r in live_rows if r in live]
         # ---- interleaved queries ----
         for _ in range(5):
             i = rng.integers(0, len(queries))

@@ -322,14 +322,49 @@ __global__ void __launch_bounds__(K3_WARPS * 32) exact_rerank_kernel(K3Args a) {
     for (uint32_t b = 0; b < a.kp; b += 32) {
         const uint64_t mine = cand[b + lane];
         uint64_t res = kInvalidPacked;
-        for (int c = 0; c < 32; ++c) {
-            const uint64_t pc = shfl_u64(mine, c);
-            const uint32_t slot = packed_lo(pc);
-            if (pc == kInvalidPacked) break;  // ascending: the rest of the block is padding
-            if (slot == self_slot) continue;
-            const uint4* xrow = reinterpret_cast<const uint4*>(a.x_rows + (size_t)slot * a.x_row_bytes);
-            const float d = warp_distance<ST, METRIC>(qrow, xrow, n_chunks, qn, a.x_nrm[slot], lane);
-            if (lane == c) res = pack_ds(d, slot);
+        bool end_of_list = false;
+        // four candidates in flight per step: 4x the memory-level parallelism of a one-by-one loop,
+        // each accumulator still follows the canonical order
+        for (int c0 = 0; c0 < 32 && !end_of_list; c0 += 4) {
+            uint32_t slot[4];
+            bool on[4];
+            bool any = false;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint64_t pc = shfl_u64(mine, c0 + u);
+                if (pc == kInvalidPacked) end_of_list = true;  // ascending: the rest of the block is padding
+                slot[u] = packed_lo(pc);
+                on[u] = pc != kInvalidPacked && slot[u] != self_slot;
+                any = any || on[u];
+            }
+            if (!any) continue;
+            ChunkAcc<ST, METRIC> acc[4];
+            const uint4* xr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                xr[u] = reinterpret_cast<const uint4*>(a.x_rows + (size_t)(on[u] ? slot[u] : 0u) * a.x_row_bytes);
+            for (int ch = lane; ch < n_chunks; ch += 32) {
+                const uint4 qv = qrow[ch];
+                uint4 xv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (on[u]) xv[u] = ldg_nc_v4(xr[u] + ch);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (on[u]) acc[u].add(qv, xv[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!on[u]) continue;
+                float f = 0.0f;
+                int i = 0;
+                if constexpr (Storage<ST>::kFloat)
+                    f = butterfly_sum(acc[u].f);
+                else
+                    i = butterfly_sum_i(acc[u].i);
+                const float d = finish_distance<ST, METRIC>(f, i, qn, a.x_nrm[slot[u]]);
+                if (lane == c0 + u) res = pack_ds(d, slot[u]);
+            }
         }
         if (__ballot_sync(kFullMask, res != kInvalidPacked) == 0) continue;
         res = warp_sort32(res, lane, less);
