@@ -75,7 +75,7 @@ typedef struct {
 /* Runtime tunables of the graph search (all 0 = keep current). */
 typedef struct {
     uint32_t expansion_search; /* itopk; rounded up to a multiple of 32, <= 512 */
-    uint32_t max_iterations;   /* parent expansions per query; 0 = auto */
+    uint32_t max_iterations;   /* beam-search iterations per query; 0 = keep, >= 1000000 = automatic */
     uint32_t n_seeds;          /* entry points taken from the seed layer, <= 32 */
     uint32_t min_graph_size;   /* below this many live vectors search is brute force */
     uint32_t search_width;     /* parents expanded per iteration, 1..4 */

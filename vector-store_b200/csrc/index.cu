@@ -1133,7 +1133,7 @@ vsb_status vsb_set_search_params(vsb_index* ix, const vsb_search_params* p) {
     if (!ix || !p) return fail(VSB_EINVAL, "null argument");
     std::lock_guard<std::mutex> g(ix->mu);
     if (p->expansion_search) ix->itopk = std::min<uint32_t>(round_up(p->expansion_search, 32), 512);
-    if (p->max_iterations) ix->max_iters = p->max_iterations;
+    if (p->max_iterations) ix->max_iters = p->max_iterations >= 1000000u ? 0 : p->max_iterations;  // >= 1e6: back to auto
     if (p->n_seeds) ix->n_seeds = std::min<uint32_t>(p->n_seeds, 32);
     if (p->min_graph_size) ix->min_graph_size = p->min_graph_size;
     if (p->search_width) ix->search_width = std::min<uint32_t>(p->search_width, 4);
