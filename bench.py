@@ -73,17 +73,21 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler is started before the
+    warm-up so it is already streaming when the (possibly very short) timed region begins; samples are matched to
+    the region by their own timestamps."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+        "clocks_event_reasons.sw_power_cap"
 
     def __init__(self, device: int):
         self.device, self.proc, self.lines = device, None, []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.device), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -91,32 +95,51 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        rows = []
+        for t_recv, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                rows.append((t_recv, float(f[1]), float(f[2]), float(f[3]), f[4:8]))
             except ValueError:
                 continue
-            for nm, val in zip(names, f[3:7]):
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.03 <= r[0] <= self.t1 + 0.03]
+        note = None
+        if not inside and rows:  # region shorter than the sampling period: take the samples closest to it
+            mid = 0.5 * ((self.t0 or 0) + (self.t1 or 0))
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+            note = "timed region shorter than the 20 ms sampling period: nearest samples used"
+        reasons = set()
+        for r in inside:
+            for nm, val in zip(names, r[4]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None,
+               "sm_max_mhz": max(r[2] for r in inside) if inside else None,
+               "power_w_max": max(r[3] for r in inside) if inside else None, "samples": len(inside),
+               "reasons": sorted(reasons)}
+        if note:
+            out["note"] = note
+        return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -270,6 +293,9 @@ def main():
     h_keys = torch.empty((B, k), dtype=torch.int64).pin_memory()
     h_dists = torch.empty((B, k), dtype=torch.float32).pin_memory()
     h_counts = torch.empty((B,), dtype=torch.int32).pin_memory()
+    assert world == 1 or B % world == 0, "query batch must divide evenly over the ranks"
+    q_slice = torch.empty((B // world, a.dim), dtype=torch.float32, device=dev)
+    q_e2e = torch.empty((B, a.dim), dtype=torch.float32, device=dev)
     gath_k = torch.empty((world, B, k), dtype=torch.int64, device=dev)
     gath_d = torch.empty((world, B, k), dtype=torch.float32, device=dev)
 
@@ -341,21 +367,23 @@ def main():
     bytes_per_query = E * (trav_row_bytes + 4) + P * st["graph_degree"] * 4  # +4: the row's norm (cosine)
 
     # ---- timed region 1: inputs resident in HBM ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(a.warmup):
         search_step(q_dev[i % NB])
     barrier()
     launches0 = idx.stats()["kernel_launches"]
     idx.set_kernel_timing(True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.profiler.start()  # ncu --profile-from-start off captures exactly the timed region
+    sampler.mark_begin()
     ev0.record()
     for i in range(a.steps):
         search_step(q_dev[i % NB])
     ev1.record()
     barrier()
+    sampler.mark_end()
     torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
@@ -379,8 +407,12 @@ def main():
         if world == 1:
             idx.search_raw(q_host[b].data_ptr(), B, k, h_keys.data_ptr(), h_dists.data_ptr(), h_counts.data_ptr())
             return
-        q_dev[b].copy_(q_host[b], non_blocking=True)
-        search_step(q_dev[b])
+        # every shard needs every query: each rank uploads 1/N of the batch from its pinned buffer and the
+        # slices are exchanged over NVLink (job-wide H2D = one batch, not N batches)
+        s0, s1 = shard.shard_range(B, rank, world)
+        q_slice[:s1 - s0].copy_(q_host[b][s0:s1], non_blocking=True)
+        dist.all_gather_into_tensor(q_e2e, q_slice)
+        search_step(q_e2e)
         h_keys.copy_(out_k, non_blocking=True)
         h_dists.copy_(out_d, non_blocking=True)
         torch.cuda.synchronize()

@@ -62,6 +62,7 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
     a.queue_cap = a.search_width * deg_pad < 32 ? 32 : a.search_width * deg_pad;
     a.metric = p.metric;
     a.out_keys = p.out_keys; a.out_dists = p.out_dists; a.out_counts = p.out_counts; a.out_packed = p.out_packed; a.self_base = p.self_base; a.counters = p.counters;
+    a.out_stride = p.out_stride ? p.out_stride : p.k;
     const int cpl = pick_cpl((int)(p.x.row_bytes / 16));
     if (p.q.n <= graph_search_small_batch()) {
         // CTA-per-query kernel: 8 warps and up to 8 parents per iteration for one query

@@ -41,6 +41,7 @@ struct K4Args {
     uint32_t* out_counts;
     uint64_t* out_packed;  // if set: emit the first k live entries as packed (ord(dist)<<32 | slot) for K3 instead of keys
     long long self_base;   // >= 0: query i is row self_base + i of x and is left out of its own result
+    uint32_t out_stride;   // entries per query in out_packed (>= k; the rest is padded with kInvalidPacked)
     unsigned long long* counters;
 };
 
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
         const uint32_t pos = count + __popc(m & ((1u << lane) - 1));
         if (valid && pos < a.k) {
             if (a.out_packed != nullptr) {
-                a.out_packed[(size_t)q * a.k + pos] = ((uint64_t)packed_hi(e) << 32) | slot;
+                a.out_packed[(size_t)q * a.out_stride + pos] = ((uint64_t)packed_hi(e) << 32) | slot;
             } else {
                 a.out_keys[(size_t)q * a.k + pos] = a.keys[slot];
                 a.out_dists[(size_t)q * a.k + pos] = ord_to_f32(packed_hi(e));
@@ -363,9 +364,11 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
         count += __popc(m);
     }
     if (count > a.k) count = a.k;
+    if (a.out_packed != nullptr) {
+        for (uint32_t i = count + lane; i < a.out_stride; i += 32) a.out_packed[(size_t)q * a.out_stride + i] = kInvalidPacked;
+    }
     for (uint32_t i = count + lane; i < a.k; i += 32) {
         if (a.out_packed != nullptr) {
-            a.out_packed[(size_t)q * a.k + i] = kInvalidPacked;
         } else {
             a.out_keys[(size_t)q * a.k + i] = 0xFFFFFFFFFFFFFFFFull;
             a.out_dists[(size_t)q * a.k + i] = __int_as_float(0x7F800000);
@@ -557,7 +560,7 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
             const uint32_t pos = count + __popc(m & ((1u << lane) - 1));
             if (valid && pos < a.k) {
                 if (a.out_packed != nullptr) {
-                    a.out_packed[(size_t)q * a.k + pos] = ((uint64_t)packed_hi(e) << 32) | slot;
+                    a.out_packed[(size_t)q * a.out_stride + pos] = ((uint64_t)packed_hi(e) << 32) | slot;
                 } else {
                     a.out_keys[(size_t)q * a.k + pos] = a.keys[slot];
                     a.out_dists[(size_t)q * a.k + pos] = ord_to_f32(packed_hi(e));
@@ -566,9 +569,11 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
             count += __popc(m);
         }
         if (count > a.k) count = a.k;
+        if (a.out_packed != nullptr) {
+            for (uint32_t i = count + lane; i < a.out_stride; i += 32) a.out_packed[(size_t)q * a.out_stride + i] = kInvalidPacked;
+        }
         for (uint32_t i = count + lane; i < a.k; i += 32) {
             if (a.out_packed != nullptr) {
-                a.out_packed[(size_t)q * a.k + i] = kInvalidPacked;
             } else {
                 a.out_keys[(size_t)q * a.k + i] = 0xFFFFFFFFFFFFFFFFull;
                 a.out_dists[(size_t)q * a.k + i] = __int_as_float(0x7F800000);

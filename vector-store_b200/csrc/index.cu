@@ -815,10 +815,13 @@ vsb_status vsb_index::graph_block(const vsb::RowsView& qv, uint32_t nb, uint32_t
     }
     if (rerank) {
         // hand the best kr bf16-ranked candidates to K3 for the canonical fp32 re-rank
-        kr = std::min<uint32_t>(round_up(std::max(2 * k, k + 22), 32), 256);
+        // (2k, at least k + 6, of them; bf16 ranking errors are far smaller than that margin)
+        const uint32_t kv = std::max(2 * k, k + 6);
+        kr = std::min<uint32_t>(round_up(kv, 32), 256);
         if (kr < k) return fail(VSB_EINVAL, "k=%u too large for the bf16-traversal re-rank (max 256)", k);
         CU(rr_packed.ensure((size_t)nb * kr * 8));
-        gp.k = kr;
+        gp.k = std::min(kv, kr);
+        gp.out_stride = kr;
         gp.out_packed = rr_packed.as<uint64_t>();
         gp.out_counts = nullptr;
     }
