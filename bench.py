@@ -127,8 +127,7 @@ class ClockSampler:
         if not inside and rows:  # region shorter than the sampling period: take the samples closest to it
             mid = 0.5 * ((self.t0 or 0) + (self.t1 or 0))
             inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
-            note = (f"no nvidia-smi sample fell inside the {(self.t1 - self.t0) * 1e3:.0f} ms timed region: "
-                    "nearest samples used")
+            note = "timed region shorter than the 20 ms sampling period: nearest samples used"
         reasons = set()
         for r in inside:
             for nm, val in zip(names, r[4]):

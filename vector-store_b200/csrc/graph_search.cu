@@ -1,6 +1,4 @@
 // graph_search.cu — host launcher of K4 (kernel in graph_search.cuh, instantiated per storage scalar).
-#include <algorithm>
-
 #include "graph_search.cuh"
 
 namespace vsb {
@@ -83,18 +81,7 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
         g_kernel_launches += 1;
         return;
     }
-    // persistent grid: 3 CTAs (12 query warps) per SM is what registers and shared memory allow
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (sm_count <= 0) sm_count = 148;
-    }
-    const uint32_t want_ctas = (p.q.n + K4_WARPS - 1) / K4_WARPS;
-    dim3 grid(std::min<uint32_t>(want_ctas, 3u * (uint32_t)sm_count));
-    a.work_counter = p.work_counter;
-    cudaMemsetAsync(a.work_counter, 0, 4, stream);
+    dim3 grid((p.q.n + K4_WARPS - 1) / K4_WARPS);
     const size_t smem = (size_t)K4_WARPS * ((size_t)a.itopk * 8 + ((size_t)4 << bits) + (size_t)a.queue_cap * 8);
     switch (p.storage) {
         case VSB_ST_F32: launch_k4_f32(a, cpl, grid, smem, stream); break;

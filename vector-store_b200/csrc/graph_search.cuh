@@ -42,7 +42,6 @@ struct K4Args {
     uint64_t* out_packed;  // if set: emit the first k live entries as packed (ord(dist)<<32 | slot) for K3 instead of keys
     long long self_base;   // >= 0: query i is row self_base + i of x and is left out of its own result
     uint32_t out_stride;   // entries per query in out_packed (>= k; the rest is padded with kInvalidPacked)
-    uint32_t* work_counter;  // K4: zero-initialised global counter the persistent warps pull query ids from
     unsigned long long* counters;
 };
 
@@ -195,6 +194,9 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
 
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * K4_WARPS + warp;
+    if (q >= a.nq) return;
+
     const uint32_t hsize = 1u << a.hash_bits, hmask = hsize - 1;
     const uint32_t qcap = a.queue_cap;
     const size_t per_warp = (size_t)a.itopk * 8 + (size_t)hsize * 4 + (size_t)qcap * 8;
@@ -207,15 +209,6 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
     const bool is_cos = a.metric == VSB_METRIC_COS;
     const int n_chunks = a.x_row_bytes / 16;
     const bool full = n_chunks == CPL * 32;
-
-    // Persistent warps: the grid is sized to the SMs (3 CTAs x 4 warps each) and every warp pulls the next
-    // query from a global counter, so uneven query costs and the last partial wave do not idle SMs.
-    for (;;) {
-    uint32_t q = 0;
-    if (lane == 0) q = atomicAdd(a.work_counter, 1u);
-    q = __shfl_sync(kFullMask, q, 0);
-    if (q >= a.nq) break;
-    __syncwarp();
 
     for (uint32_t i = lane; i < a.itopk; i += 32) list[i] = kInvalidPacked;
     for (uint32_t i = lane; i < hsize; i += 32) hash[i] = kHashEmpty;
@@ -388,8 +381,6 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
             atomicAdd(&a.counters[1], n_parents);
         }
     }
-    __syncwarp();
-    }  // persistent work loop
 }
 
 // ------------------------------------------------------------------------------------------------

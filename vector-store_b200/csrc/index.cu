@@ -134,7 +134,6 @@ struct vsb_index {
     bool trav16 = false;
     uint32_t row_bytes16 = 0;
     DevBuf rr_packed;             // K4 -> K3 hand-over of the traversal shadow path
-    DevBuf work_counter;          // K4 persistent work queue counter
     DevBuf seed_rows, seed_sq, seed_nrm, seed_slots;
     DevBuf seed16_rows, seed16_sq, seed16_nrm;   // bf16 shadow of the seed block (f32 storage only)
     DevBuf q16_rows, q16_sq, q16_nrm;            // bf16 shadow of the converted queries (f32 storage only)
@@ -809,8 +808,6 @@ vsb_status vsb_index::graph_block(const vsb::RowsView& qv, uint32_t nb, uint32_t
     gp.out_dists = g_dists;
     gp.out_counts = have_tail ? nullptr : o_counts;
     gp.self_base = self_base;
-    CU(work_counter.ensure(16));
-    gp.work_counter = work_counter.as<uint32_t>();
     uint32_t kr = 0;
     if (packed_out != nullptr) {
         gp.out_packed = packed_out;

@@ -95,7 +95,6 @@ struct SearchParams {
     uint64_t* out_packed = nullptr;          // packed (dist, slot) output for a following K3 re-rank
     long long self_base = -1;                // >= 0: query i is row self_base + i (excluded from its own list)
     uint32_t out_stride = 0;                 // packed entries per query (0 = k)
-    uint32_t* work_counter = nullptr;        // 4-byte device scratch for K4's persistent work queue
     unsigned long long* counters = nullptr;  // [2]: distance evals, parent expansions (instrumented only)
 };
 void launch_graph_search(const SearchParams& p, cudaStream_t stream);
