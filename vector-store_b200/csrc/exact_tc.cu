@@ -20,6 +20,8 @@
 // kind::f16 (bf16 / f16 storage, exact products) or kind::tf32 (f32 storage, candidate grade).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "kernels.h"
 #include "select.cuh"
 
@@ -30,7 +32,8 @@ namespace {
 constexpr int TC_M = 128;
 constexpr int TC_N = 256;
 constexpr int TC_KBYTES = 128;
-constexpr int TC_STAGES = 3;
+constexpr int TC_STAGES = 3;       // 1-CTA variant: 3 x 48 KB
+constexpr int TC2_STAGES = 4;      // 2-CTA variant: 4 x 32 KB (each CTA stages its own A and half of B)
 constexpr int TC_BUFCAP = 64;
 constexpr int TC_THREADS = 192;
 constexpr uint32_t TC_A_BYTES = TC_M * TC_KBYTES;   // 16 KB
@@ -40,6 +43,9 @@ constexpr uint32_t TC_OFF_BUF = TC_STAGES * TC_STAGE_BYTES;
 constexpr uint32_t TC_OFF_COLP = TC_OFF_BUF + TC_M * TC_BUFCAP * 8;
 constexpr uint32_t TC_OFF_BAR = TC_OFF_COLP + 2 * TC_N * 4;
 constexpr uint32_t TC_SMEM_BYTES = TC_OFF_BAR + 128 + 1024;  // + alignment slack
+// both variants use the same offsets for buf / colp / barriers: 4 x 32 KB < 3 x 48 KB
+static_assert(TC2_STAGES * (TC_A_BYTES + TC_B_BYTES / 2) <= TC_OFF_BUF, "2-CTA stages must fit the stage area");
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even (leader) CTA
 
 enum { KIND_BF16 = 0, KIND_F16 = 1, KIND_TF32 = 2 };
 
@@ -91,6 +97,53 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* leader_bar, int c0,
+                                                int c1) {
+    // issued by both CTAs of the pair; the transaction bytes are credited to the leader CTA's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank) {
+    asm volatile(
+        "{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\nmbarrier.arrive.shared::cluster.b64 _, [ra];\n}\n" ::"r"(
+            smem_u32(bar)),
+        "r"(cta_rank)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+    // arrives on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far retire
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tc_mma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if constexpr (KIND == KIND_TF32) {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -137,7 +190,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return d;
 }
 
-template <int KIND, int METRIC, bool TILE_MIN>
+// CTA2 = true: the kernel runs as clusters of two CTAs (cta_group::2).  Each CTA owns its own 128 query rows
+// (its half of the M = 256 accumulator) and stages only 128 of the tile's 256 corpus rows; the leader CTA issues
+// the MMAs for the pair, so a CTA moves 32 KB instead of 48 KB per K slab and a fourth stage fits.
+template <int KIND, int METRIC, bool TILE_MIN, bool CTA2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     exact_candidates_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                                TcArgs a) {
@@ -146,9 +202,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     uint64_t* buf = reinterpret_cast<uint64_t*>(smem + TC_OFF_BUF);
     float* colp = reinterpret_cast<float*>(smem + TC_OFF_COLP);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
-    uint64_t* full = bars;                    // [TC_STAGES]
-    uint64_t* empty = bars + TC_STAGES;       // [TC_STAGES]
-    uint64_t* tmem_full = bars + 2 * TC_STAGES;   // [2]
+    uint64_t* full = bars;                    // [<= TC2_STAGES]
+    uint64_t* empty = bars + TC2_STAGES;      // [<= TC2_STAGES]
+    uint64_t* tmem_full = bars + 2 * TC2_STAGES;  // [2]
     uint64_t* tmem_empty = tmem_full + 2;         // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -161,27 +217,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t n_tiles = r_hi > r_lo ? (r_hi - r_lo + TC_N - 1) / TC_N : 0;
     const uint32_t n_slabs = (a.row_bytes + TC_KBYTES - 1) / TC_KBYTES;
     constexpr int ELEMS_PER_SLAB = KIND == KIND_TF32 ? 32 : 64;
+    constexpr int STAGES = CTA2 ? TC2_STAGES : TC_STAGES;
+    constexpr uint32_t B_BYTES = CTA2 ? TC_B_BYTES / 2 : TC_B_BYTES;
+    constexpr uint32_t STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    const uint32_t cta_rank = CTA2 ? cluster_cta_rank() : 0u;
+    const bool leader = cta_rank == 0;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);
+            mbar_init(&tmem_empty[i], CTA2 ? 8 : 4);  // the leader also waits for the peer CTA's epilogue warps
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                     "r"(512u));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        if constexpr (CTA2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                         "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                         "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -193,11 +260,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const int n0 = (int)(r_lo + t * TC_N);
                 for (uint32_t slab = 0; slab < n_slabs; ++slab) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * TC_STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full[stage], TC_STAGE_BYTES);
-                    tma_load_2d(sa, &tmap_q, &full[stage], (int)(slab * ELEMS_PER_SLAB), (int)q0);
-                    tma_load_2d(sa + TC_A_BYTES, &tmap_x, &full[stage], (int)(slab * ELEMS_PER_SLAB), n0);
-                    if (++stage == TC_STAGES) {
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    if constexpr (CTA2) {
+                        // both CTAs load their own halves; all bytes are credited to the leader's barrier
+                        if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+                        tma_load_2d_2sm(sa, &tmap_q, &full[stage], (int)(slab * ELEMS_PER_SLAB), (int)q0);
+                        tma_load_2d_2sm(sa + TC_A_BYTES, &tmap_x, &full[stage], (int)(slab * ELEMS_PER_SLAB),
+                                        n0 + (int)cta_rank * (TC_N / 2));
+                    } else {
+                        mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+                        tma_load_2d(sa, &tmap_q, &full[stage], (int)(slab * ELEMS_PER_SLAB), (int)q0);
+                        tma_load_2d(sa + TC_A_BYTES, &tmap_x, &full[stage], (int)(slab * ELEMS_PER_SLAB), n0);
+                    }
+                    if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -206,10 +281,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (lane == 0 && leader) {
             constexpr uint32_t fmt = KIND == KIND_BF16 ? 1u : (KIND == KIND_F16 ? 0u : 2u);
             constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_N >> 3) << 17) |
-                                       ((uint32_t)(TC_M >> 4) << 24);
+                                       ((uint32_t)((CTA2 ? 2 * TC_M : TC_M) >> 4) << 24);
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = 0; t < n_tiles; ++t) {
                 const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
@@ -219,21 +294,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 for (uint32_t slab = 0; slab < n_slabs; ++slab) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                     const uint64_t adesc = make_smem_desc(sa);
                     const uint64_t bdesc = make_smem_desc(sa + TC_A_BYTES);
 #pragma unroll
                     for (uint32_t k = 0; k < TC_KBYTES / 32; ++k) {
                         // +32 bytes of K inside the swizzle atom = +2 in the (addr >> 4) field
-                        tc_mma<KIND>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (slab | k) != 0 ? 1u : 0u);
+                        if constexpr (CTA2)
+                            tc_mma_2sm<KIND>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (slab | k) != 0 ? 1u : 0u);
+                        else
+                            tc_mma<KIND>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (slab | k) != 0 ? 1u : 0u);
                     }
-                    tc_commit(&empty[stage]);
-                    if (++stage == TC_STAGES) {
+                    if constexpr (CTA2) tc_commit_2sm(&empty[stage]); else tc_commit(&empty[stage]);
+                    if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                tc_commit(&tmem_full[acc]);
+                if constexpr (CTA2) tc_commit_2sm(&tmem_full[acc]); else tc_commit(&tmem_full[acc]);
             }
         }
     } else {
@@ -375,17 +453,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             // accumulator drained: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if (CTA2 && !leader) mbar_arrive_remote(&tmem_empty[acc], 0);
+                else mbar_arrive(&tmem_empty[acc]);
+            }
         }
         const uint32_t rest = __ballot_sync(kFullMask, cnt > 0);
         if (rest) flush(rest);
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+        if constexpr (CTA2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
     }
 }
 
@@ -422,26 +506,48 @@ bool make_map(CUtensorMap* map, int kind, const void* base, uint32_t rows, uint3
     return r == CUDA_SUCCESS;
 }
 
-template <int KIND, int METRIC>
-void launch_tc_inst(const CUtensorMap& mq, const CUtensorMap& mx, const TcArgs& a, dim3 grid, cudaStream_t stream) {
-    if (a.tile_min) {
-        cudaFuncSetAttribute(exact_candidates_tc_kernel<KIND, METRIC, true>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-        exact_candidates_tc_kernel<KIND, METRIC, true><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mq, mx, a);
+template <int KIND, int METRIC, bool TILE_MIN, bool CTA2>
+void launch_tc_one(const CUtensorMap& mq, const CUtensorMap& mx, const TcArgs& a, dim3 grid, cudaStream_t stream) {
+    auto kern = exact_candidates_tc_kernel<KIND, METRIC, TILE_MIN, CTA2>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    if constexpr (CTA2) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, kern, mq, mx, a);
     } else {
-        cudaFuncSetAttribute(exact_candidates_tc_kernel<KIND, METRIC, false>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-        exact_candidates_tc_kernel<KIND, METRIC, false><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mq, mx, a);
+        kern<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mq, mx, a);
+    }
+}
+
+template <int KIND, int METRIC>
+void launch_tc_inst(const CUtensorMap& mq, const CUtensorMap& mx, const TcArgs& a, dim3 grid, cudaStream_t stream,
+                    bool cta2) {
+    if (a.tile_min) {
+        launch_tc_one<KIND, METRIC, true, false>(mq, mx, a, grid, stream);  // the seed layer is tiny: 1-CTA form
+    } else if (cta2) {
+        launch_tc_one<KIND, METRIC, false, true>(mq, mx, a, grid, stream);
+    } else {
+        launch_tc_one<KIND, METRIC, false, false>(mq, mx, a, grid, stream);
     }
 }
 
 template <int KIND>
 void launch_tc_kind(int metric, const CUtensorMap& mq, const CUtensorMap& mx, const TcArgs& a, dim3 grid,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, bool cta2) {
     switch (metric) {
-        case VSB_METRIC_L2SQ: launch_tc_inst<KIND, VSB_METRIC_L2SQ>(mq, mx, a, grid, stream); break;
-        case VSB_METRIC_COS: launch_tc_inst<KIND, VSB_METRIC_COS>(mq, mx, a, grid, stream); break;
-        default: launch_tc_inst<KIND, VSB_METRIC_IP>(mq, mx, a, grid, stream); break;
+        case VSB_METRIC_L2SQ: launch_tc_inst<KIND, VSB_METRIC_L2SQ>(mq, mx, a, grid, stream, cta2); break;
+        case VSB_METRIC_COS: launch_tc_inst<KIND, VSB_METRIC_COS>(mq, mx, a, grid, stream, cta2); break;
+        default: launch_tc_inst<KIND, VSB_METRIC_IP>(mq, mx, a, grid, stream, cta2); break;
     }
 }
 
@@ -473,9 +579,14 @@ uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count) {
 bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream, bool tile_min) {
     if (p.q.n == 0 || p.x_hi <= p.x_lo) return true;
     const int kind = p.storage == VSB_ST_F32 ? KIND_TF32 : (p.storage == VSB_ST_BF16 ? KIND_BF16 : KIND_F16);
+    static const bool cta2_env = [] {
+        const char* e = getenv("VSB_TC_2CTA");
+        return e != nullptr && e[0] == '1';
+    }();
+    const bool cta2 = cta2_env && !tile_min;
     CUtensorMap mq, mx;
     if (!make_map(&mq, kind, p.q.rows, p.q.n, p.q.row_bytes, TC_M)) return false;
-    if (!make_map(&mx, kind, p.x.rows, p.x_hi, p.x.row_bytes, TC_N)) return false;
+    if (!make_map(&mx, kind, p.x.rows, p.x_hi, p.x.row_bytes, cta2 ? TC_N / 2 : TC_N)) return false;
     TcArgs a;
     a.q_sq = p.q.sq; a.q_nrm = p.q.nrm; a.nq = p.q.n;
     a.x_sq = p.x.sq; a.x_nrm = p.x.nrm; a.x_lo = p.x_lo; a.x_hi = p.x_hi; a.row_bytes = p.x.row_bytes;
@@ -486,11 +597,13 @@ bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream, bool 
     a.rows_per_split = ((rps + TC_N - 1) / TC_N) * TC_N;
     a.part = p.part;
     a.tile_min = tile_min ? 1 : 0;
-    dim3 grid((p.q.n + TC_M - 1) / TC_M, p.n_splits);
+    uint32_t q_tiles = (p.q.n + TC_M - 1) / TC_M;
+    if (cta2) q_tiles = (q_tiles + 1) & ~1u;  // CTA pairs: an odd tail tile gets an all-padding partner
+    dim3 grid(q_tiles, p.n_splits);
     switch (kind) {
-        case KIND_BF16: launch_tc_kind<KIND_BF16>(p.metric, mq, mx, a, grid, stream); break;
-        case KIND_F16: launch_tc_kind<KIND_F16>(p.metric, mq, mx, a, grid, stream); break;
-        default: launch_tc_kind<KIND_TF32>(p.metric, mq, mx, a, grid, stream); break;
+        case KIND_BF16: launch_tc_kind<KIND_BF16>(p.metric, mq, mx, a, grid, stream, cta2); break;
+        case KIND_F16: launch_tc_kind<KIND_F16>(p.metric, mq, mx, a, grid, stream, cta2); break;
+        default: launch_tc_kind<KIND_TF32>(p.metric, mq, mx, a, grid, stream, cta2); break;
     }
     g_kernel_launches += 1;
     g_tc_launches += 1;
