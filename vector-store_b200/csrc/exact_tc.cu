@@ -565,13 +565,25 @@ uint32_t exact_tc_min_splits_tile_min(uint32_t n_rows, uint32_t kp) {
 }
 
 uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count) {
+    // One CTA per SM: the sweep takes ceil(q_tiles * s / SMs) waves of 1/s of the corpus each.  Pick the split
+    // count that minimises waves / s (wave quantisation: 79 query tiles x 2 splits = 158 CTAs would run as
+    // two waves on 148 SMs), with a small per-split penalty for the extra list warm-up and merging.
     const uint32_t q_tiles = (nq + TC_M - 1) / TC_M;
-    uint32_t want = ((uint32_t)sm_count + q_tiles - 1) / q_tiles;   // >= one CTA per SM
-    const uint32_t max_by_rows = (n_rows + 2 * TC_N - 1) / (2 * TC_N);  // >= 2 tiles per split
-    uint32_t s = want < max_by_rows ? want : max_by_rows;
-    if (s < 1) s = 1;
-    if (s > 1024) s = 1024;
-    return s;
+    uint32_t max_by_rows = (n_rows + 2 * TC_N - 1) / (2 * TC_N);  // >= 2 tiles per split
+    if (max_by_rows < 1) max_by_rows = 1;
+    const uint32_t s_max = max_by_rows < 160 ? max_by_rows : 160;
+    uint32_t best = 1;
+    double best_cost = 1e30;
+    for (uint32_t s = 1; s <= s_max; ++s) {
+        const uint32_t ctas = q_tiles * s;
+        const uint32_t waves = (ctas + (uint32_t)sm_count - 1) / (uint32_t)sm_count;
+        const double cost = (double)waves / s * (1.0 + 0.015 * s);
+        if (cost < best_cost - 1e-12) {
+            best_cost = cost;
+            best = s;
+        }
+    }
+    return best;
 }
 
 // Same contract as launch_exact_candidates (exact.cu); returns false if the TMA descriptors could
