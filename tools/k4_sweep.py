@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--widths", default="1,2,4")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--bf16-traversal", action="store_true")
+    ap.add_argument("--exact-only", action="store_true", help="skip the graph build and the ANN sweep")
     a = ap.parse_args()
     import torch
     from importlib import import_module
@@ -37,7 +38,8 @@ def main():
         xc = ds.embedding_like(min(CH, a.n - c0), a.dim, seed=1234 + c0 // CH)
         idx.add_batch(np.arange(c0, c0 + len(xc), dtype=np.uint64), xc)
     t0 = time.perf_counter()
-    idx.build()
+    if not a.exact_only:
+        idx.build()
     print(json.dumps({"build_s": time.perf_counter() - t0, "stats": idx.stats()}), flush=True)
     dev = torch.device("cuda", 0)
     B, k = a.batch, 10
@@ -60,6 +62,8 @@ def main():
                       "tensor_core_path": idx.stats()["tc_launches"] > tc0, "same_as_first": bool((ok.cpu().numpy() == gt).all())}),
           flush=True)
     peak = 6541.1
+    if a.exact_only:
+        return
     for w in [int(x) for x in a.widths.split(",")]:
         for ef in [int(x) for x in a.efs.split(",")]:
             idx.set_search_params(expansion_search=ef, search_width=w)
