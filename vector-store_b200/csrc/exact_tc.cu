@@ -41,7 +41,7 @@ constexpr uint32_t TC_B_BYTES = TC_N * TC_KBYTES;   // 32 KB
 constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr uint32_t TC_OFF_BUF = TC_STAGES * TC_STAGE_BYTES;
 constexpr uint32_t TC_OFF_COLP = TC_OFF_BUF + TC_M * TC_BUFCAP * 8;
-constexpr uint32_t TC_OFF_BAR = TC_OFF_COLP + 2 * TC_N * 4;
+constexpr uint32_t TC_OFF_BAR = TC_OFF_COLP + 4 * 2 * TC_N * 4;  // per epilogue warp, per accumulator stage
 constexpr uint32_t TC_SMEM_BYTES = TC_OFF_BAR + 128 + 1024;  // + alignment slack
 // both variants use the same offsets for buf / colp / barriers: 4 x 32 KB < 3 x 48 KB
 static_assert(TC2_STAGES * (TC_A_BYTES + TC_B_BYTES / 2) <= TC_OFF_BUF, "2-CTA stages must fit the stage area");
@@ -372,9 +372,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const uint32_t n0 = r_lo + t * TC_N;
             float best_d = __int_as_float(0x7F800000);
             uint32_t best_c = kInvalidSlot;
-            // per-column parameter of this tile (NaN marks columns outside the split)
-            float* cp = colp + acc * TC_N;
-            for (int c = etid; c < TC_N; c += 128) {
+            // per-column parameter of this tile (NaN marks columns outside the split); every epilogue warp keeps
+            // its own copy so the four warps never wait for each other
+            float* cp = colp + ((warp - 2) * 2 + acc) * TC_N;
+            for (int c = lane; c < TC_N; c += 32) {
                 const uint32_t n = n0 + c;
                 float p = __int_as_float(0x7FC00000);
                 if (n < r_hi) {
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 }
                 cp[c] = p;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            __syncwarp();
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_N;
@@ -394,10 +395,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             for (int ch = 0; ch < TC_N / 32; ++ch) {
                 uint32_t v[32];
                 tmem_ld32(taddr + ch * 32, v);
-                // fast path: branch-free distance + threshold test of 32 columns (~4 instructions each)
+                // fast path: distance of 32 columns and their minimum (FFMA + FMNMX per column); only when the
+                // minimum beats the row's threshold — rare once the list has warmed up — is anything else done
                 const float4* cp4 = reinterpret_cast<const float4*>(cp + ch * 32);
                 float d[32];
-                uint32_t mask = 0;
+                float dmin = __int_as_float(0x7F800000);
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
                     const float4 p4 = cp4[j4];
@@ -409,20 +411,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         if constexpr (METRIC == VSB_METRIC_L2SQ) d[j] = fmaf(dot, -2.0f, pj[jj]) + qsq;
                         else if constexpr (METRIC == VSB_METRIC_COS) d[j] = fmaf(dot * pj[jj], -inv_qn, 1.0f);
                         else d[j] = fmaf(dot, -1.0f, pj[jj]);
-                        if constexpr (TILE_MIN) {
-                            const bool lt = d[j] < best_d;
-                            best_d = lt ? d[j] : best_d;
-                            best_c = lt ? (uint32_t)(ch * 32 + j) : best_c;
-                        } else {
-                            mask |= (d[j] <= thr) ? (1u << j) : 0u;
-                        }
+                        dmin = fminf(dmin, d[j]);  // NaN (masked column) never wins
                     }
                 }
-                if constexpr (!TILE_MIN) {
-                    if (mask) {  // rare once the row's threshold has tightened
+                if constexpr (TILE_MIN) {
+                    if (dmin < best_d) {
+#pragma unroll
+                        for (int j = 31; j >= 0; --j)
+                            if (d[j] == dmin) best_c = (uint32_t)(ch * 32 + j);
+                        best_d = dmin;
+                    }
+                } else {
+                    if (dmin <= thr) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            if (mask & (1u << j)) {
+                            if (d[j] <= thr) {
                                 const uint32_t n = n0 + ch * 32 + j;
                                 bool ok = true;
                                 if (deny != nullptr && bit_test(deny, n)) ok = false;
@@ -572,12 +575,16 @@ uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count) {
     uint32_t max_by_rows = (n_rows + 2 * TC_N - 1) / (2 * TC_N);  // >= 2 tiles per split
     if (max_by_rows < 1) max_by_rows = 1;
     const uint32_t s_max = max_by_rows < 160 ? max_by_rows : 160;
+    static const double penalty = [] {
+        const char* e = getenv("VSB_TC_SPLIT_PENALTY");
+        return e ? atof(e) : 0.05;
+    }();
     uint32_t best = 1;
     double best_cost = 1e30;
     for (uint32_t s = 1; s <= s_max; ++s) {
         const uint32_t ctas = q_tiles * s;
         const uint32_t waves = (ctas + (uint32_t)sm_count - 1) / (uint32_t)sm_count;
-        const double cost = (double)waves / s * (1.0 + 0.015 * s);
+        const double cost = (double)waves / s * (1.0 + penalty * s);
         if (cost < best_cost - 1e-12) {
             best_cost = cost;
             best = s;
