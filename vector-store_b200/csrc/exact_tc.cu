@@ -179,31 +179,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Split form for software pipelining: the load of the next 32 columns is issued before the current ones are
-// processed.  tmem_ld32_wait names the destination registers as in/out operands so the compiler cannot move
-// a use of them above the wait.
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld32_wait(uint32_t* v) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
-                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
-                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]),
-                   "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),
-                   "+r"(v[30]), "+r"(v[31])
-                 :
-                 : "memory");
-}
-
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -416,7 +391,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_N;
-            auto process = [&](uint32_t (&v)[32], const int ch) {
+#pragma unroll 1
+            for (int ch = 0; ch < TC_N / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(taddr + ch * 32, v);
                 // fast path: distance of 32 columns and their minimum (FFMA + FMNMX per column); only when the
                 // minimum beats the row's threshold — rare once the list has warmed up — is anything else done
                 const float4* cp4 = reinterpret_cast<const float4*>(cp + ch * 32);
@@ -467,18 +445,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     const uint32_t need = __ballot_sync(kFullMask, cnt > TC_BUFCAP - 32);
                     if (need) flush(need);
                 }
-            };
-            uint32_t va[32], vb[32];
-            tmem_ld32_issue(taddr, va);
-            tmem_ld32_wait(va);
-#pragma unroll 1
-            for (int ch = 0; ch < TC_N / 32; ch += 2) {
-                tmem_ld32_issue(taddr + (ch + 1) * 32, vb);  // in flight while chunk ch is processed
-                process(va, ch);
-                tmem_ld32_wait(vb);
-                if (ch + 2 < TC_N / 32) tmem_ld32_issue(taddr + (ch + 2) * 32, va);
-                process(vb, ch + 1);
-                if (ch + 2 < TC_N / 32) tmem_ld32_wait(va);
             }
             if constexpr (TILE_MIN) {
                 if (q_valid && best_c != kInvalidSlot && t < a.kp) {
