@@ -401,6 +401,15 @@ def main():
     peak, peak_src = load_peaks()
     achieved = B * bytes_per_query / (k4_ms * 1e-3) / 1e9 if k4_ms > 0 else 0.0
     phase_ms = {p: st[p + "_ns"] / 1e6 / a.steps for p in ("convert", "seed", "graph_search", "exact", "merge")}
+    traffic = None  # DRAM bytes of one K4 launch from the committed ncu --set full capture, same configuration only
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "k4_traffic.json")))
+        if world == 1 and all(tr[k_] == v_ for k_, v_ in (("n", a.n), ("dim", a.dim), ("storage", a.storage),
+                                                           ("traversal", a.traversal), ("batch", B), ("k", k),
+                                                           ("expansion_search", ef_used), ("search_width", a.search_width))):
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
 
     # ---- timed region 2: end to end through the host-pointer C ABI ----
     def e2e_step(b):
@@ -458,7 +467,8 @@ def main():
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "graph_search_kernel (K4)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": B * bytes_per_query, "peak_source": peak_src,
                      "kernel_ms_per_launch": k4_ms, "distance_evals_per_query": E, "parent_expansions_per_query": P,
                      "bytes_per_query": bytes_per_query, "phase_ms_per_step": phase_ms},
         "build_vectors_per_s": build_vps, "build_s": {"add_h2d_convert": t_add, "graph": t_build, "generate": t_gen},
