@@ -34,7 +34,7 @@ if ROOT not in sys.path:
 
 METRIC_NAME = "ann_search_qps_at_recall10_ge_0.95"
 UNIT = "queries/s"
-EF_SWEEP = (32, 64, 96, 128, 160, 192, 224, 256, 320, 384, 512)  # both arms pick the smallest that reaches the target
+EF_SWEEP = (32, 64, 96, 128, 160, 192, 224, 256, 320, 384, 512, 768, 1024)  # both arms pick the smallest that reaches the target
 
 
 def parse_args():

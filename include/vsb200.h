@@ -74,7 +74,7 @@ typedef struct {
 
 /* Runtime tunables of the graph search (all 0 = keep current). */
 typedef struct {
-    uint32_t expansion_search; /* itopk; rounded up to a multiple of 32, <= 512 */
+    uint32_t expansion_search; /* itopk; rounded up to a multiple of 32, <= 1024 */
     uint32_t max_iterations;   /* beam-search iterations per query; 0 = keep, >= 1000000 = automatic */
     uint32_t n_seeds;          /* entry points taken from the seed layer, <= 32 */
     uint32_t min_graph_size;   /* below this many live vectors search is brute force */

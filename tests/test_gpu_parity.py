@@ -585,3 +585,41 @@ def test_build_compacts_tombstones():
     assert idx.size() == n - 4990 and idx.contains(int(keys[dead[0]]))
     gk2, _, _ = idx.search_batch(x[dead[:10]], 1)
     assert np.array_equal(gk2[:, 0], keys[dead[:10]])
+
+
+def test_c2_full_size_properties():
+    # BASELINE config #2 at full size: 1M x 768 f32 cosine — size-independent properties + recall vs exact
+    n, dim, k = 1_000_000, 768, 10
+    v = V()
+    idx = v.GpuIndex(dim, v.Metric.Cos, v.Scalar.F32, bf16_traversal=True)
+    idx.reserve(n)
+    first = None
+    for c0 in range(0, n, 100_000):
+        xc = embedding_like(100_000, dim, seed=1234 + c0 // 100_000)
+        if first is None:
+            first = xc[:256].copy()
+        idx.add_batch(np.arange(c0, c0 + len(xc), dtype=np.uint64), xc)
+    assert idx.size() == n
+    idx.build()
+    st = idx.stats()
+    assert st["n_graphed"] == n and st["hbm_bytes"] > n * (3072 + 1536)
+    q = embedding_like(2000, dim, seed=4321)
+    idx.set_search_params(expansion_search=160, search_width=2)
+    tk, td, tc = idx.search_batch(q, k, exact=True)
+    gk, gd, gc = idx.search_batch(q, k)
+    gk2, gd2, _ = idx.search_batch(q, k)
+    assert np.array_equal(gk, gk2) and np.array_equal(gd, gd2)          # deterministic
+    assert np.all(gc == k) and np.all(tc == k)
+    assert np.all(np.diff(gd, axis=1) >= 0) and np.all(np.diff(td, axis=1) >= 0)
+    assert np.all((gd >= 0) & (gd <= 2))                                # distance.rs:66-69
+    r = O.recall_at_k(gk, tk)
+    print(f"C2 1M x 768 recall@10 at ef=160: {r:.4f}")
+    assert r >= 0.94
+    # every hit's distance is the canonical fp32 distance of that stored row (checked on the oracle for 3 queries)
+    for i in range(3):
+        rows = np.stack([embedding_like(100_000, dim, seed=1234 + int(key) // 100_000)[int(key) % 100_000]
+                         for key in gk[i][:3]])
+        od = O.distance_matrix(rows, q[i:i + 1], O.COS, O.F32)[0]
+        assert np.array_equal(gd[i][:3].view(np.uint32), od.view(np.uint32))
+    sk, sd, _ = idx.search_batch(first, 1, exact=True)                  # a stored row is its own nearest neighbour
+    assert np.array_equal(sk[:, 0], np.arange(256, dtype=np.uint64)) and np.all(sd[:, 0] <= 1e-6)

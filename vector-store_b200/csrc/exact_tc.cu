@@ -318,7 +318,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // ===== epilogue: one thread per query row =====
         const int quarter = warp & 3;                // TMEM lane quarter this warp may read
         const int row = quarter * 32 + lane;         // row inside the CTA tile
-        const int etid = (warp - 2) * 32 + lane;     // 0..127 among epilogue threads
         const uint32_t q = q0 + row;
         const bool q_valid = q < a.nq;
         const LessByKey less{a.keys};

@@ -959,7 +959,7 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
         qv.n = nb;
         const vsb::RowsView x = corpus_view();
         const uint32_t* deny_bm = any_tombstone ? deny.as<uint32_t>() : nullptr;
-        const bool use_graph = !exact && d_allow == nullptr && n_graphed > 0 && k <= 512;
+        const bool use_graph = !exact && d_allow == nullptr && n_graphed > 0 && k <= 1024;
         const uint32_t tail_lo = use_graph ? n_graphed : 0, tail_hi = n_slots;
         const bool have_tail = tail_hi > tail_lo;
         uint64_t* g_keys = o_keys;
@@ -1063,7 +1063,7 @@ vsb_status vsb_create(const vsb_options* o, vsb_index** out) {
     ix->degree = std::min<uint32_t>(std::max<uint32_t>(2 * M, 8), 64);
     ix->graph_stride = round_up(ix->degree, 32);
     ix->k_init = std::min<uint32_t>(std::max<uint32_t>(ef_add / 2, ix->degree), 128);
-    ix->itopk = std::min<uint32_t>(round_up(ef_search, 32), 512);
+    ix->itopk = std::min<uint32_t>(round_up(ef_search, 32), 1024);
     ix->trav16 = (o->flags & VSB_FLAG_BF16_TRAVERSAL) != 0 && o->storage == VSB_F32;
     ix->row_bytes16 = storage_row_bytes(VSB_BF16, o->dimensions);
     if (const char* e = getenv("VSB_DISABLE_TC")) ix->tc_enabled = !(e[0] == '1');
@@ -1153,7 +1153,7 @@ vsb_status vsb_export_graph(vsb_index* ix, uint32_t* rows_out, uint64_t* keys_ou
 vsb_status vsb_set_search_params(vsb_index* ix, const vsb_search_params* p) {
     if (!ix || !p) return fail(VSB_EINVAL, "null argument");
     std::lock_guard<std::mutex> g(ix->mu);
-    if (p->expansion_search) ix->itopk = std::min<uint32_t>(round_up(p->expansion_search, 32), 512);
+    if (p->expansion_search) ix->itopk = std::min<uint32_t>(round_up(p->expansion_search, 32), 1024);
     if (p->max_iterations) ix->max_iters = p->max_iterations >= 1000000u ? 0 : p->max_iterations;  // >= 1e6: back to auto
     if (p->n_seeds) ix->n_seeds = std::min<uint32_t>(p->n_seeds, 32);
     if (p->min_graph_size) ix->min_graph_size = p->min_graph_size;
