@@ -51,3 +51,30 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(d, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src.replace(
                     "oracle/exact.c", "").replace("oracle/graph_oracle.py", ""), f"{f} references oracle/"
+
+
+def _build_c_client(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "abi_client")
+    libdir = os.path.join(ROOT, "vector-store_b200")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi_client.c"), "-o", exe, "-L", libdir, "-lvsb200", "-lm",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    return exe
+
+
+def test_header_compiles_as_c_and_links(tmp_path):
+    """include/vsb200.h is valid C99 and a pure-C program links against libvsb200.so."""
+    import subprocess
+    exe = _build_c_client(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "scenario passed" in r.stdout
+    else:
+        assert r.returncode == 77, (r.returncode, r.stdout, r.stderr)  # loud failure, no CPU fallback

@@ -623,3 +623,11 @@ def test_c2_full_size_properties():
         assert np.array_equal(gd[i][:3].view(np.uint32), od.view(np.uint32))
     sk, sd, _ = idx.search_batch(first, 1, exact=True)                  # a stored row is its own nearest neighbour
     assert np.array_equal(sk[:, 0], np.arange(256, dtype=np.uint64)) and np.all(sd[:, 0] <= 1e-6)
+
+
+def test_c_abi_client_replays_reference_scenario(tmp_path):
+    # a plain C program (tests/abi_client.c) drives G1 through the C ABI — no Python in the data path
+    import subprocess
+    from test_abi import _build_c_client
+    r = subprocess.run([_build_c_client(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0 and "scenario passed" in r.stdout, r.stdout + r.stderr
