@@ -127,7 +127,8 @@ class ClockSampler:
         if not inside and rows:  # region shorter than the sampling period: take the samples closest to it
             mid = 0.5 * ((self.t0 or 0) + (self.t1 or 0))
             inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
-            note = "timed region shorter than the 20 ms sampling period: nearest samples used"
+            note = (f"no nvidia-smi sample fell inside the {(self.t1 - self.t0) * 1e3:.0f} ms timed region: "
+                    "nearest samples used")
         reasons = set()
         for r in inside:
             for nm, val in zip(names, r[4]):
@@ -275,6 +276,11 @@ def main():
     idx.build()
     barrier()
     t_build = time.perf_counter() - t0
+    # clock sampler: started long before the timed region (nvidia-smi needs a second or two to come up on an
+    # 8-GPU box) and only on rank 0, whose line is the one reported
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     build_vps = a.n / (t_add + t_build)  # first H2D to graph ready, whole job
 
     # ---- query pool: NB distinct batches, pinned on the host and resident on the device ----
@@ -367,8 +373,6 @@ def main():
     bytes_per_query = E * (trav_row_bytes + 4) + P * st["graph_degree"] * 4  # +4: the row's norm (cosine)
 
     # ---- timed region 1: inputs resident in HBM ----
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     for i in range(a.warmup):
         search_step(q_dev[i % NB])
     barrier()
