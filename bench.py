@@ -302,8 +302,13 @@ def main():
     assert world == 1 or B % world == 0, "query batch must divide evenly over the ranks"
     q_slice = torch.empty((B // world, a.dim), dtype=torch.float32, device=dev)
     q_e2e = torch.empty((B, a.dim), dtype=torch.float32, device=dev)
-    gath_k = torch.empty((world, B, k), dtype=torch.int64, device=dev)
-    gath_d = torch.empty((world, B, k), dtype=torch.float32, device=dev)
+    # per-rank record for the exchange: [B*k keys (8 B) | B*k distances (4 B)] -> ONE all-gather per step
+    assert (B * k) % 2 == 0, "B*k must be even so that every rank's record stays 8-byte aligned"
+    rec_bytes = B * k * 12
+    rec_local = torch.empty(rec_bytes, dtype=torch.uint8, device=dev)
+    rec_all = torch.empty(world * rec_bytes, dtype=torch.uint8, device=dev)
+    keys_l = rec_local[:B * k * 8].view(torch.int64).view(B, k)
+    dists_l = rec_local[B * k * 8:].view(torch.float32).view(B, k)
 
     def search_step(qd, exact=False):
         """device-resident step: local shard search [+ all-gather + K8 merge]; result in out_k/out_d"""
@@ -311,10 +316,9 @@ def main():
             idx.search_dev(qd.data_ptr(), B, k, out_k.data_ptr(), out_d.data_ptr(), 0, stream, exact)
             return
         idx.search_dev(qd.data_ptr(), B, k, keys_l.data_ptr(), dists_l.data_ptr(), 0, stream, exact)
-        dist.all_gather_into_tensor(gath_k.view(world * B, k), keys_l)
-        dist.all_gather_into_tensor(gath_d.view(world * B, k), dists_l)
-        index_mod.merge_topk_dev(gath_k.data_ptr(), gath_d.data_ptr(), world, B, k, out_k.data_ptr(), out_d.data_ptr(),
-                                 0, local_rank, stream)
+        dist.all_gather_into_tensor(rec_all, rec_local)
+        index_mod.merge_topk_strided_dev(rec_all.data_ptr(), rec_all.data_ptr() + B * k * 8, world, rec_bytes // 8,
+                                         rec_bytes // 4, B, k, out_k.data_ptr(), out_d.data_ptr(), 0, local_rank, stream)
 
     # ---- exact ground truth (GPU brute force, bit-exact vs the oracle by tests/test_gpu_parity.py) ----
     gt = []

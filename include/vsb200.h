@@ -191,6 +191,14 @@ vsb_status vsb_batcher_stats(vsb_batcher* batcher, uint64_t* n_queries, uint64_t
 vsb_status vsb_save(vsb_index* index, const char* path);
 vsb_status vsb_load(const char* path, int32_t device, vsb_index** out);
 
+/* Same merge for parts that are NOT stored back to back: part p's keys start at d_keys + p*key_part_stride
+ * (u64 elements), its distances at d_distances + p*dist_part_stride (f32 elements).  Lets one all-gather of a
+ * per-rank record [q*k keys | q*k distances] feed the merge directly. */
+vsb_status vsb_merge_topk_strided_dev(const uint64_t* d_keys, const float* d_distances, uint32_t parts,
+                                      uint64_t key_part_stride, uint64_t dist_part_stride, uint64_t q, uint32_t k,
+                                      uint64_t* d_out_keys, float* d_out_distances, uint32_t* d_out_counts,
+                                      int device, void* stream);
+
 /* A11: usearch.rs:1179-1205  f32_to_b1x8 (host utility, same bit order) */
 void vsb_f32_to_b1x8(const float* v, uint64_t n, uint8_t* out /* ceil(n/8) bytes */);
 

@@ -150,6 +150,19 @@ def test_merge_topk_kernel_matches_numpy():
         o = np.lexsort((ak, ad))[:k]
         assert np.array_equal(gk[i], ak[o]) and np.array_equal(gd[i], ad[o])
     assert np.all(oc.cpu().numpy() == k)
+    # strided form: one record per part [q*k keys | q*k distances], as a single all-gather delivers it
+    rec = torch.empty(parts * nq * k * 12, dtype=torch.uint8, device="cuda")
+    for p in range(parts):
+        base = p * nq * k * 12
+        rec[base:base + nq * k * 8].view(torch.int64).copy_(tk[p].reshape(-1))
+        rec[base + nq * k * 8:base + nq * k * 12].view(torch.float32).copy_(td[p].reshape(-1))
+    ok2 = torch.empty_like(ok)
+    od2 = torch.empty_like(od)
+    index_mod.merge_topk_strided_dev(rec.data_ptr(), rec.data_ptr() + nq * k * 8, parts, nq * k * 12 // 8,
+                                     nq * k * 12 // 4, nq, k, ok2.data_ptr(), od2.data_ptr(), 0, 0,
+                                     torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(ok2, ok) and torch.equal(od2, od)
 
 
 # ---- reference golden vectors through the actor mirror (reads like the reference's own tests) ----------

@@ -1253,6 +1253,19 @@ vsb_status vsb_merge_topk_dev(const uint64_t* d_keys, const float* d_distances, 
     return VSB_OK;
 }
 
+vsb_status vsb_merge_topk_strided_dev(const uint64_t* d_keys, const float* d_distances, uint32_t parts,
+                                      uint64_t key_part_stride, uint64_t dist_part_stride, uint64_t q, uint32_t k,
+                                      uint64_t* d_out_keys, float* d_out_distances, uint32_t* d_out_counts, int device,
+                                      void* stream) {
+    if (!d_keys || !d_distances || !d_out_keys || !d_out_distances) return fail(VSB_EINVAL, "null buffer");
+    if (parts == 0 || k == 0 || (uint64_t)parts * k > 2048) return fail(VSB_EINVAL, "parts*k must be in [1, 2048]");
+    if (device >= 0) CU(cudaSetDevice(device));
+    vsb::launch_merge_topk(d_keys, d_distances, parts, q, k, d_out_keys, d_out_distances, d_out_counts,
+                           static_cast<cudaStream_t>(stream), key_part_stride, dist_part_stride);
+    CU(cudaGetLastError());
+    return VSB_OK;
+}
+
 void vsb_f32_to_b1x8(const float* v, uint64_t n, uint8_t* out) {
     const uint64_t nb = (n + 7) / 8;
     for (uint64_t j = 0; j < nb; ++j) {

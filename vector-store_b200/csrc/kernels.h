@@ -105,8 +105,10 @@ void launch_seed_scan(int storage, int metric, const RowsView& q, const RowsView
                       cudaStream_t stream);
 
 // K8 (merge.cu) ----------------------------------------------------------------------------------
+// key_part_stride / dist_part_stride: elements between consecutive parts (0 = q*k, parts back to back)
 void launch_merge_topk(const uint64_t* keys, const float* dists, uint32_t parts, uint64_t q, uint32_t k,
-                       uint64_t* out_keys, float* out_dists, uint32_t* out_counts, cudaStream_t stream);
+                       uint64_t* out_keys, float* out_dists, uint32_t* out_counts, cudaStream_t stream,
+                       uint64_t key_part_stride = 0, uint64_t dist_part_stride = 0);
 // fills [n] key/dist arrays with the padding values
 void launch_fill_empty(uint64_t* keys, float* dists, uint32_t* counts, uint64_t q, uint32_t k, cudaStream_t stream);
 

@@ -18,6 +18,7 @@ __device__ __forceinline__ bool dk_less(uint32_t da, uint64_t ka, uint32_t db, u
 
 __global__ void __launch_bounds__(K8_THREADS) merge_topk_kernel(const uint64_t* __restrict__ keys,
                                                                 const float* __restrict__ dists, uint32_t parts,
+                                                                uint64_t key_part_stride, uint64_t dist_part_stride,
                                                                 uint64_t nq, uint32_t k, uint32_t n_pow2,
                                                                 uint64_t* __restrict__ out_keys,
                                                                 float* __restrict__ out_dists,
@@ -32,9 +33,9 @@ __global__ void __launch_bounds__(K8_THREADS) merge_topk_kernel(const uint64_t* 
         uint32_t d = 0xFFFFFFFFu;
         if (i < total) {
             const uint32_t p = i / k, j = i % k;
-            const size_t src = ((size_t)p * nq + q) * k + j;
-            key = keys[src];
-            d = key == 0xFFFFFFFFFFFFFFFFull ? 0xFFFFFFFFu : f32_to_ord(dists[src]);
+            const size_t in_part = (size_t)q * k + j;
+            key = keys[(size_t)p * key_part_stride + in_part];
+            d = key == 0xFFFFFFFFFFFFFFFFull ? 0xFFFFFFFFu : f32_to_ord(dists[(size_t)p * dist_part_stride + in_part]);
         }
         sk[i] = key;
         sd[i] = d;
@@ -87,14 +88,17 @@ __global__ void fill_empty_kernel(uint64_t* keys, float* dists, uint32_t* counts
 }  // namespace
 
 void launch_merge_topk(const uint64_t* keys, const float* dists, uint32_t parts, uint64_t q, uint32_t k,
-                       uint64_t* out_keys, float* out_dists, uint32_t* out_counts, cudaStream_t stream) {
+                       uint64_t* out_keys, float* out_dists, uint32_t* out_counts, cudaStream_t stream,
+                       uint64_t key_part_stride, uint64_t dist_part_stride) {
+    if (key_part_stride == 0) key_part_stride = q * k;    // parts stored back to back
+    if (dist_part_stride == 0) dist_part_stride = q * k;
     if (q == 0 || k == 0) return;
     uint32_t n_pow2 = 2;
     while (n_pow2 < parts * k) n_pow2 <<= 1;
     const size_t smem = (size_t)n_pow2 * 12;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    merge_topk_kernel<<<(unsigned)q, K8_THREADS, smem, stream>>>(keys, dists, parts, q, k, n_pow2, out_keys,
+    merge_topk_kernel<<<(unsigned)q, K8_THREADS, smem, stream>>>(keys, dists, parts, key_part_stride, dist_part_stride, q, k, n_pow2, out_keys,
                                                                   out_dists, out_counts);
     g_kernel_launches += 1;
 }

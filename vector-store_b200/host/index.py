@@ -245,3 +245,10 @@ class Batcher:
             self.close()
         except Exception:
             pass
+
+
+def merge_topk_strided_dev(d_keys: int, d_dists: int, parts: int, key_part_stride: int, dist_part_stride: int, q: int,
+                           k: int, d_out_keys: int, d_out_dists: int, d_out_counts: int, device: int,
+                           stream: int) -> None:
+    check(lib().vsb_merge_topk_strided_dev(d_keys, d_dists, parts, key_part_stride, dist_part_stride, q, k, d_out_keys,
+                                           d_out_dists, d_out_counts or None, device, stream or None))

@@ -65,6 +65,8 @@ SYMBOLS = [
     ("vsb_batcher_stats", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("vsb_save", C.c_int, [_P, C.c_char_p]),
     ("vsb_load", C.c_int, [C.c_char_p, C.c_int32, C.POINTER(_P)]),
+    ("vsb_merge_topk_strided_dev", C.c_int, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _P, _P,
+                                             _P, C.c_int, _P]),
     ("vsb_f32_to_b1x8", None, [_P, C.c_uint64, _P]),
     ("vsb_last_error", C.c_char_p, []),
     ("vsb_version", C.c_char_p, []),
