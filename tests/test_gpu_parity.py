@@ -644,3 +644,71 @@ def test_c_abi_client_replays_reference_scenario(tmp_path):
     from test_abi import _build_c_client
     r = subprocess.run([_build_c_client(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0 and "scenario passed" in r.stdout, r.stdout + r.stderr
+
+
+# ---- edge cases the reference's tests touch: empty / tiny / oversized inputs, growth, everything deleted ---------
+def test_edge_cases_tiny_and_degenerate_inputs():
+    v = V()
+    # dim 1, k larger than the index, duplicate vectors (ties by key)
+    idx = v.GpuIndex(1, v.Metric.L2sq, v.Scalar.F32)
+    idx.reserve(8)
+    idx.add_batch(np.array([30, 10, 20], np.uint64), np.array([[1.0], [1.0], [1.0]], np.float32))
+    keys, dists, counts = idx.search_batch(np.array([[1.0]], np.float32), 5)
+    assert list(keys[0][:3]) == [10, 20, 30] and counts[0] == 3 and np.all(dists[0][:3] == 0)
+    assert keys[0][3] == np.uint64(0xFFFFFFFFFFFFFFFF) and np.isinf(dists[0][3])
+    # zero queries is a no-op; zero vectors in cosine space follow the 0 / 1 convention
+    k0, d0, c0 = idx.search_batch(np.zeros((0, 1), np.float32), 3)
+    assert k0.shape == (0, 3)
+    cidx = v.GpuIndex(4, v.Metric.Cos, v.Scalar.F32)
+    cidx.reserve(4)
+    cidx.add_batch(np.array([1, 2], np.uint64), np.array([[0, 0, 0, 0], [1, 0, 0, 0]], np.float32))
+    ck, cd, _ = cidx.search_batch(np.array([[0, 0, 0, 0], [2, 0, 0, 0]], np.float32), 2)
+    assert list(ck[0]) == [1, 2] and list(cd[0]) == [0.0, 1.0]      # both-zero -> 0, one-zero -> 1
+    assert list(ck[1]) == [2, 1] and list(cd[1]) == [0.0, 1.0]
+    # capacity errors and growth keep the contents
+    with pytest.raises(v.VsbError) as e:
+        idx.add_batch(np.arange(100, 110, dtype=np.uint64), np.zeros((10, 1), np.float32))
+    assert e.value.status == 4  # VSB_EFULL
+    idx.reserve(64)
+    idx.add_batch(np.arange(100, 110, dtype=np.uint64), np.arange(10, dtype=np.float32)[:, None])
+    assert idx.size() == 13 and idx.search(np.array([9.0], np.float32), 1)[0][0] == 109
+    with pytest.raises(v.VsbError) as e:
+        idx.search_batch(np.zeros((1, 2), np.float32), 1)
+    assert e.value.status == 2  # VSB_EDIM
+    with pytest.raises(v.VsbError):
+        v.GpuIndex(8, v.Metric.Hamming, v.Scalar.F32)                # "Binary space type requires B1 quantization."
+    assert v.GpuIndex(8, v.Metric.Cos, v.Scalar.B1).metric == v.Metric.Hamming   # usearch.rs:450-464
+
+
+def test_everything_deleted_then_refilled():
+    n, dim = 9000, 32
+    x = embedding_like(n, dim, n_clusters=8)
+    keys = np.arange(n, dtype=np.uint64)
+    idx = make_index(x, keys, O.COS, O.F32)
+    idx.build()
+    idx.remove_batch(keys)
+    assert idx.size() == 0
+    k, d, c = idx.search_batch(x[:5], 3)
+    assert np.all(c == 0) and np.all(k == np.uint64(0xFFFFFFFFFFFFFFFF))
+    idx.build()                                                       # compacts to an empty index
+    assert idx.stats()["n_slots"] == 0
+    idx.add_batch(keys[:100] | np.uint64(1 << 48), x[:100])          # new epoch of the same rows
+    k, d, c = idx.search_batch(x[:5], 1)
+    assert np.array_equal(k[:, 0], keys[:5] | np.uint64(1 << 48)) and np.all(c == 1)
+
+
+def test_wide_rows_fall_back_to_exact_search_and_large_k():
+    # rows wider than K4 supports (> 6144 bytes) are served by the exact path; k up to 200 works there
+    rng = np.random.default_rng(1)
+    n, dim = 6000, 2000
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    keys = np.arange(n, dtype=np.uint64)
+    idx = make_index(x, keys, O.IP, O.F32)
+    idx.build()
+    assert idx.stats()["n_graphed"] == 0
+    q = rng.standard_normal((3, dim)).astype(np.float32)
+    gk, gd, gc = idx.search_batch(q, 200)
+    ok, od, oc, _ = O.exact_topk(x, q, 200, O.IP, O.F32, keys=keys)
+    assert_bit_equal(gk, gd, gc, ok, od, oc)
+    for d in gd.ravel():
+        V().Distance.try_from(float(d), V().SpaceType.DotProduct, dim)   # negative IP distances are valid
