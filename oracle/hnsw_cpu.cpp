@@ -113,8 +113,18 @@ struct Hnsw {
             uint32_t cnt = nb[0];
             std::memcpy(buf, nb + 1, cnt * 4);
             locks[c.second].unlock();
+            // software prefetch of the neighbours' vectors, as hnswlib / usearch do: the loop is DRAM-latency bound
+            for (uint32_t i = 0; i < cnt; ++i) {
+                const char* p = reinterpret_cast<const char*>(&data[(size_t)buf[i] * dim]);
+                __builtin_prefetch(p);
+                __builtin_prefetch(p + 64);
+            }
             for (uint32_t i = 0; i < cnt; ++i) {
                 uint32_t v = buf[i];
+                if (i + 1 < cnt) {
+                    const char* p = reinterpret_cast<const char*>(&data[(size_t)buf[i + 1] * dim]);
+                    for (int off = 128; off < dim * 4; off += 64) __builtin_prefetch(p + off);
+                }
                 if (vis[v] == epoch) continue;
                 vis[v] = epoch;
                 float d = dist(q, q_inv, v);
