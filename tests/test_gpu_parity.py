@@ -712,3 +712,18 @@ def test_wide_rows_fall_back_to_exact_search_and_large_k():
     assert_bit_equal(gk, gd, gc, ok, od, oc)
     for d in gd.ravel():
         V().Distance.try_from(float(d), V().SpaceType.DotProduct, dim)   # negative IP distances are valid
+
+
+def test_golden_fixture_file_through_the_c_abi():
+    # tests/golden/index_path_goldens.json: the same cases the oracle is pinned on, through libvsb200
+    from golden_cases import METRIC, STORAGE, check_case, load_cases
+    v = V()
+    for cid, c, keys, rows, q in load_cases():
+        m, s = METRIC[c["metric"]], STORAGE[c["storage"]]
+        idx = v.GpuIndex(rows.shape[1], v.Metric(m), v.Scalar(s))
+        idx.reserve(len(keys))
+        idx.add_batch(keys, rows)
+        for exact in (False, True):
+            kk, dd, cc = idx.search_batch(q[None, :], c["k"], exact=exact)
+            check_case(c, kk[0][:cc[0]], dd[0][:cc[0]], O.HAMMING if s == O.B1 else m)
+        idx.close()

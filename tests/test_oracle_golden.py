@@ -201,3 +201,13 @@ def test_n4_fbin_ibin_roundtrip(tmp_path):
     assert np.array_equal(ds.read_ibin(str(tmp_path / "g.ibin")), gt)
     raw = open(tmp_path / "d.fbin", "rb").read()
     assert raw[:8] == np.array([37, 12], "<u4").tobytes() and len(raw) == 8 + 37 * 12 * 4
+
+
+def test_golden_fixture_file_against_the_oracle():
+    from golden_cases import METRIC, STORAGE, check_case, load_cases
+    cases = load_cases()
+    assert len(cases) >= 15
+    for cid, c, keys, rows, q in cases:
+        m, s = METRIC[c["metric"]], STORAGE[c["storage"]]
+        kk, dd, cc, _ = O.exact_topk(rows, q[None, :], c["k"], m, s, keys=keys)
+        check_case(c, kk[0][:cc[0]], dd[0][:cc[0]], O.HAMMING if s == O.B1 else m)
