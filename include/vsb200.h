@@ -100,6 +100,10 @@ typedef struct {
     uint64_t convert_ns, seed_ns, graph_search_ns, exact_ns, merge_ns;
     uint64_t convert_launches, seed_launches, graph_search_launches, exact_launches, merge_launches;
     uint64_t tc_launches;          /* distance-tile launches that ran on tcgen05 (exact_tc.cu), process-wide */
+    /* exact search on float rows: queries whose tiled candidate stage (TF32 / 16-bit tensor-core tiles, fp32
+     * SIMT tiles) was PROVEN to contain the canonical top-k; queries the first stage could not certify; and
+     * queries that went all the way to the canonical full scan (near-ties below fp32 summation noise) */
+    uint64_t exact_certified, exact_fallback, exact_scanned;
 } vsb_stats;
 
 /* usearch.rs:172  usearch::Index::new(&options) */
@@ -163,7 +167,8 @@ vsb_status vsb_search_filtered(vsb_index* index, const float* queries, uint64_t 
                                uint64_t* keys, float* distances, uint32_t* counts);
 
 /* Device-resident variants: d_* are device pointers on the index's device,
- * `stream` is a cudaStream_t.  No host synchronisation. `exact` != 0 selects brute force. */
+ * `stream` is a cudaStream_t.  No host synchronisation, except `exact` != 0 (brute force) on float rows,
+ * which reads the certification count back (see vsb_stats.exact_certified). */
 vsb_status vsb_search_dev(vsb_index* index, const float* d_queries, uint64_t q, uint32_t k,
                           uint64_t* d_keys, float* d_distances, uint32_t* d_counts,
                           void* stream, int exact);

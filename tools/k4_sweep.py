@@ -51,7 +51,8 @@ def main():
     torch.cuda.synchronize()
     gt = ok.cpu().numpy().copy()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tc0 = idx.stats()["tc_launches"]
+    st0 = idx.stats()
+    tc0 = st0["tc_launches"]
     e0.record()
     for _ in range(3):
         idx.search_dev(q.data_ptr(), B, k, ok.data_ptr(), od.data_ptr(), 0, stream, True)
@@ -59,7 +60,9 @@ def main():
     torch.cuda.synchronize()
     ems = e0.elapsed_time(e1) / 3
     print(json.dumps({"exact_search_ms": round(ems, 2), "tflops": round(2.0 * B * a.n * a.dim / ems / 1e9, 1),
-                      "tensor_core_path": idx.stats()["tc_launches"] > tc0, "same_as_first": bool((ok.cpu().numpy() == gt).all())}),
+                      "tensor_core_path": idx.stats()["tc_launches"] > tc0,
+                      "certified": (idx.stats()["exact_certified"] - st0["exact_certified"]) // 3,
+                      "fallback": (idx.stats()["exact_fallback"] - st0["exact_fallback"]) // 3, "same_as_first": bool((ok.cpu().numpy() == gt).all())}),
           flush=True)
     peak = 6541.1
     if a.exact_only:

@@ -10,6 +10,8 @@
 //
 // Replaces: usearch::Index::search as called at vs_index/usearch.rs:203-222 when the caller
 // wants exact results (ground truth, the un-graphed tail, filtered search, kNN-graph build).
+#include <algorithm>
+
 #include "kernels.h"
 #include "select.cuh"
 
@@ -287,6 +289,12 @@ struct K3Args {
     uint32_t* out_counts;
     uint64_t* out_packed;
     int64_t self_base;
+    // certification of a reduced-precision candidate stage (see ExactCert in kernels.h); all nullable
+    const float* x_nrm_max;
+    float cert_rel, cert_sum;
+    uint32_t* uncert_flags;
+    uint32_t* uncert_count;
+    const uint32_t* q_map;  // query q of this launch is query q_map[q] of the caller (outputs, self slot)
 };
 
 constexpr int K3_WARPS = 4;
@@ -313,12 +321,16 @@ __global__ void __launch_bounds__(K3_WARPS * 32) exact_rerank_kernel(K3Args a) {
             warp_list_merge(cand, (int)a.kp, v, lane, less);
         }
     }
+    __syncwarp();
+    // every row that is NOT a candidate has a candidate-stage distance >= the worst kept one
+    const uint64_t cand_floor = cand[a.kp - 1];
+    const uint32_t oq = a.q_map != nullptr ? a.q_map[q] : q;
 
     // 2. canonical re-evaluation, 32 candidates at a time
     const uint4* qrow = reinterpret_cast<const uint4*>(a.q_rows + (size_t)q * a.q_row_bytes);
     const int n_chunks = a.x_row_bytes / 16;
     const float qn = a.q_nrm[q];
-    const uint32_t self_slot = a.self_base >= 0 ? (uint32_t)(a.self_base + q) : kInvalidSlot;
+    const uint32_t self_slot = a.self_base >= 0 ? (uint32_t)(a.self_base + oq) : kInvalidSlot;
     for (uint32_t b = 0; b < a.kp; b += 32) {
         const uint64_t mine = cand[b + lane];
         uint64_t res = kInvalidPacked;
@@ -377,15 +389,165 @@ __global__ void __launch_bounds__(K3_WARPS * 32) exact_rerank_kernel(K3Args a) {
         const uint64_t p = fin[i];
         const bool valid = p != kInvalidPacked && i < a.k;
         if (i < a.k) {
-            if (a.out_packed != nullptr) a.out_packed[(size_t)q * a.k + i] = valid ? p : kInvalidPacked;
+            if (a.out_packed != nullptr) a.out_packed[(size_t)oq * a.k + i] = valid ? p : kInvalidPacked;
             if (a.out_keys != nullptr) {
-                a.out_keys[(size_t)q * a.k + i] = valid ? a.keys[packed_lo(p)] : 0xFFFFFFFFFFFFFFFFull;
-                a.out_dists[(size_t)q * a.k + i] = valid ? ord_to_f32(packed_hi(p)) : __int_as_float(0x7F800000);
+                a.out_keys[(size_t)oq * a.k + i] = valid ? a.keys[packed_lo(p)] : 0xFFFFFFFFFFFFFFFFull;
+                a.out_dists[(size_t)oq * a.k + i] = valid ? ord_to_f32(packed_hi(p)) : __int_as_float(0x7F800000);
             }
         }
         count += __popc(__ballot_sync(kFullMask, valid));
     }
-    if (lane == 0 && a.out_counts != nullptr) a.out_counts[q] = count;
+    if (lane == 0 && a.out_counts != nullptr) a.out_counts[oq] = count;
+
+    // 4. certificate: the candidate stage ran at reduced precision (TF32).  A non-candidate row x has
+    //    candidate-stage distance >= cand_floor, hence canonical distance >= cand_floor - eps(q).  If the k-th
+    //    canonical distance found is strictly below that bound, no such row can enter (or tie into) the top-k and
+    //    the result equals the full-precision brute force.  Otherwise the query is flagged for the SIMT path.
+    if (a.uncert_flags != nullptr && lane == 0) {
+        bool ok = true;
+        if (cand_floor != kInvalidPacked) {  // list full: rows were dropped
+            const uint64_t pk = fin[a.k - 1];
+            if (pk == kInvalidPacked) {
+                ok = false;
+            } else {
+                const float floor_d = ord_to_f32(packed_hi(cand_floor)), dk = ord_to_f32(packed_hi(pk));
+                const float xm = *a.x_nrm_max;
+                // |candidate-stage distance - canonical distance| <= eps for every row of the block:
+                //   cert_rel bounds the dot-product error relative to |q||x|, cert_sum the rounding of an
+                //   fp32 sum of `dim` terms (the norms of the L2 expansion, the canonical sum itself)
+                float eps;
+                if constexpr (METRIC == VSB_METRIC_COS)
+                    eps = a.cert_rel + 1e-6f;
+                else if constexpr (METRIC == VSB_METRIC_L2SQ)
+                    eps = (a.cert_rel + a.cert_sum) * (qn * qn + xm * xm);
+                else
+                    eps = a.cert_rel * qn * xm + 0x1p-22f * (1.0f + qn * xm);
+                ok = dk + eps < floor_d;  // false for NaN
+            }
+        }
+        a.uncert_flags[q] = ok ? 0u : 1u;
+        if (!ok) atomicAdd(a.uncert_count, 1u);
+    }
+}
+
+// K1c — canonical scan: every admissible row of [x_lo, x_hi) is evaluated in the canonical order against a
+// block of SCAN_QB queries; each warp keeps one (distance, key)-ordered list of kf entries per query.  No
+// candidate stage, hence nothing to certify: this is the last resort for queries whose certificate failed
+// (near-ties below the resolution of the tiled stages), bandwidth-amortised over SCAN_QB queries per row read.
+constexpr int SCAN_WARPS = 4, SCAN_QB = 8;
+struct ScanArgs {
+    const uint8_t* q_rows;
+    const float* q_nrm;
+    uint32_t nq, q_row_bytes;
+    const uint8_t* x_rows;
+    const float* x_nrm;
+    uint32_t x_row_bytes, x_lo, x_hi;
+    const uint32_t* deny;
+    const uint64_t* keys;
+    const uint32_t* allow;
+    uint64_t allow_bits;
+    uint32_t kf, n_splits, rows_per_split;
+    uint64_t* part;  // [nq][n_splits * SCAN_WARPS][kf]
+};
+
+template <int ST, int METRIC>
+__global__ void __launch_bounds__(SCAN_WARPS * 32) exact_scan_kernel(ScanArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q0 = blockIdx.x * SCAN_QB, split = blockIdx.y;
+    const int nv = (int)min((uint32_t)SCAN_QB, a.nq - q0);
+    uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warp * SCAN_QB * a.kf;  // [SCAN_QB][kf]
+    for (uint32_t i = lane; i < SCAN_QB * a.kf; i += 32) lists[i] = kInvalidPacked;
+    __syncwarp();
+    const LessByKey less{a.keys};
+    const int n_chunks = a.x_row_bytes / 16;
+    const uint32_t lo = a.x_lo + split * a.rows_per_split;
+    const uint32_t hi = min(lo + a.rows_per_split, a.x_hi);
+    float qn[SCAN_QB];
+#pragma unroll
+    for (int j = 0; j < SCAN_QB; ++j) qn[j] = j < nv ? a.q_nrm[q0 + j] : 0.0f;
+
+    for (uint32_t r0 = lo + warp * 32; r0 < hi; r0 += 32 * SCAN_WARPS) {
+        const uint32_t row = r0 + lane;
+        bool ok = row < hi;
+        if (ok && a.deny != nullptr && bit_test(a.deny, row)) ok = false;
+        if (ok && a.allow != nullptr) {
+            const uint64_t rid = a.keys[row] & kRowMask48;
+            ok = rid < a.allow_bits && bit_test(a.allow, (uint32_t)rid);
+        }
+        uint32_t mask = __ballot_sync(kFullMask, ok);
+        uint64_t res[SCAN_QB];
+#pragma unroll
+        for (int j = 0; j < SCAN_QB; ++j) res[j] = kInvalidPacked;
+        while (mask) {  // two rows in flight
+            const int c0 = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int c1 = mask ? __ffs(mask) - 1 : -1;
+            if (c1 >= 0) mask &= mask - 1;
+            const uint32_t s0 = r0 + c0, s1 = c1 >= 0 ? r0 + c1 : s0;
+            const uint4* x0 = reinterpret_cast<const uint4*>(a.x_rows + (size_t)s0 * a.x_row_bytes);
+            const uint4* x1 = reinterpret_cast<const uint4*>(a.x_rows + (size_t)s1 * a.x_row_bytes);
+            ChunkAcc<ST, METRIC> acc0[SCAN_QB], acc1[SCAN_QB];
+            for (int ch = lane; ch < n_chunks; ch += 32) {
+                const uint4 xv0 = ldg_nc_v4(x0 + ch), xv1 = ldg_nc_v4(x1 + ch);
+#pragma unroll
+                for (int j = 0; j < SCAN_QB; ++j) {
+                    if (j < nv) {
+                        const uint4 qv = __ldg(reinterpret_cast<const uint4*>(a.q_rows + (size_t)(q0 + j) * a.q_row_bytes) + ch);
+                        acc0[j].add(qv, xv0);
+                        acc1[j].add(qv, xv1);
+                    }
+                }
+            }
+            const float xn0 = a.x_nrm[s0], xn1 = a.x_nrm[s1];
+#pragma unroll
+            for (int j = 0; j < SCAN_QB; ++j) {
+                if (j < nv) {
+                    float f0 = 0.0f, f1 = 0.0f;
+                    int i0 = 0, i1 = 0;
+                    if constexpr (Storage<ST>::kFloat) {
+                        f0 = butterfly_sum(acc0[j].f);
+                        f1 = butterfly_sum(acc1[j].f);
+                    } else {
+                        i0 = butterfly_sum_i(acc0[j].i);
+                        i1 = butterfly_sum_i(acc1[j].i);
+                    }
+                    const float d0 = finish_distance<ST, METRIC>(f0, i0, qn[j], xn0);
+                    const float d1 = finish_distance<ST, METRIC>(f1, i1, qn[j], xn1);
+                    if (lane == c0) res[j] = pack_ds(d0, s0);
+                    if (lane == c1) res[j] = pack_ds(d1, s1);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < SCAN_QB; ++j) {
+            if (j < nv) {
+                uint64_t* list = lists + (size_t)j * a.kf;
+                const uint64_t tail = list[a.kf - 1];
+                if (__ballot_sync(kFullMask, res[j] != kInvalidPacked && less(res[j], tail)) == 0) continue;
+                const uint64_t sorted = warp_sort32(res[j], lane, less);
+                warp_list_merge(list, (int)a.kf, sorted, lane, less);
+            }
+        }
+    }
+    __syncwarp();
+    for (int j = 0; j < nv; ++j)
+        for (uint32_t i = lane; i < a.kf; i += 32)
+            a.part[(((size_t)(q0 + j) * a.n_splits + split) * SCAN_WARPS + warp) * a.kf + i] = lists[(size_t)j * a.kf + i];
+}
+
+template <int ST, int METRIC>
+void launch_scan(const ScanArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
+    cudaFuncSetAttribute(exact_scan_kernel<ST, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    exact_scan_kernel<ST, METRIC><<<grid, SCAN_WARPS * 32, smem, stream>>>(a);
+}
+
+// max over a block of row norms (non-negative floats order like their bit patterns); *out must be zeroed
+__global__ void max_norm_kernel(const float* nrm, uint32_t lo, uint32_t hi, float* out) {
+    float m = 0.0f;
+    for (uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) m = fmaxf(m, nrm[i]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
 }
 
 template <int ST, int METRIC>
@@ -459,8 +621,45 @@ void launch_exact_candidates(const ExactParams& p, cudaStream_t stream) {
     g_kernel_launches += 1;
 }
 
+uint32_t exact_scan_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count) {
+    const uint32_t q_blocks = (nq + SCAN_QB - 1) / SCAN_QB;
+    const uint32_t want = (4u * (uint32_t)sm_count + q_blocks - 1) / q_blocks;
+    const uint32_t max_by_rows = (n_rows + 1023) / 1024;
+    uint32_t s = want < max_by_rows ? want : max_by_rows;
+    return s < 1 ? 1 : s;
+}
+
+uint32_t exact_scan_lists_per_query(uint32_t n_splits) { return n_splits * SCAN_WARPS; }
+
+void launch_exact_scan(const ExactParams& p, uint32_t k, cudaStream_t stream) {
+    if (p.q.n == 0 || p.x_hi <= p.x_lo) return;
+    ScanArgs a;
+    a.q_rows = p.q.rows; a.q_nrm = p.q.nrm; a.nq = p.q.n; a.q_row_bytes = p.q.row_bytes;
+    a.x_rows = p.x.rows; a.x_nrm = p.x.nrm; a.x_row_bytes = p.x.row_bytes; a.x_lo = p.x_lo; a.x_hi = p.x_hi;
+    a.deny = p.deny; a.keys = p.keys; a.allow = p.allow; a.allow_bits = p.allow_bits;
+    a.kf = p.kp;  // the caller sets kp = round_up(k (+1 for self), 32): lists hold exactly what K3 needs
+    (void)k;
+    a.n_splits = p.n_splits;
+    const uint32_t rows = p.x_hi - p.x_lo;
+    a.rows_per_split = ((rows + p.n_splits - 1) / p.n_splits + 31) / 32 * 32;
+    a.part = p.part;
+    dim3 grid((p.q.n + SCAN_QB - 1) / SCAN_QB, p.n_splits);
+    const size_t smem = (size_t)SCAN_WARPS * SCAN_QB * a.kf * 8;
+    VSB_DISPATCH_PAIR(p.storage, p.metric, (launch_scan<ST, METRIC>(a, grid, smem, stream)));
+    g_kernel_launches += 1;
+}
+
+void launch_max_norm(const float* nrm, uint32_t lo, uint32_t hi, float* out, cudaStream_t stream) {
+    cudaMemsetAsync(out, 0, sizeof(float), stream);
+    if (hi <= lo) return;
+    const uint32_t blocks = std::min<uint32_t>((hi - lo + 1023) / 1024, 296);
+    max_norm_kernel<<<blocks, 256, 0, stream>>>(nrm, lo, hi, out);
+    g_kernel_launches += 1;
+}
+
 void launch_exact_rerank(const ExactParams& p, uint32_t k, uint64_t* out_keys, float* out_dists,
-                         uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t stream) {
+                         uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t stream,
+                         const ExactCert* cert, const uint32_t* q_map) {
     if (p.q.n == 0) return;
     K3Args a;
     a.q_rows = p.q.rows; a.q_nrm = p.q.nrm; a.nq = p.q.n; a.q_row_bytes = p.q.row_bytes;
@@ -469,6 +668,12 @@ void launch_exact_rerank(const ExactParams& p, uint32_t k, uint64_t* out_keys, f
     a.k = k; a.kf = ((k + 31) / 32) * 32;
     a.out_keys = out_keys; a.out_dists = out_dists; a.out_counts = out_counts; a.out_packed = out_packed;
     a.self_base = self_base;
+    a.x_nrm_max = cert ? cert->x_nrm_max : nullptr;
+    a.cert_rel = cert ? cert->rel : 0.0f;
+    a.cert_sum = cert ? cert->sum : 0.0f;
+    a.uncert_flags = cert ? cert->flags : nullptr;
+    a.uncert_count = cert ? cert->count : nullptr;
+    a.q_map = q_map;
     dim3 grid((p.q.n + K3_WARPS - 1) / K3_WARPS);
     const size_t smem = (size_t)K3_WARPS * (a.kp + a.kf) * 8;
     VSB_DISPATCH_PAIR(p.storage, p.metric, (launch_k3<ST, METRIC>(a, grid, smem, stream)));

@@ -138,6 +138,12 @@ struct vsb_index {
     DevBuf seed16_rows, seed16_sq, seed16_nrm;   // bf16 shadow of the seed block (f32 storage only)
     DevBuf q16_rows, q16_sq, q16_nrm;            // bf16 shadow of the converted queries (f32 storage only)
     DevBuf q_in, q_rows, q_sq, q_nrm, part, seed_part, tmp_keys, tmp_dists, counters, add_in, allow;
+    // certified TF32 candidate stage for exact search on f32 rows (exact_block)
+    DevBuf cert_state, fb_map, fb_rows, fb_sq, fb_nrm;
+    bool cert_enabled = true;     // VSB_DISABLE_CERT=1: exact f32 search always on the SIMT tiles
+    uint32_t cert_kp = 128;       // candidate list length of the certified TF32 stage (VSB_CERT_KP)
+    uint32_t cert_kp16 = 32;      // ... of the certified f16/bf16 tensor-core stage (VSB_CERT_KP16)
+    uint64_t cert_ok = 0, cert_fallback = 0, cert_scanned = 0;
     std::unordered_map<uint64_t, uint32_t> key2slot;
     std::vector<uint32_t> h_deny;
 
@@ -180,7 +186,7 @@ struct vsb_index {
         const DevBuf* all[] = {&rows, &sq, &nrm, &keys, &deny, &graph, &rows16, &sq16, &nrm16, &rr_packed, &seed_rows, &seed_sq, &seed_nrm, &seed_slots,
                                &seed16_rows, &seed16_sq, &seed16_nrm, &q16_rows, &q16_sq, &q16_nrm,
                                &q_in, &q_rows, &q_sq, &q_nrm, &part, &seed_part, &tmp_keys, &tmp_dists, &counters,
-                               &add_in, &allow};
+                               &add_in, &allow, &cert_state, &fb_map, &fb_rows, &fb_sq, &fb_nrm};
         size_t s = 0;
         for (auto* b : all) s += b->bytes;
         return s;
@@ -391,16 +397,23 @@ vsb_status vsb_index::exact_block(const vsb::RowsView& q, const vsb::RowsView& x
     const uint32_t extra = std::max<uint32_t>(16, k / 4) + (self_base >= 0 ? 1 : 0);
     p.kp = round_up(k + extra, 32);
     if (p.kp > 256) return fail(VSB_EINVAL, "k=%u too large for the exact path (max 200)", k);
-    // tensor-core tiles: 16-bit storages multiply exactly (only the fp32 accumulation order differs, covered
-    // by the over-fetch); f32 storage runs as TF32 and is used only where candidate-grade lists suffice
-    bool tc = tc_enabled && vsb::exact_tc_supported(storage, metric) && (x_hi - x_lo) >= tc_min_rows &&
-              (approx_ok || storage != VSB_F32);
+    // Tensor-core tiles: 16-bit storages multiply exactly, f32 rows run as TF32.  Any tiled stage (tensor core
+    // or SIMT) sums in its own order, so its lists are candidate-grade; for exact results on float storages K3
+    // CERTIFIES each query (no dropped row can reach or tie into the canonical top-k) and the queries it
+    // cannot certify fall through: TF32 tiles -> fp32 SIMT tiles -> canonical scan (K1c, needs no certificate).
+    // Integer storages (i8, b1) are exact in every stage and ordered by (distance, key) throughout.
+    const bool tc_shape = tc_enabled && vsb::exact_tc_supported(storage, metric) && (x_hi - x_lo) >= tc_min_rows;
+    const bool is_float = storage == VSB_F32 || storage == VSB_F16 || storage == VSB_BF16;
+    const bool certify = is_float && !approx_ok && cert_enabled;
+    bool tc = tc_shape && (approx_ok || storage != VSB_F32 || certify);
+    const uint32_t kp_simt = p.kp;
+    if (certify && tc) p.kp = std::min<uint32_t>(256, std::max<uint32_t>(p.kp, round_up(storage == VSB_F32 ? cert_kp : cert_kp16, 32)));
     p.n_splits = tc ? vsb::exact_tc_pick_splits(q.n, x_hi - x_lo, sm_count)
                     : vsb::exact_pick_splits(q.n, x_hi - x_lo, sm_count);
     CU(part.ensure(vsb::exact_part_elems(q.n, p.n_splits, p.kp) * 8));
     p.part = part.as<uint64_t>();
     if (tc) {
-        if (shadow_q != nullptr && shadow_x != nullptr) {
+        if (shadow_q != nullptr && shadow_x != nullptr && !certify) {
             // candidate stage on the bf16 shadow (half the bytes, kind::f16 rate); K3 re-ranks on the real rows
             vsb::ExactParams pc = p;
             pc.storage = VSB_BF16;
@@ -411,9 +424,115 @@ vsb_status vsb_index::exact_block(const vsb::RowsView& q, const vsb::RowsView& x
             tc = vsb::launch_exact_candidates_tc(p, s);
         }
     }
-    if (!tc) vsb::launch_exact_candidates(p, s);
+    if (!tc) {
+        if (p.kp != kp_simt) {  // the tensor-core launch was refused: plain SIMT with its own list length
+            p.kp = kp_simt;
+            p.n_splits = vsb::exact_pick_splits(q.n, x_hi - x_lo, sm_count);
+            CU(part.ensure(vsb::exact_part_elems(q.n, p.n_splits, p.kp) * 8));
+            p.part = part.as<uint64_t>();
+        }
+        vsb::launch_exact_candidates(p, s);
+    }
     CU(cudaGetLastError());
-    vsb::launch_exact_rerank(p, k, out_keys, out_dists, out_counts, out_packed, self_base, s);
+    if (!certify) {
+        vsb::launch_exact_rerank(p, k, out_keys, out_dists, out_counts, out_packed, self_base, s);
+        CU(cudaGetLastError());
+        return VSB_OK;
+    }
+
+    // cert_state: [0] = max row norm of the block, [1] = number of flagged queries, [2..] flags
+    CU(cert_state.ensure((size_t)(q.n + 2) * 4));
+    float* d_xmax = cert_state.as<float>();
+    uint32_t* d_count = cert_state.as<uint32_t>() + 1;
+    uint32_t* d_flags = cert_state.as<uint32_t>() + 2;
+    vsb::launch_max_norm(x.nrm, x_lo, x_hi, d_xmax, s);
+    vsb::ExactCert cert;
+    cert.x_nrm_max = d_xmax;
+    cert.flags = d_flags;
+    cert.count = d_count;
+    // An fp32 sum of `dim` products, in any order, is within dim * 2^-24 |q||x| of the real dot product (2^-23 per
+    // add if the adder truncates); candidate and canonical evaluation together: dim * 2^-22 with margin.
+    // TF32 additionally keeps only 10 mantissa bits of each operand: <= 2^-10 relative each, 2^-9 on the product.
+    const float rel_fp32 = (float)dim * 0x1p-22f;
+    const float rel_tf32 = 1.25f * 0x1p-9f + rel_fp32;
+    cert.sum = (float)dim * 0x1p-23f;
+    cert.rel = (tc && storage == VSB_F32) ? rel_tf32 : rel_fp32;
+
+    // flagged queries of one stage -> compact map (indices into the caller's query block) + gathered rows
+    std::vector<uint32_t> map, flags;
+    auto collect = [&](uint32_t n_stage, const std::vector<uint32_t>* prev) -> vsb_status {
+        flags.resize(n_stage);
+        CU(cudaMemcpyAsync(flags.data(), d_flags, (size_t)n_stage * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        std::vector<uint32_t> next;
+        for (uint32_t i = 0; i < n_stage; ++i)
+            if (flags[i]) next.push_back(prev ? (*prev)[i] : i);
+        map.swap(next);
+        const uint32_t nf = (uint32_t)map.size();
+        CU(fb_map.ensure((size_t)nf * 4));
+        CU(fb_rows.ensure((size_t)nf * q.row_bytes));
+        CU(fb_sq.ensure((size_t)nf * 4));
+        CU(fb_nrm.ensure((size_t)nf * 4));
+        CU(cudaMemcpyAsync(fb_map.p, map.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, s));
+        vsb::launch_gather_rows(q.rows, q.row_bytes, q.sq, q.nrm, fb_map.as<uint32_t>(), nf, fb_rows.as<uint8_t>(),
+                                fb_sq.as<float>(), fb_nrm.as<float>(), s);
+        CU(cudaStreamSynchronize(s));  // `map` is pageable and is rebuilt by the next stage
+        return VSB_OK;
+    };
+    auto read_count = [&](uint32_t* out) -> vsb_status {
+        CU(cudaMemcpyAsync(out, d_count, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        return VSB_OK;
+    };
+
+    CU(cudaMemsetAsync(d_count, 0, 4, s));
+    vsb::launch_exact_rerank(p, k, out_keys, out_dists, out_counts, out_packed, self_base, s, &cert);
+    CU(cudaGetLastError());
+    uint32_t n_flagged = 0;
+    ST(read_count(&n_flagged));
+    cert_ok += q.n - n_flagged;
+    cert_fallback += n_flagged;
+    if (n_flagged == 0) return VSB_OK;
+    ST(collect(q.n, nullptr));
+
+    vsb::ExactParams pf = p;
+    pf.q.rows = fb_rows.as<uint8_t>();
+    pf.q.sq = fb_sq.as<float>();
+    pf.q.nrm = fb_nrm.as<float>();
+    pf.q.n = (uint32_t)map.size();
+    if (tc && storage == VSB_F32) {
+        // second stage: full fp32 products on the SIMT tiles, same certificate with the fp32 bound
+        pf.kp = kp_simt;
+        pf.n_splits = vsb::exact_pick_splits(pf.q.n, x_hi - x_lo, sm_count);
+        CU(part.ensure(vsb::exact_part_elems(pf.q.n, pf.n_splits, pf.kp) * 8));
+        pf.part = part.as<uint64_t>();
+        vsb::launch_exact_candidates(pf, s);
+        CU(cudaGetLastError());
+        cert.rel = rel_fp32;
+        CU(cudaMemsetAsync(d_count, 0, 4, s));
+        vsb::launch_exact_rerank(pf, k, out_keys, out_dists, out_counts, out_packed, self_base, s, &cert,
+                                 fb_map.as<uint32_t>());
+        CU(cudaGetLastError());
+        ST(read_count(&n_flagged));
+        if (n_flagged == 0) return VSB_OK;
+        const std::vector<uint32_t> prev = map;
+        ST(collect(pf.q.n, &prev));
+        pf.q.n = (uint32_t)map.size();
+    }
+
+    // last stage: canonical scan of the whole block for what is left
+    cert_scanned += pf.q.n;
+    pf.kp = round_up(k + (self_base >= 0 ? 1 : 0), 32);
+    const uint32_t scan_splits = vsb::exact_scan_pick_splits(pf.q.n, x_hi - x_lo, sm_count);
+    pf.n_splits = scan_splits;
+    const uint32_t lists = vsb::exact_scan_lists_per_query(scan_splits);
+    CU(part.ensure(vsb::exact_part_elems(pf.q.n, lists, pf.kp) * 8));
+    pf.part = part.as<uint64_t>();
+    vsb::launch_exact_scan(pf, k, s);
+    CU(cudaGetLastError());
+    pf.n_splits = lists;
+    vsb::launch_exact_rerank(pf, k, out_keys, out_dists, out_counts, out_packed, self_base, s, nullptr,
+                             fb_map.as<uint32_t>());
     CU(cudaGetLastError());
     return VSB_OK;
 }
@@ -1067,6 +1186,9 @@ vsb_status vsb_create(const vsb_options* o, vsb_index** out) {
     ix->trav16 = (o->flags & VSB_FLAG_BF16_TRAVERSAL) != 0 && o->storage == VSB_F32;
     ix->row_bytes16 = storage_row_bytes(VSB_BF16, o->dimensions);
     if (const char* e = getenv("VSB_DISABLE_TC")) ix->tc_enabled = !(e[0] == '1');
+    if (const char* e = getenv("VSB_DISABLE_CERT")) ix->cert_enabled = !(e[0] == '1');
+    if (const char* e = getenv("VSB_CERT_KP")) ix->cert_kp = (uint32_t)strtoul(e, nullptr, 10);
+    if (const char* e = getenv("VSB_CERT_KP16")) ix->cert_kp16 = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("VSB_TC_MIN_ROWS")) ix->tc_min_rows = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("VSB_ALLPAIRS_MAX")) ix->allpairs_max = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("VSB_ALLPAIRS_PREFIX")) ix->allpairs_prefix = (uint32_t)strtoul(e, nullptr, 10);
@@ -1207,6 +1329,9 @@ vsb_status vsb_get_stats(vsb_index* ix, vsb_stats* out) {
     out->exact_launches = ix->phase_launches[vsb_index::PH_EXACT];
     out->merge_launches = ix->phase_launches[vsb_index::PH_MERGE];
     out->tc_launches = vsb::g_tc_launches.load();
+    out->exact_certified = ix->cert_ok;
+    out->exact_fallback = ix->cert_fallback;
+    out->exact_scanned = ix->cert_scanned;
     return VSB_OK;
 }
 

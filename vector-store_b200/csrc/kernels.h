@@ -50,8 +50,25 @@ void launch_exact_candidates(const ExactParams& p, cudaStream_t stream);
 //   out_keys/out_dists/out_counts: user-facing result (nullable)
 //   out_packed: [q.n][k] packed (ord(dist)<<32 | slot), kInvalidPacked padded (nullable; used by the build)
 //   self_base: if >= 0 the query i is row (self_base + i) of x and is dropped from its own list
+//   cert: the candidate stage ran at reduced precision; flag every query whose top-k is not PROVABLY the
+//         full-precision one (see exact_rerank_kernel step 4) so the caller can re-run those on the SIMT path
+//   q_map: query i of this launch is query q_map[i] of the caller (outputs are written to row q_map[i])
+struct ExactCert {
+    const float* x_nrm_max = nullptr;  // device scalar: max row norm of the searched block
+    float rel = 0.0f;                  // bound on |dot_candidate - dot_canonical| / (|q| |x|)
+    float sum = 0.0f;                  // relative rounding bound of an fp32 sum of `dim` terms
+    uint32_t* flags = nullptr;         // [q.n] 1 = not certified
+    uint32_t* count = nullptr;         // device scalar, incremented per flagged query (zeroed by the caller)
+};
 void launch_exact_rerank(const ExactParams& p, uint32_t k, uint64_t* out_keys, float* out_dists,
-                         uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t stream);
+                         uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t stream,
+                         const ExactCert* cert = nullptr, const uint32_t* q_map = nullptr);
+// K1c canonical scan (no candidate stage): writes exact_scan_lists_per_query(n_splits) lists of p.kp entries
+// per query into p.part; follow with launch_exact_rerank on ExactParams{kp, n_splits = lists per query}.
+uint32_t exact_scan_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count);
+uint32_t exact_scan_lists_per_query(uint32_t n_splits);
+void launch_exact_scan(const ExactParams& p, uint32_t k, cudaStream_t stream);
+void launch_max_norm(const float* nrm, uint32_t lo, uint32_t hi, float* out, cudaStream_t stream);
 
 // K1 on tcgen05 tensor cores (exact_tc.cu): same contract as launch_exact_candidates.
 bool exact_tc_supported(int storage, int metric);

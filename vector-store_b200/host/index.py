@@ -163,6 +163,21 @@ class GpuIndex:
         check(fn(self._h, _ptr(q), n, k, _ptr(keys), _ptr(dists), _ptr(counts)))
         return keys, dists, counts
 
+    def search_filtered(self, queries, k: int, allow_mask):
+        """Batched filtered search: allow_mask[i] (bool) admits the row whose id (key & 2^48-1) is i."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        self._check_dim(q)
+        mask = np.asarray(allow_mask, dtype=bool)
+        bm = np.packbits(mask, bitorder="little")
+        bm = np.concatenate([bm, np.zeros((-len(bm)) % 4, np.uint8)]).view(np.uint32)
+        n = q.shape[0]
+        keys = np.empty((n, k), dtype=np.uint64)
+        dists = np.empty((n, k), dtype=np.float32)
+        counts = np.empty(n, dtype=np.uint32)
+        check(self._lib.vsb_search_filtered(self._h, _ptr(q), n, k, _ptr(bm), len(mask), _ptr(keys), _ptr(dists),
+                                            _ptr(counts)))
+        return keys, dists, counts
+
     def search_raw(self, q_ptr: int, n: int, k: int, keys_ptr: int, dists_ptr: int, counts_ptr: int,
                    exact: bool = False) -> None:
         """Host-pointer call without NumPy marshalling (bench e2e leg uses pinned torch buffers)."""

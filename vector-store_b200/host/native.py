@@ -33,7 +33,8 @@ class VsbStats(C.Structure):
                                           "n_slots", "n_graphed", "graph_degree", "row_bytes", "n_seed_rows",
                                           "hbm_bytes", "convert_ns", "seed_ns", "graph_search_ns", "exact_ns",
                                           "merge_ns", "convert_launches", "seed_launches", "graph_search_launches",
-                                          "exact_launches", "merge_launches", "tc_launches")]
+                                          "exact_launches", "merge_launches", "tc_launches",
+                                          "exact_certified", "exact_fallback", "exact_scanned")]
 
 
 # every symbol include/vsb200.h declares: (name, restype, argtypes)
