@@ -1099,7 +1099,8 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
         if (have_tail) {
             t_begin(PH_EXACT, s);
             vsb_status est = exact_block(qv, x, tail_lo, tail_hi, deny_bm, keys.as<uint64_t>(), d_allow, allow_bits, k,
-                                         t_keys, t_dists, use_graph ? nullptr : o_counts, nullptr, -1, s, false);
+                                         t_keys, t_dists, use_graph ? nullptr : o_counts, nullptr, -1, s,
+                                         /*approx_ok=*/use_graph);  // the ANN tail needs no certificate (no host sync)
             t_end(s);
             ST(est);
         }
