@@ -43,11 +43,13 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--n", "--rows", dest="n", type=int, default=1_000_000)  # torchrun's own parser trips over a bare --n
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--batch", type=int, default=10_000)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--storage", default="f32", choices=["f32", "bf16", "f16"])
+    ap.add_argument("--clusters", type=int, default=256,
+                    help="mixture components of the synthetic corpus (256 at 1M rows = 3.9k rows per cluster; scale with --n)")
     ap.add_argument("--target-recall", type=float, default=0.95)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="corpus rows of the bounded CPU-baseline sample")
     ap.add_argument("--search-width", type=int, default=2)
@@ -59,7 +61,10 @@ def parse_args():
 
 
 def workload_name(a):
-    return f"{a.n}x{a.dim} {a.storage} cosine embedding-shaped synthetic (BASELINE configs[1]), k={a.k}, query batch {a.batch}"
+    cfg = "configs[1]" if a.n <= 2_000_000 else "configs[2]"
+    mix = "" if a.clusters == 256 else f" ({a.clusters} mixture components)"
+    return (f"{a.n}x{a.dim} {a.storage} cosine embedding-shaped synthetic{mix} (BASELINE {cfg}), k={a.k}, "
+            f"query batch {a.batch}")
 
 
 def load_peaks():
@@ -152,8 +157,8 @@ def cpu_hnsw_run(a, steps, warmup, full_line):
     threads = os.cpu_count() or 1
     n = min(a.cpu_sample, a.n)
     CH = 100_000  # same chunked stream as the GPU arm: row r comes from chunk r // CH
-    x = np.concatenate([ds.embedding_like(min(CH, n - c0), a.dim, seed=1234 + c0 // CH) for c0 in range(0, n, CH)])
-    q = ds.embedding_like(a.cpu_queries, a.dim, seed=4321)
+    x = np.concatenate([ds.embedding_like(min(CH, n - c0), a.dim, seed=1234 + c0 // CH, n_clusters=a.clusters) for c0 in range(0, n, CH)])
+    q = ds.embedding_like(a.cpu_queries, a.dim, seed=4321, n_clusters=a.clusters)
     st = O.BF16 if a.storage == "bf16" else O.F32
     h = O.HnswCpu(a.dim, O.COS, n, 16, 128, 64, storage=st, threads=threads)
     t0 = time.perf_counter()
@@ -245,7 +250,7 @@ def main():
     # loading and the first cudaMalloc's are not billed to the timed build below ----
     warm = v.GpuIndex(a.dim, v.Metric.Cos, scalar, device=local_rank, bf16_traversal=trav16)
     warm.reserve(40_000)
-    wx = ds.embedding_like(40_000, a.dim, seed=7)
+    wx = ds.embedding_like(40_000, a.dim, seed=7, n_clusters=a.clusters)
     warm.add_batch(np.arange(40_000, dtype=np.uint64)[:30_000], wx[:30_000])
     warm.build()
     warm.add_batch(np.arange(30_000, 40_000, dtype=np.uint64), wx[30_000:])
@@ -263,7 +268,7 @@ def main():
     # global row r comes from chunk r // CH of the global stream, so shards of any world size hold the same data
     for c0 in range((lo // CH) * CH, hi, CH):
         t0 = time.perf_counter()
-        xc = ds.embedding_like(min(CH, a.n - c0), a.dim, seed=1234 + c0 // CH)
+        xc = ds.embedding_like(min(CH, a.n - c0), a.dim, seed=1234 + c0 // CH, n_clusters=a.clusters)
         s, e = max(lo, c0) - c0, min(hi, c0 + CH) - c0
         xc = xc[s:e]
         keys = np.arange(c0 + s, c0 + e, dtype=np.uint64)
@@ -289,7 +294,7 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     q_host, q_dev = [], []
     for b in range(NB):
-        qb = torch.from_numpy(ds.embedding_like(B, a.dim, seed=4321 + b)).pin_memory()
+        qb = torch.from_numpy(ds.embedding_like(B, a.dim, seed=4321 + b, n_clusters=a.clusters)).pin_memory()
         q_host.append(qb)
         q_dev.append(qb.to(dev, non_blocking=False))
     keys_l = torch.empty((B, k), dtype=torch.int64, device=dev)
