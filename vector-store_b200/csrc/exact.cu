@@ -297,90 +297,141 @@ struct K3Args {
     const uint32_t* q_map;  // query q of this launch is query q_map[q] of the caller (outputs, self slot)
 };
 
-constexpr int K3_WARPS = 4;
+constexpr int K3_WARPS = 4;   // warp-per-query variant: queries per CTA
+constexpr int K3C_WARPS = 8;  // CTA-per-query variant (small batches): warps sharing one query's candidates
 
+// canonical distances of up to four candidate rows, evaluated by one warp (four rows in flight: 4x the
+// memory-level parallelism of a one-by-one loop, each accumulator still follows the canonical order)
 template <int ST, int METRIC>
-__global__ void __launch_bounds__(K3_WARPS * 32) exact_rerank_kernel(K3Args a) {
+__device__ __forceinline__ void k3_eval4(const K3Args& a, const uint4* qrow, int n_chunks, float qn, const uint32_t (&slot)[4],
+                                         const bool (&on)[4], float (&d)[4], int lane) {
+    ChunkAcc<ST, METRIC> acc[4];
+    const uint4* xr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        xr[u] = reinterpret_cast<const uint4*>(a.x_rows + (size_t)(on[u] ? slot[u] : 0u) * a.x_row_bytes);
+    for (int ch = lane; ch < n_chunks; ch += 32) {
+        const uint4 qv = qrow[ch];
+        uint4 xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (on[u]) xv[u] = ldg_nc_v4(xr[u] + ch);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (on[u]) acc[u].add(qv, xv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        d[u] = 0.0f;
+        if (!on[u]) continue;
+        float f = 0.0f;
+        int i = 0;
+        if constexpr (Storage<ST>::kFloat)
+            f = butterfly_sum(acc[u].f);
+        else
+            i = butterfly_sum_i(acc[u].i);
+        d[u] = finish_distance<ST, METRIC>(f, i, qn, a.x_nrm[slot[u]]);
+    }
+}
+
+// CTA == false: one warp per query, K3_WARPS queries per CTA (large batches).
+// CTA == true : one CTA of K3C_WARPS warps per query; the candidates are re-evaluated four per warp in parallel
+//               (a single-query call would otherwise walk its 2k candidates with one warp).
+template <int ST, int METRIC, bool CTA>
+__global__ void __launch_bounds__((CTA ? K3C_WARPS : K3_WARPS) * 32) exact_rerank_kernel(K3Args a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t q = blockIdx.x * K3_WARPS + warp;
+    const uint32_t q = CTA ? blockIdx.x : blockIdx.x * K3_WARPS + warp;
     if (q >= a.nq) return;
-    uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warp * (a.kp + a.kf);  // [kp]
-    uint64_t* fin = cand + a.kp;                                                            // [kf]
+    uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw) + (CTA ? 0 : (size_t)warp * (a.kp + a.kf));  // [kp]
+    uint64_t* fin = cand + a.kp;                                                                         // [kf]
+    uint64_t* res_s = fin + a.kf;                                                                        // [kp] (CTA only)
     const LessByKey less{a.keys};
+    const bool lead = !CTA || warp == 0;
 
     // 1. merge the split lists by candidate-grade distance
-    for (uint32_t i = lane; i < a.kp; i += 32) cand[i] = a.part[((size_t)q * a.n_splits) * a.kp + i];
-    for (uint32_t i = lane; i < a.kf; i += 32) fin[i] = kInvalidPacked;
-    __syncwarp();
-    for (uint32_t s = 1; s < a.n_splits; ++s) {
-        const uint64_t* src = a.part + ((size_t)q * a.n_splits + s) * a.kp;
-        for (uint32_t b = 0; b < a.kp; b += 32) {
-            uint64_t v = src[b + lane];  // already ascending inside the list
-            if (shfl_u64(v, 0) == kInvalidPacked) break;
-            warp_list_merge(cand, (int)a.kp, v, lane, less);
+    if (lead) {
+        for (uint32_t i = lane; i < a.kp; i += 32) cand[i] = a.part[((size_t)q * a.n_splits) * a.kp + i];
+        for (uint32_t i = lane; i < a.kf; i += 32) fin[i] = kInvalidPacked;
+        __syncwarp();
+        for (uint32_t s = 1; s < a.n_splits; ++s) {
+            const uint64_t* src = a.part + ((size_t)q * a.n_splits + s) * a.kp;
+            for (uint32_t b = 0; b < a.kp; b += 32) {
+                uint64_t v = src[b + lane];  // already ascending inside the list
+                if (shfl_u64(v, 0) == kInvalidPacked) break;
+                warp_list_merge(cand, (int)a.kp, v, lane, less);
+            }
         }
+        __syncwarp();
     }
-    __syncwarp();
+    if constexpr (CTA) {
+        for (uint32_t i = threadIdx.x; i < a.kp; i += K3C_WARPS * 32) res_s[i] = kInvalidPacked;
+        __syncthreads();
+    }
     // every row that is NOT a candidate has a candidate-stage distance >= the worst kept one
     const uint64_t cand_floor = cand[a.kp - 1];
     const uint32_t oq = a.q_map != nullptr ? a.q_map[q] : q;
 
-    // 2. canonical re-evaluation, 32 candidates at a time
+    // 2. canonical re-evaluation
     const uint4* qrow = reinterpret_cast<const uint4*>(a.q_rows + (size_t)q * a.q_row_bytes);
     const int n_chunks = a.x_row_bytes / 16;
     const float qn = a.q_nrm[q];
     const uint32_t self_slot = a.self_base >= 0 ? (uint32_t)(a.self_base + oq) : kInvalidSlot;
-    for (uint32_t b = 0; b < a.kp; b += 32) {
-        const uint64_t mine = cand[b + lane];
-        uint64_t res = kInvalidPacked;
-        bool end_of_list = false;
-        // four candidates in flight per step: 4x the memory-level parallelism of a one-by-one loop,
-        // each accumulator still follows the canonical order
-        for (int c0 = 0; c0 < 32 && !end_of_list; c0 += 4) {
+    if constexpr (CTA) {
+        for (uint32_t g = warp; g * 4 < a.kp; g += K3C_WARPS) {
             uint32_t slot[4];
             bool on[4];
             bool any = false;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const uint64_t pc = shfl_u64(mine, c0 + u);
-                if (pc == kInvalidPacked) end_of_list = true;  // ascending: the rest of the block is padding
+                const uint64_t pc = cand[g * 4 + u];
                 slot[u] = packed_lo(pc);
                 on[u] = pc != kInvalidPacked && slot[u] != self_slot;
                 any = any || on[u];
             }
             if (!any) continue;
-            ChunkAcc<ST, METRIC> acc[4];
-            const uint4* xr[4];
+            float d[4];
+            k3_eval4<ST, METRIC>(a, qrow, n_chunks, qn, slot, on, d, lane);
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                xr[u] = reinterpret_cast<const uint4*>(a.x_rows + (size_t)(on[u] ? slot[u] : 0u) * a.x_row_bytes);
-            for (int ch = lane; ch < n_chunks; ch += 32) {
-                const uint4 qv = qrow[ch];
-                uint4 xv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (on[u]) xv[u] = ldg_nc_v4(xr[u] + ch);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (on[u]) acc[u].add(qv, xv[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (!on[u]) continue;
-                float f = 0.0f;
-                int i = 0;
-                if constexpr (Storage<ST>::kFloat)
-                    f = butterfly_sum(acc[u].f);
-                else
-                    i = butterfly_sum_i(acc[u].i);
-                const float d = finish_distance<ST, METRIC>(f, i, qn, a.x_nrm[slot[u]]);
-                if (lane == c0 + u) res = pack_ds(d, slot[u]);
-            }
+                if (lane == u && on[u]) res_s[g * 4 + u] = pack_ds(d[u], slot[u]);
         }
-        if (__ballot_sync(kFullMask, res != kInvalidPacked) == 0) continue;
-        res = warp_sort32(res, lane, less);
-        warp_list_merge(fin, (int)a.kf, res, lane, less);
+        __syncthreads();
+        if (warp != 0) return;
+        for (uint32_t b = 0; b < a.kp; b += 32) {
+            uint64_t res = res_s[b + lane];
+            if (__ballot_sync(kFullMask, res != kInvalidPacked) == 0) continue;
+            res = warp_sort32(res, lane, less);
+            warp_list_merge(fin, (int)a.kf, res, lane, less);
+        }
+    } else {
+        for (uint32_t b = 0; b < a.kp; b += 32) {
+            const uint64_t mine = cand[b + lane];
+            uint64_t res = kInvalidPacked;
+            bool end_of_list = false;
+            for (int c0 = 0; c0 < 32 && !end_of_list; c0 += 4) {
+                uint32_t slot[4];
+                bool on[4];
+                bool any = false;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint64_t pc = shfl_u64(mine, c0 + u);
+                    if (pc == kInvalidPacked) end_of_list = true;  // ascending: the rest of the block is padding
+                    slot[u] = packed_lo(pc);
+                    on[u] = pc != kInvalidPacked && slot[u] != self_slot;
+                    any = any || on[u];
+                }
+                if (!any) continue;
+                float d[4];
+                k3_eval4<ST, METRIC>(a, qrow, n_chunks, qn, slot, on, d, lane);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (on[u] && lane == c0 + u) res = pack_ds(d[u], slot[u]);
+            }
+            if (__ballot_sync(kFullMask, res != kInvalidPacked) == 0) continue;
+            res = warp_sort32(res, lane, less);
+            warp_list_merge(fin, (int)a.kf, res, lane, less);
+        }
     }
 
     // 3. emit
@@ -399,10 +450,10 @@ __global__ void __launch_bounds__(K3_WARPS * 32) exact_rerank_kernel(K3Args a) {
     }
     if (lane == 0 && a.out_counts != nullptr) a.out_counts[oq] = count;
 
-    // 4. certificate: the candidate stage ran at reduced precision (TF32).  A non-candidate row x has
-    //    candidate-stage distance >= cand_floor, hence canonical distance >= cand_floor - eps(q).  If the k-th
-    //    canonical distance found is strictly below that bound, no such row can enter (or tie into) the top-k and
-    //    the result equals the full-precision brute force.  Otherwise the query is flagged for the SIMT path.
+    // 4. certificate: the candidate stage summed in its own order / at reduced precision (TF32).  A non-candidate
+    //    row x has candidate-stage distance >= cand_floor, hence canonical distance >= cand_floor - eps(q).  If
+    //    the k-th canonical distance found is strictly below that bound, no such row can enter (or tie into) the
+    //    top-k and the result equals the canonical brute force.  Otherwise the query is flagged for the next stage.
     if (a.uncert_flags != nullptr && lane == 0) {
         bool ok = true;
         if (cand_floor != kInvalidPacked) {  // list full: rows were dropped
@@ -557,8 +608,14 @@ void launch_k1(const K1Args& a, dim3 grid, size_t smem, cudaStream_t stream) {
 }
 
 template <int ST, int METRIC>
-void launch_k3(const K3Args& a, dim3 grid, size_t smem, cudaStream_t stream) {
-    exact_rerank_kernel<ST, METRIC><<<grid, K3_WARPS * 32, smem, stream>>>(a);
+void launch_k3(const K3Args& a, bool cta, cudaStream_t stream) {
+    if (cta) {
+        const size_t smem = (size_t)(2 * a.kp + a.kf) * 8;
+        exact_rerank_kernel<ST, METRIC, true><<<a.nq, K3C_WARPS * 32, smem, stream>>>(a);
+    } else {
+        const size_t smem = (size_t)K3_WARPS * (a.kp + a.kf) * 8;
+        exact_rerank_kernel<ST, METRIC, false><<<(a.nq + K3_WARPS - 1) / K3_WARPS, K3_WARPS * 32, smem, stream>>>(a);
+    }
 }
 
 }  // namespace
@@ -674,9 +731,9 @@ void launch_exact_rerank(const ExactParams& p, uint32_t k, uint64_t* out_keys, f
     a.uncert_flags = cert ? cert->flags : nullptr;
     a.uncert_count = cert ? cert->count : nullptr;
     a.q_map = q_map;
-    dim3 grid((p.q.n + K3_WARPS - 1) / K3_WARPS);
-    const size_t smem = (size_t)K3_WARPS * (a.kp + a.kf) * 8;
-    VSB_DISPATCH_PAIR(p.storage, p.metric, (launch_k3<ST, METRIC>(a, grid, smem, stream)));
+    // small batches: a CTA per query (candidates spread over 8 warps) instead of a warp per query
+    const bool cta = p.q.n <= 1024 && a.kp >= 8;
+    VSB_DISPATCH_PAIR(p.storage, p.metric, (launch_k3<ST, METRIC>(a, cta, stream)));
     g_kernel_launches += 1;
 }
 

@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
     uint32_t* newq = hash + hsize;                                // [qcap]
     float* newd = reinterpret_cast<float*>(newq + qcap);          // [qcap]
     uint32_t* par = reinterpret_cast<uint32_t*>(newd + qcap);     // [K4B_MAX_WIDTH]
-    uint32_t* ctrl = par + K4B_MAX_WIDTH;                         // [0]=n_new [1]=np [2]=n_hashed
+    uint32_t* ctrl = par + K4B_MAX_WIDTH;                         // [0]=n_new [1]=np [2]=n_hashed [3]=n_keep
     const LessBySlot less;
     const bool is_l2 = a.metric == VSB_METRIC_L2SQ;
     const bool is_cos = a.metric == VSB_METRIC_COS;
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
 
     for (uint32_t i = tid; i < a.itopk; i += K4B_WARPS * 32) list[i] = kInvalidPacked;
     for (uint32_t i = tid; i < hsize; i += K4B_WARPS * 32) hash[i] = kHashEmpty;
-    if (tid < 3) ctrl[tid] = 0;
+    if (tid < 4) ctrl[tid] = 0;
 
     const uint4* qrow = reinterpret_cast<const uint4*>(a.q_rows + (size_t)q * a.q_row_bytes);
     float qf[QF];
@@ -437,39 +437,86 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
     unsigned long long n_evals = 0, n_parents = 0;
     __syncthreads();
 
+    const uint32_t width = a.search_width;
+    const uint32_t deg_pad = ((a.degree + 31) / 32) * 32;
+    // warp 0: the `width` best unexpanded list entries become the next parents; the graph rows of the `width`
+    // after them are prefetched into L2 (they are the likely parents of the following iteration)
+    auto pick_parents = [&]() {
+        uint32_t np = 0, ahead = 0;
+        for (uint32_t b = 0; b < a.itopk && ahead < width; b += 32) {
+            const uint64_t e = list[b + lane];
+            const bool unexp = e != kInvalidPacked && !(packed_lo(e) & kExpandedBit);
+            uint32_t m = __ballot_sync(kFullMask, unexp);
+            bool mine = false;
+            while (m && ahead < width) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                if (np < width) {
+                    if (lane == src) {
+                        par[np] = packed_lo(e);
+                        mine = true;
+                    }
+                    ++np;
+                } else {
+                    if (lane == src)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.graph + (size_t)packed_lo(e) * a.graph_stride));
+                    ++ahead;
+                }
+            }
+            if (mine) list[b + lane] = e | kExpandedBit;
+        }
+        if (lane == 0) ctrl[1] = np;
+        n_parents += np;
+    };
+
     // all warps: evaluate the queue (warp w takes entries w, w+8, ...), sort it in groups of 32,
-    // warp 0 folds the groups into the list
+    // warp 0 folds the groups into the list and picks the next parents
     auto evaluate_queue = [&]() {
         __syncthreads();
         const uint32_t n_new = ctrl[0];
         if (n_new != 0) {
             const uint32_t mine = n_new > (uint32_t)warp ? (n_new - warp + K4B_WARPS - 1) / K4B_WARPS : 0;
+            // the norm of the entry this thread will finish below: issued now so that its latency hides behind
+            // the row loads instead of adding a dependent global round trip to every iteration
+            float xn_first = 0.0f;
+            if (is_cos && (uint32_t)tid < n_new) xn_first = __ldg(a.x_nrm + newq[tid]);
             evaluate_entries<ST, CPL, U>(a.x_rows, a.x_row_bytes, newq, newd, (uint32_t)warp, K4B_WARPS, mine, n_new, qf, qc,
                                          is_l2, lane, n_chunks, full);
             __syncthreads();
-            for (uint32_t g = warp; g * 32 < n_new; g += K4B_WARPS) {
-                uint64_t res = kInvalidPacked;
-                if (g * 32 + lane < n_new) {
-                    const uint32_t slot = newq[g * 32 + lane];
-                    const float xn = is_cos ? __ldg(a.x_nrm + slot) : 0.0f;
-                    res = pack_ds(finish_raw<ST>(newd[g * 32 + lane], a.metric, qn, xn), slot);
-                }
+            // finish the distances and keep only what can enter the list: late in the search that is a handful
+            // of entries per iteration, i.e. ONE sorted group for warp 0 to fold instead of n_new / 32
+            const uint64_t worst = list[a.itopk - 1];
+            for (uint32_t i = tid; i < n_new; i += K4B_WARPS * 32) {
+                const uint32_t slot = newq[i];
+                const float xn = !is_cos ? 0.0f : (i == (uint32_t)tid ? xn_first : __ldg(a.x_nrm + slot));
+                const uint64_t res = pack_ds(finish_raw<ST>(newd[i], a.metric, qn, xn), slot);
+                if (res < worst) newp[atomicAdd(&ctrl[3], 1u)] = res;
+            }
+            __syncthreads();
+            const uint32_t n_keep = ctrl[3];
+            for (uint32_t g = warp; g * 32 < n_keep; g += K4B_WARPS) {
+                const uint64_t res = g * 32 + lane < n_keep ? newp[g * 32 + lane] : kInvalidPacked;
                 newp[g * 32 + lane] = warp_sort32(res, lane, less);
             }
             __syncthreads();
             if (warp == 0) {
-                for (uint32_t g = 0; g * 32 < n_new; ++g) {
+                for (uint32_t g = 0; g * 32 < n_keep; ++g) {
                     const uint64_t cand = newp[g * 32 + lane];
-                    const uint64_t worst = list[a.itopk - 1];
-                    if (__ballot_sync(kFullMask, cand < worst) == 0) continue;  // nothing here can enter the list
+                    const uint64_t tail = list[a.itopk - 1];
+                    if (__ballot_sync(kFullMask, cand < tail) == 0) continue;  // nothing here can enter the list
                     warp_list_merge(list, (int)a.itopk, cand, lane, less);
                 }
                 if (lane == 0) {
                     ctrl[2] += n_new;
                     ctrl[0] = 0;
+                    ctrl[3] = 0;
                 }
                 n_evals += n_new;
             }
+        }
+        if (warp == 0) {
+            __syncwarp();
+            pick_parents();
         }
         __syncthreads();
     };
@@ -493,8 +540,6 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
     }
     evaluate_queue();
 
-    const uint32_t width = a.search_width;
-    const uint32_t deg_pad = ((a.degree + 31) / 32) * 32;
     for (uint32_t it = 0; it < a.max_iters; ++it) {
         if (ctrl[2] > (hsize >> 2) * 3) {  // uniform: written before the last barrier
             __syncthreads();
@@ -513,29 +558,7 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
             if (cnt) atomicAdd(&ctrl[2], cnt);
             __syncthreads();
         }
-        if (warp == 0) {
-            uint32_t np = 0;
-            for (uint32_t b = 0; b < a.itopk && np < width; b += 32) {
-                const uint64_t e = list[b + lane];
-                const bool unexp = e != kInvalidPacked && !(packed_lo(e) & kExpandedBit);
-                uint32_t m = __ballot_sync(kFullMask, unexp);
-                bool mine = false;
-                while (m && np < width) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    if (lane == src) {
-                        par[np] = packed_lo(e);
-                        mine = true;
-                    }
-                    ++np;
-                }
-                if (mine) list[b + lane] = e | kExpandedBit;
-            }
-            if (lane == 0) ctrl[1] = np;
-            n_parents += np;
-        }
-        __syncthreads();
-        const uint32_t np = ctrl[1];
+        const uint32_t np = ctrl[1];  // picked by warp 0 at the end of the previous evaluate_queue
         if (np == 0) break;
         for (uint32_t t = tid; t < np * deg_pad; t += K4B_WARPS * 32) {
             const uint32_t i = t / deg_pad, r = t % deg_pad;
