@@ -70,7 +70,7 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
         a.max_iters = p.max_iters ? p.max_iters : (2 * a.itopk) / a.search_width + 8;
         a.queue_cap = a.search_width * deg_pad;
         dim3 gridb(p.q.n);
-        const size_t smemb = (size_t)a.itopk * 8 + (size_t)a.queue_cap * 16 + ((size_t)4 << bits) + 64;
+        const size_t smemb = (size_t)a.itopk * 16 + (size_t)a.queue_cap * 16 + ((size_t)4 << bits) + 64 + 128;
         switch (p.storage) {
             case VSB_ST_F32: launch_k4b_f32(a, cpl, gridb, smemb, stream); break;
             case VSB_ST_F16: launch_k4b_f16(a, cpl, gridb, smemb, stream); break;

@@ -12,6 +12,9 @@
 //     into the list.
 // HBM-bound by design: bytes/query = E * row_bytes + P * R * 4 (E, P counted in-kernel).
 #pragma once
+#ifdef VSB_K4B_PROFILE
+#include <cstdio>
+#endif
 #include "kernels.h"
 #include "select.cuh"
 
@@ -390,6 +393,19 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
 // expanded per iteration, so a query needs ~ef/8 dependent memory round trips instead of ~ef.
 constexpr int K4B_WARPS = 8;
 constexpr int K4B_MAX_WIDTH = 8;
+constexpr int K4B_PICK_ROUNDS = 4;  // list entries per thread in the parallel parent pick (itopk <= 1024)
+
+// -DVSB_K4B_PROFILE: thread 0 of CTA 0 accumulates clock64() per phase of the iteration and prints the split
+#ifdef VSB_K4B_PROFILE
+#define K4B_T(i)                                       \
+    do {                                               \
+        const long long now_ = clock64();              \
+        prof_[i] += now_ - prof_t_;                    \
+        prof_t_ = now_;                                \
+    } while (0)
+#else
+#define K4B_T(i) do { } while (0)
+#endif
 
 template <int ST, int CPL>
 __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4Args a) {
@@ -403,13 +419,15 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
     const uint32_t q = blockIdx.x;
     const uint32_t hsize = 1u << a.hash_bits, hmask = hsize - 1;
     const uint32_t qcap = a.queue_cap;
-    uint64_t* list = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* newp = list + a.itopk;                              // [qcap] sorted groups of 32
+    uint64_t* list = reinterpret_cast<uint64_t*>(smem_raw);       // [itopk] current list
+    uint64_t* list_alt = list + a.itopk;                          // [itopk] target of the next parallel merge
+    uint64_t* newp = list_alt + a.itopk;                          // [qcap] sorted groups of 32
     uint32_t* hash = reinterpret_cast<uint32_t*>(newp + qcap);    // [hsize]
     uint32_t* newq = hash + hsize;                                // [qcap]
     float* newd = reinterpret_cast<float*>(newq + qcap);          // [qcap]
     uint32_t* par = reinterpret_cast<uint32_t*>(newd + qcap);     // [K4B_MAX_WIDTH]
     uint32_t* ctrl = par + K4B_MAX_WIDTH;                         // [0]=n_new [1]=np [2]=n_hashed [3]=n_keep
+    uint32_t* wcnt = ctrl + 4;                                    // [K4B_PICK_ROUNDS * K4B_WARPS] unexpanded per warp
     const LessBySlot less;
     const bool is_l2 = a.metric == VSB_METRIC_L2SQ;
     const bool is_cos = a.metric == VSB_METRIC_COS;
@@ -436,43 +454,84 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
     const float qn = a.q_nrm[q];
     unsigned long long n_evals = 0, n_parents = 0;
     __syncthreads();
+#ifdef VSB_K4B_PROFILE
+    long long prof_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t_ = clock64();
+    const long long prof_start_ = prof_t_;
+#endif
 
     const uint32_t width = a.search_width;
     const uint32_t deg_pad = ((a.degree + 31) / 32) * 32;
-    // warp 0: the `width` best unexpanded list entries become the next parents; the graph rows of the `width`
-    // after them are prefetched into L2 (they are the likely parents of the following iteration)
+    // all threads: the `width` best unexpanded list entries become the next parents (rank among the unexpanded
+    // entries by ballot + per-warp counts); the graph rows of the `width` after them are prefetched into L2
+    // (they are the likely parents of the following iteration).  Ends with a barrier.
     auto pick_parents = [&]() {
-        uint32_t np = 0, ahead = 0;
-        for (uint32_t b = 0; b < a.itopk && ahead < width; b += 32) {
-            const uint64_t e = list[b + lane];
-            const bool unexp = e != kInvalidPacked && !(packed_lo(e) & kExpandedBit);
-            uint32_t m = __ballot_sync(kFullMask, unexp);
-            bool mine = false;
-            while (m && ahead < width) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                if (np < width) {
-                    if (lane == src) {
-                        par[np] = packed_lo(e);
-                        mine = true;
-                    }
-                    ++np;
-                } else {
-                    if (lane == src)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.graph + (size_t)packed_lo(e) * a.graph_stride));
-                    ++ahead;
+        uint64_t e[K4B_PICK_ROUNDS];
+        uint32_t m[K4B_PICK_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < K4B_PICK_ROUNDS; ++r) {
+            const uint32_t t = r * K4B_WARPS * 32 + tid;
+            e[r] = t < a.itopk ? list[t] : kInvalidPacked;
+            const bool unexp = e[r] != kInvalidPacked && !(packed_lo(e[r]) & kExpandedBit);
+            m[r] = __ballot_sync(kFullMask, unexp);
+            if (lane == 0) wcnt[r * K4B_WARPS + warp] = __popc(m[r]);
+        }
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int r = 0; r < K4B_PICK_ROUNDS; ++r) {
+#pragma unroll
+            for (int w = 0; w < K4B_WARPS; ++w) {
+                const uint32_t c = wcnt[r * K4B_WARPS + w];
+                total += c;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < K4B_PICK_ROUNDS; ++r) {
+            uint32_t base = before;
+#pragma unroll
+            for (int w = 0; w < K4B_WARPS; ++w) {
+                const uint32_t c = wcnt[r * K4B_WARPS + w];
+                if (w < warp) base += c;
+                before += c;
+            }
+            if (m[r] >> lane & 1u) {
+                const uint32_t rank = base + __popc(m[r] & ((1u << lane) - 1));
+                if (rank < width) {
+                    par[rank] = packed_lo(e[r]);
+                    list[r * K4B_WARPS * 32 + tid] = e[r] | kExpandedBit;
+                } else if (rank < 2 * width) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.graph + (size_t)packed_lo(e[r]) * a.graph_stride));
                 }
             }
-            if (mine) list[b + lane] = e | kExpandedBit;
         }
-        if (lane == 0) ctrl[1] = np;
-        n_parents += np;
+        const uint32_t np = total < width ? total : width;
+        if (tid == 0) {
+            ctrl[1] = np;
+            n_parents += np;
+        }
+        __syncthreads();
     };
 
-    // all warps: evaluate the queue (warp w takes entries w, w+8, ...), sort it in groups of 32,
-    // warp 0 folds the groups into the list and picks the next parents
+    // first index of the ascending run [seq, seq + len) whose value is not below x
+    auto lower_bound = [&](const uint64_t* seq, uint32_t len, uint64_t x) -> uint32_t {
+        uint32_t lo = 0, n = len;
+        while (n > 0) {
+            const uint32_t half = n >> 1;
+            const bool go = seq[lo + half] < x;
+            lo = go ? lo + half + 1 : lo;
+            n = go ? n - half - 1 : half;
+        }
+        return lo;
+    };
+
+    // all warps: evaluate the queue (warp w takes entries w, w+8, ...), keep what can enter the list, sort it in
+    // groups of 32, then merge list and groups IN PARALLEL: every element finds its final position as its own index
+    // plus its rank in each other sorted run (packed values are unique), and is scattered into the other list buffer
     auto evaluate_queue = [&]() {
+        K4B_T(0);  // own share of the neighbour fetch + visited filter
         __syncthreads();
+        K4B_T(1);  // waiting for the rest of the CTA
         const uint32_t n_new = ctrl[0];
         if (n_new != 0) {
             const uint32_t mine = n_new > (uint32_t)warp ? (n_new - warp + K4B_WARPS - 1) / K4B_WARPS : 0;
@@ -482,9 +541,9 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
             if (is_cos && (uint32_t)tid < n_new) xn_first = __ldg(a.x_nrm + newq[tid]);
             evaluate_entries<ST, CPL, U>(a.x_rows, a.x_row_bytes, newq, newd, (uint32_t)warp, K4B_WARPS, mine, n_new, qf, qc,
                                          is_l2, lane, n_chunks, full);
+            K4B_T(2);  // row loads + partial sums of warp 0's entries
             __syncthreads();
-            // finish the distances and keep only what can enter the list: late in the search that is a handful
-            // of entries per iteration, i.e. ONE sorted group for warp 0 to fold instead of n_new / 32
+            K4B_T(3);  // waiting for the slowest warp
             const uint64_t worst = list[a.itopk - 1];
             for (uint32_t i = tid; i < n_new; i += K4B_WARPS * 32) {
                 const uint32_t slot = newq[i];
@@ -492,33 +551,43 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
                 const uint64_t res = pack_ds(finish_raw<ST>(newd[i], a.metric, qn, xn), slot);
                 if (res < worst) newp[atomicAdd(&ctrl[3], 1u)] = res;
             }
+            for (uint32_t i = tid; i < a.itopk; i += K4B_WARPS * 32) list_alt[i] = kInvalidPacked;
             __syncthreads();
+            K4B_T(4);  // finish + filter
             const uint32_t n_keep = ctrl[3];
             for (uint32_t g = warp; g * 32 < n_keep; g += K4B_WARPS) {
                 const uint64_t res = g * 32 + lane < n_keep ? newp[g * 32 + lane] : kInvalidPacked;
                 newp[g * 32 + lane] = warp_sort32(res, lane, less);
             }
             __syncthreads();
-            if (warp == 0) {
-                for (uint32_t g = 0; g * 32 < n_keep; ++g) {
-                    const uint64_t cand = newp[g * 32 + lane];
-                    const uint64_t tail = list[a.itopk - 1];
-                    if (__ballot_sync(kFullMask, cand < tail) == 0) continue;  // nothing here can enter the list
-                    warp_list_merge(list, (int)a.itopk, cand, lane, less);
+            K4B_T(5);  // group sort
+            if (n_keep != 0) {
+                const uint32_t n_groups = (n_keep + 31) / 32;
+                for (uint32_t i = tid; i < a.itopk + n_groups * 32; i += K4B_WARPS * 32) {
+                    const bool from_list = i < a.itopk;
+                    const uint32_t own_g = from_list ? 0xFFFFFFFFu : (i - a.itopk) >> 5;
+                    const uint64_t x = from_list ? list[i] : newp[i - a.itopk];
+                    if (x == kInvalidPacked) continue;
+                    uint32_t pos = from_list ? i : ((i - a.itopk) & 31u) + lower_bound(list, a.itopk, x);
+                    for (uint32_t g = 0; g < n_groups; ++g)
+                        if (g != own_g) pos += lower_bound(newp + g * 32, 32, x);
+                    if (pos < a.itopk) list_alt[pos] = x;
                 }
-                if (lane == 0) {
-                    ctrl[2] += n_new;
-                    ctrl[0] = 0;
-                    ctrl[3] = 0;
-                }
+                uint64_t* t = list;
+                list = list_alt;
+                list_alt = t;
+            }
+            if (tid == 0) {
+                ctrl[2] += n_new;
+                ctrl[0] = 0;
+                ctrl[3] = 0;
                 n_evals += n_new;
             }
+            __syncthreads();
         }
-        if (warp == 0) {
-            __syncwarp();
-            pick_parents();
-        }
-        __syncthreads();
+        K4B_T(6);  // parallel merge into the list
+        pick_parents();
+        K4B_T(7);  // parent pick
     };
 
     // ---- seeds (warp 0) ----
@@ -570,6 +639,13 @@ __global__ void __launch_bounds__(K4B_WARPS * 32, 1) graph_search_cta_kernel(K4A
         evaluate_queue();
     }
 
+#ifdef VSB_K4B_PROFILE
+    if (tid == 0 && q == 0)
+        printf("k4b cycles: total %lld | fetch %lld wait %lld | rows %lld wait %lld | finish %lld sort %lld fold %lld pick %lld | "
+               "evals %llu parents %llu\n",
+               clock64() - prof_start_, prof_[0], prof_[1], prof_[2], prof_[3], prof_[4], prof_[5], prof_[6], prof_[7], n_evals,
+               n_parents);
+#endif
     // ---- emit (warp 0) ----
     if (warp == 0) {
         uint32_t count = 0;

@@ -943,8 +943,9 @@ vsb_status vsb_index::graph_block(const vsb::RowsView& qv, uint32_t nb, uint32_t
     }
     if (rerank) {
         // hand the best kr bf16-ranked candidates to K3 for the canonical fp32 re-rank
-        // (2k, at least k + 6, of them; bf16 ranking errors are far smaller than that margin)
-        const uint32_t kv = std::max(2 * k, k + 6);
+        // (2k for small k, k + 32 + k/4 for large k, at least k + 6; bf16 ranking errors only reorder
+        // candidates near the k-th distance and are far smaller than that margin)
+        const uint32_t kv = std::max(std::min(2 * k, k + 32 + k / 4), k + 6);
         kr = std::min<uint32_t>(round_up(kv, 32), 256);
         if (kr < k) return fail(VSB_EINVAL, "k=%u too large for the bf16-traversal re-rank (max 256)", k);
         CU(rr_packed.ensure((size_t)nb * kr * 8));

@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(os.path.dirname(_HERE), "libvsb200.so")
+# VSB200_LIB: an instrumented build of the same library (tools/ profiling runs); never a different backend
+_LIB_PATH = os.environ.get("VSB200_LIB") or os.path.join(os.path.dirname(_HERE), "libvsb200.so")
 
 VSB_OK, VSB_EINVAL, VSB_EDIM, VSB_EDUPKEY, VSB_EFULL, VSB_EOOM, VSB_ECUDA, VSB_ENCCL = range(8)
 STATUS_NAMES = ["OK", "EINVAL", "EDIM", "EDUPKEY", "EFULL", "EOOM", "ECUDA", "ENCCL"]
