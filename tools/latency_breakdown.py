@@ -32,8 +32,8 @@ def main():
     hc = torch.empty((10_000,), dtype=torch.int32).pin_memory()
     idx.search_raw(q.data_ptr(), 2560, k, hk.data_ptr(), hd.data_ptr(), hc.data_ptr(), exact=True)
     truth = hk.numpy()[:2560].copy()
-    for width in (1, 2, 4, 8):
-        for ef in (96, 128, 160, 192):
+    for width in [int(x) for x in os.environ.get("WIDTHS", "2").split(",")]:
+        for ef in [int(x) for x in os.environ.get("EFS", "128,160,192").split(",")]:
             idx.set_search_params(expansion_search=ef, search_width=width)
             found = np.empty((2560, k), np.int64)
             for c in range(10):
