@@ -53,8 +53,8 @@ def parse_args():
     ap.add_argument("--target-recall", type=float, default=0.95)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="corpus rows of the bounded CPU-baseline sample")
     ap.add_argument("--search-width", type=int, default=2)
-    ap.add_argument("--traversal", default="bf16", choices=["bf16", "native"],
-                    help="f32 storage: traverse a bf16 copy and re-rank the best candidates on the f32 rows")
+    ap.add_argument("--traversal", default="bf16", choices=["bf16", "i8", "native"],
+                    help="f32 storage: traverse a bf16 (or scaled-int8) copy and re-rank the best candidates on the f32 rows")
     ap.add_argument("--cpu-queries", type=int, default=2_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -245,10 +245,11 @@ def main():
     n_local = hi - lo
 
     # ---- corpus shard: generated and ingested chunk by chunk (host RAM stays bounded) ----
-    trav16 = a.storage == "f32" and a.traversal == "bf16"
+    trav8 = a.storage == "f32" and a.traversal == "i8"
+    trav16 = a.storage == "f32" and a.traversal in ("bf16", "i8")
     # ---- process warm-up (untimed): a 40k-row index exercises every kernel once, so CUDA's lazy module
     # loading and the first cudaMalloc's are not billed to the timed build below ----
-    warm = v.GpuIndex(a.dim, v.Metric.Cos, scalar, device=local_rank, bf16_traversal=trav16)
+    warm = v.GpuIndex(a.dim, v.Metric.Cos, scalar, device=local_rank, bf16_traversal=trav16, i8_traversal=trav8)
     warm.reserve(40_000)
     wx = ds.embedding_like(40_000, a.dim, seed=7, n_clusters=a.clusters)
     warm.add_batch(np.arange(40_000, dtype=np.uint64)[:30_000], wx[:30_000])
@@ -260,7 +261,7 @@ def main():
     warm.close()
     del warm, wx
 
-    idx = v.GpuIndex(a.dim, v.Metric.Cos, scalar, device=local_rank, bf16_traversal=trav16)
+    idx = v.GpuIndex(a.dim, v.Metric.Cos, scalar, device=local_rank, bf16_traversal=trav16, i8_traversal=trav8)
     idx.reserve(n_local)
     t_gen = 0.0
     t_add = 0.0
@@ -378,7 +379,7 @@ def main():
     idx.set_instrumented(False)
     E = st["distance_evals"] / max(st["queries"], 1)
     P = st["parent_expansions"] / max(st["queries"], 1)
-    trav_row_bytes = st["row_bytes"] // 2 if trav16 else st["row_bytes"]
+    trav_row_bytes = st["row_bytes"] // 4 if trav8 else (st["row_bytes"] // 2 if trav16 else st["row_bytes"])
     bytes_per_query = E * (trav_row_bytes + 4) + P * st["graph_degree"] * 4  # +4: the row's norm (cosine)
 
     # ---- timed region 1: inputs resident in HBM ----
@@ -470,7 +471,9 @@ def main():
         "dtype": a.storage, "data": "synthetic",
         "config": {"workload": workload_name(a), "index": "M=16 (degree 32) ef_add=128; build = exact all-pairs kNN on a 131072-row prefix (tcgen05) + "
                                                               "K7 streaming insert + one K4/K6 refinement pass",
-                   "traversal": ("bf16 copy of the f32 rows for the graph traversal, fp32 re-rank of the best "
+                   "traversal": ("scaled-int8 copy of the f32 rows for the graph traversal, fp32 re-rank of 4k candidates on "
+                                 "the f32 rows" if trav8 else
+                                 "bf16 copy of the f32 rows for the graph traversal, fp32 re-rank of the best "
                                  "candidates on the f32 rows" if trav16 else "native storage scalar"),
                    "expansion_search": ef_used, "search_width": a.search_width, "max_iterations": max_iters_used,
                    "recall_at_10": round(recall_timed, 4), "ef_sweep": sweep,

@@ -71,6 +71,11 @@ typedef struct {
  * the best candidates are then re-ranked on the f32 rows (K3), so returned distances stay the
  * canonical fp32 distances of the stored vectors.  Costs +50 % HBM for the rows. */
 #define VSB_FLAG_BF16_TRAVERSAL 1u
+/* f32 storage + cosine only (ignored otherwise): the search walks a scaled-int8 copy of the rows (per-row
+ * scale max|x|/127, a quarter of the f32 bytes, dp4a arithmetic) and re-ranks 4k candidates on the f32 rows,
+ * so returned distances are still the canonical fp32 ones.  Implies VSB_FLAG_BF16_TRAVERSAL (the bf16 copy
+ * keeps serving the build and the seed tiles); +25 % HBM for the rows on top of it. */
+#define VSB_FLAG_I8_TRAVERSAL 2u
 
 /* Runtime tunables of the graph search (all 0 = keep current). */
 typedef struct {

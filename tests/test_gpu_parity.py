@@ -450,6 +450,52 @@ def test_bf16_traversal_flag_keeps_fp32_distances():
     assert np.array_equal(gk[:, 0], np.arange(n, n + 50, dtype=np.uint64))
 
 
+def test_i8_traversal_flag_keeps_fp32_distances_and_recall():
+    # VSB_FLAG_I8_TRAVERSAL: K4 walks a scaled-int8 copy (cosine, f32 storage), K3 re-ranks 4k candidates on the
+    # f32 rows => canonical f32 distances; recall must stay with the bf16 traversal's
+    n, dim, k = 30000, 768, 10
+    x = embedding_like(n, dim, n_clusters=64)
+    q = embedding_like(400, dim, seed=4321, n_clusters=64)
+    keys = np.arange(n, dtype=np.uint64)
+    v = V()
+    recalls = {}
+    for mode in ("bf16", "i8"):
+        idx = v.GpuIndex(dim, v.Metric.Cos, v.Scalar.F32, bf16_traversal=True, i8_traversal=(mode == "i8"))
+        idx.reserve(n + 100)
+        idx.add_batch(keys[: n // 2], x[: n // 2])
+        idx.remove_batch(keys[100:200])                       # compaction at build carries the int8 copy along
+        idx.add_batch(keys[n // 2:], x[n // 2:])
+        idx.build()
+        alive = np.ones(n, np.uint8)
+        alive[100:200] = 0
+        tk, td, _ = idx.search_batch(q, k, exact=True)
+        ok, od, _, _ = O.exact_topk(x, q[:8], k, O.COS, O.F32, keys=keys, alive=alive)
+        assert np.array_equal(tk[:8], ok) and np.array_equal(td[:8].view(np.uint32), od.view(np.uint32))
+        for nq in (400, 3):
+            gk, gd, gc = idx.search_batch(q[:nq], k)
+            r = O.recall_at_k(gk, tk[:nq])
+            print(f"{mode} traversal, batch {nq}: recall@10 = {r:.4f}")
+            assert np.all(gc == k) and np.all(np.diff(gd, axis=1) >= 0) and r >= 0.95
+            d0 = O.distance_matrix(x[gk[0].astype(np.int64)], q[:1], O.COS, O.F32)[0]
+            assert np.array_equal(gd[0].view(np.uint32), d0.view(np.uint32))
+            recalls[(mode, nq)] = r
+        idx.add_batch(np.arange(n, n + 50, dtype=np.uint64), q[:50])  # streamed rows get their int8 copy too
+        idx.insert_pending()
+        gk, gd, _ = idx.search_batch(q[:50], 1)
+        assert np.array_equal(gk[:, 0], np.arange(n, n + 50, dtype=np.uint64))
+        idx.close()
+    assert recalls[("i8", 400)] >= recalls[("bf16", 400)] - 0.01
+    # the flag is ignored (bf16 / native traversal) where the scaled-int8 cosine trick does not apply
+    idx = v.GpuIndex(64, v.Metric.L2sq, v.Scalar.F32, i8_traversal=True)
+    idx.reserve(5000)
+    xs = embedding_like(5000, 64, n_clusters=8)
+    idx.add_batch(np.arange(5000, dtype=np.uint64), xs)
+    idx.build()
+    gk, _, _ = idx.search_batch(xs[:20], 1)
+    assert np.array_equal(gk[:, 0], np.arange(20, dtype=np.uint64))
+    idx.close()
+
+
 def test_streaming_insert_k7():
     # C5-shaped: build on 70 % of the data, stream the rest in (K7), delete some, recall stays high
     n, dim, k = 40000, 96, 10

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--widths", default="1,2,4")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--bf16-traversal", action="store_true")
+    ap.add_argument("--i8-traversal", action="store_true")
     ap.add_argument("--exact-only", action="store_true", help="skip the graph build and the ANN sweep")
     a = ap.parse_args()
     import torch
@@ -31,7 +32,7 @@ def main():
     import vector_store_b200 as v
     ds = import_module("vector_store_b200.host.datasets")
     scalar = {"f32": v.Scalar.F32, "bf16": v.Scalar.BF16, "f16": v.Scalar.F16}[a.storage]
-    idx = v.GpuIndex(a.dim, v.Metric.Cos, scalar, device=0, bf16_traversal=a.bf16_traversal)
+    idx = v.GpuIndex(a.dim, v.Metric.Cos, scalar, device=0, bf16_traversal=a.bf16_traversal, i8_traversal=a.i8_traversal)
     idx.reserve(a.n)
     CH = 100_000
     for c0 in range(0, a.n, CH):
@@ -91,11 +92,12 @@ def main():
             idx.set_kernel_timing(False)
             k4 = st["graph_search_ns"] / 1e6 / max(st["graph_search_launches"], 1)
             seed = st["seed_ns"] / 1e6 / max(st["seed_launches"], 1)
-            rb = st["row_bytes"] // 2 if a.bf16_traversal else st["row_bytes"]
+            rb = st["row_bytes"] // 4 if a.i8_traversal else (st["row_bytes"] // 2 if a.bf16_traversal else st["row_bytes"])
+            exact_ms = st["exact_ns"] / 1e6 / max(st["exact_launches"], 1)
             bpq = E * (rb + 4) + P * st["graph_degree"] * 4
             gbs = B * bpq / (k4 * 1e-3) / 1e9
             print(json.dumps({"width": w, "ef": ef, "recall": round(float(rec), 4), "qps": round(B / ms * 1e3),
-                              "E": round(E, 1), "P": round(P, 1), "k4_ms": round(k4, 3), "seed_ms": round(seed, 3),
+                              "E": round(E, 1), "P": round(P, 1), "k4_ms": round(k4, 3), "seed_ms": round(seed, 3), "rerank_ms": round(exact_ms, 3),
                               "GBps": round(gbs), "frac": round(gbs / peak, 3)}), flush=True)
 
 

@@ -85,6 +85,48 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const float* __restri
     }
 }
 
+// Scaled int8 rows for the cosine traversal copy (VSB_FLAG_I8_TRAVERSAL): x_j ~ s * q_j with the per-row scale
+// s = max|x_j| / 127 and q_j = rint(x_j / s) in [-127, 127].  The row's "norm" is stored in units of s
+// (|x| / s), so that K4's int8 cosine  1 - dot_i8 / (|q|/s_q * |x|/s_x)  equals  1 - <q,x> / (|q||x|)  up to
+// the quantisation error (relative 1/254 of the largest component per element) — no kernel change needed.
+__global__ void __launch_bounds__(256) convert_rows_i8s_kernel(const float* __restrict__ in, uint32_t n_rows, uint32_t dim,
+                                                               uint32_t in_stride, uint8_t* __restrict__ out,
+                                                               uint32_t row_bytes, float* __restrict__ sq,
+                                                               float* __restrict__ nrm) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const float* src = in + (size_t)row * in_stride;
+    float mx = 0.0f, ss = 0.0f;
+    for (uint32_t j = lane; j < dim; j += 32) {
+        const float v = src[j];
+        mx = fmaxf(mx, fabsf(v));
+        ss = __fmaf_rn(v, v, ss);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, o));
+    ss = butterfly_sum(ss);
+    const float scale = mx > 0.0f ? mx / 127.0f : 1.0f;
+    const float inv = 1.0f / scale;
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * row_bytes);
+    const int n_chunks = row_bytes / 16;
+    for (int c = lane; c < n_chunks; c += 32) {
+        uint32_t w[4] = {0, 0, 0, 0};
+        const uint32_t base = (uint32_t)c * 16;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const float v = (base + e < dim) ? src[base + e] : 0.0f;
+            int q = __float2int_rn(v * inv);
+            q = max(-127, min(127, q));
+            w[e >> 2] |= ((uint32_t)(q & 0xFF)) << (8 * (e & 3));
+        }
+        dst[c] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (lane == 0) {
+        sq[row] = ss;
+        nrm[row] = __fsqrt_rn(ss) * inv;
+    }
+}
+
 // gathers rows (and their norms) by slot into a contiguous block — used for the seed layer
 __global__ void gather_rows_kernel(const uint8_t* __restrict__ rows, uint32_t row_bytes,
                                    const float* __restrict__ sq, const float* __restrict__ nrm,
@@ -121,6 +163,15 @@ void launch_convert_rows(int storage, const float* in, uint32_t n_rows, uint32_t
     const int warps = 8;
     dim3 grid((n_rows + warps - 1) / warps), block(warps * 32);
     VSB_DISPATCH_ST(storage, (convert_rows_kernel<ST><<<grid, block, 0, stream>>>(in, n_rows, dim, out, row_bytes, sq, nrm)));
+    g_kernel_launches += 1;
+}
+
+void launch_convert_rows_i8s(const float* in, uint32_t n_rows, uint32_t dim, uint32_t in_stride, uint8_t* out,
+                             uint32_t row_bytes, float* sq, float* nrm, cudaStream_t stream) {
+    if (n_rows == 0) return;
+    const int warps = 8;
+    convert_rows_i8s_kernel<<<(n_rows + warps - 1) / warps, warps * 32, 0, stream>>>(in, n_rows, dim, in_stride, out,
+                                                                                  row_bytes, sq, nrm);
     g_kernel_launches += 1;
 }
 

@@ -1,4 +1,6 @@
 // graph_search.cu — host launcher of K4 (kernel in graph_search.cuh, instantiated per storage scalar).
+#include <cstdlib>
+
 #include "graph_search.cuh"
 
 namespace vsb {
@@ -56,7 +58,11 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
     // Visited hash: 16 KB per warp (4096 slots) = 3 CTAs x 4 query warps per SM, the same residency the
     // register budget allows; it is reset to "what is still in the list" when 3/4 full (forgotten nodes
     // cost a re-evaluation, never a duplicate).
-    const uint32_t bits = 12;
+    static const uint32_t bits_env = [] {
+        const char* e = getenv("VSB_K4_HASH_BITS");
+        return e ? (uint32_t)atoi(e) : 0u;
+    }();
+    const uint32_t bits = bits_env >= 8 && bits_env <= 14 ? bits_env : 12;
     a.hash_bits = bits;
     const uint32_t deg_pad = ((p.degree + 31) / 32) * 32;
     a.queue_cap = a.search_width * deg_pad < 32 ? 32 : a.search_width * deg_pad;
@@ -82,7 +88,7 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
         return;
     }
     dim3 grid((p.q.n + K4_WARPS - 1) / K4_WARPS);
-    const size_t smem = (size_t)K4_WARPS * ((size_t)a.itopk * 8 + ((size_t)4 << bits) + (size_t)a.queue_cap * 8);
+    const size_t smem = (size_t)K4_WARPS * ((size_t)a.itopk * 8 + ((size_t)2 << bits) + (size_t)a.queue_cap * 8);
     switch (p.storage) {
         case VSB_ST_F32: launch_k4_f32(a, cpl, grid, smem, stream); break;
         case VSB_ST_F16: launch_k4_f16(a, cpl, grid, smem, stream); break;

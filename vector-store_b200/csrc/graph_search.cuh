@@ -60,6 +60,26 @@ __device__ __forceinline__ bool hash_insert(uint32_t* tab, uint32_t mask, uint32
     return false;  // saturated neighbourhood: treat as visited
 }
 
+// Visited filter of the warp-per-query kernel: the same open-addressing table with 16-bit TAGS instead of the
+// 32-bit slot ids.  Half the shared memory per query (8 KB for 4096 entries) is what lets a fourth / fifth CTA
+// fit on the SM — the kernel is bound by rows in flight per SM.  Two different slots that share a probe position
+// AND a tag read as "visited": ~2 probes x 2^-16 per insert, i.e. one skipped candidate in ~12 queries of 2600
+// evaluations each, far below the recall resolution (checked by the ANN recall tests).
+constexpr uint16_t kTagEmpty = 0xFFFFu;
+__device__ __forceinline__ bool hash_insert16(uint16_t* tab, uint32_t mask, uint32_t bits, uint32_t slot) {
+    uint32_t h = (slot * 0x9E3779B1u) >> (32 - bits);
+    uint32_t t = (slot * 0x85EBCA6Bu) >> 16;
+    const unsigned short tag = (unsigned short)(t == kTagEmpty ? 0xFFFEu : t);
+#pragma unroll 1
+    for (int probe = 0; probe < 64; ++probe) {
+        const unsigned short old = atomicCAS(reinterpret_cast<unsigned short*>(&tab[h]), (unsigned short)kTagEmpty, tag);
+        if (old == kTagEmpty) return true;
+        if (old == tag) return false;
+        h = (h + 1) & mask;
+    }
+    return false;  // saturated neighbourhood: treat as visited
+}
+
 // ---- shared evaluation helpers (K4 and K4b) -----------------------------------------------------
 // A "group" is U stored rows in flight in registers.  Loads are unpredicated when every lane owns a
 // full set of chunks (`full`), and indices past the end of the queue are clamped to its last entry
@@ -188,8 +208,13 @@ __device__ __forceinline__ void evaluate_entries(const uint8_t* __restrict__ x_r
 
 constexpr int K4_MAX_WIDTH = 4;  // parents expanded per iteration (search_width)
 
+// resident CTAs per SM the register budget is sized for: short int8 rows (the scaled-int8 traversal copy) need
+// few load registers, and the kernel is bound by the number of rows in flight per SM, not by bytes
 template <int ST, int CPL>
-__global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a) {
+constexpr int k4_min_blocks() { return (ST == VSB_ST_I8 && CPL <= 2) ? 4 : 3; }
+
+template <int ST, int CPL>
+__global__ void __launch_bounds__(K4_WARPS * 32, k4_min_blocks<ST, CPL>()) graph_search_kernel(K4Args a) {
     constexpr int E = Storage<ST>::ELEMS;
     constexpr bool kFloat = Storage<ST>::kFloat;
     constexpr int U = CPL <= 3 ? 4 : (CPL <= 6 ? 2 : 1);  // vectors per load group
@@ -202,10 +227,10 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
 
     const uint32_t hsize = 1u << a.hash_bits, hmask = hsize - 1;
     const uint32_t qcap = a.queue_cap;
-    const size_t per_warp = (size_t)a.itopk * 8 + (size_t)hsize * 4 + (size_t)qcap * 8;
+    const size_t per_warp = (size_t)a.itopk * 8 + (size_t)hsize * 2 + (size_t)qcap * 8;
     uint64_t* list = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warp * per_warp);
-    uint32_t* hash = reinterpret_cast<uint32_t*>(list + a.itopk);
-    uint32_t* newq = hash + hsize;                           // [qcap] un-visited neighbour slots of this iteration
+    uint16_t* hash = reinterpret_cast<uint16_t*>(list + a.itopk);  // [hsize] 16-bit tags
+    uint32_t* newq = reinterpret_cast<uint32_t*>(hash + hsize);   // [qcap] un-visited neighbour slots of this iteration
     float* newd = reinterpret_cast<float*>(newq + qcap);     // [qcap] their raw sums
     const LessBySlot less;
     const bool is_l2 = a.metric == VSB_METRIC_L2SQ;
@@ -214,7 +239,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
     const bool full = n_chunks == CPL * 32;
 
     for (uint32_t i = lane; i < a.itopk; i += 32) list[i] = kInvalidPacked;
-    for (uint32_t i = lane; i < hsize; i += 32) hash[i] = kHashEmpty;
+    for (uint32_t i = lane; i < hsize; i += 32) hash[i] = kTagEmpty;
 
     // ---- query into registers ----
     const uint4* qrow = reinterpret_cast<const uint4*>(a.q_rows + (size_t)q * a.q_row_bytes);
@@ -239,7 +264,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
     // visited filter + compaction of one candidate per lane into the iteration queue
     auto enqueue = [&](uint32_t nb) {
         bool is_new = false;
-        if (nb != kInvalidSlot) is_new = hash_insert(hash, hmask, a.hash_bits, nb);
+        if (nb != kInvalidSlot) is_new = hash_insert16(hash, hmask, a.hash_bits, nb);
         const uint32_t m = __ballot_sync(kFullMask, is_new);
         if (is_new) newq[n_new + __popc(m & ((1u << lane) - 1))] = nb;
         n_new += __popc(m);
@@ -290,12 +315,12 @@ __global__ void __launch_bounds__(K4_WARPS * 32, 3) graph_search_kernel(K4Args a
     for (uint32_t it = 0; it < a.max_iters; ++it) {
         // visited hash getting crowded: forget everything except what is still in the list
         if (n_hashed > (hsize >> 2) * 3) {
-            for (uint32_t i = lane; i < hsize; i += 32) hash[i] = kHashEmpty;
+            for (uint32_t i = lane; i < hsize; i += 32) hash[i] = kTagEmpty;
             __syncwarp();
             n_hashed = 0;
             for (uint32_t b = 0; b < a.itopk; b += 32) {
                 const uint64_t e = list[b + lane];
-                if (e != kInvalidPacked) hash_insert(hash, hmask, a.hash_bits, packed_lo(e) & ~kExpandedBit);
+                if (e != kInvalidPacked) hash_insert16(hash, hmask, a.hash_bits, packed_lo(e) & ~kExpandedBit);
                 n_hashed += __popc(__ballot_sync(kFullMask, e != kInvalidPacked));
             }
             __syncwarp();

@@ -133,6 +133,11 @@ struct vsb_index {
     DevBuf rows16, sq16, nrm16;   // VSB_FLAG_BF16_TRAVERSAL: bf16 copy of the rows for K4
     bool trav16 = false;
     uint32_t row_bytes16 = 0;
+    // VSB_FLAG_I8_TRAVERSAL (f32 storage, cosine): K4 walks a scaled-int8 copy (a quarter of the f32 bytes, dp4a),
+    // K3 re-ranks rr_mult8 * k candidates on the f32 rows.  The bf16 copy stays for the build and the seed tiles.
+    DevBuf rows8, sq8, nrm8, q8_rows, q8_sq, q8_nrm;
+    bool trav8 = false;
+    uint32_t row_bytes8 = 0, rr_mult8 = 4;
     DevBuf rr_packed;             // K4 -> K3 hand-over of the traversal shadow path
     DevBuf seed_rows, seed_sq, seed_nrm, seed_slots;
     DevBuf seed16_rows, seed16_sq, seed16_nrm;   // bf16 shadow of the seed block (f32 storage only)
@@ -186,7 +191,8 @@ struct vsb_index {
         const DevBuf* all[] = {&rows, &sq, &nrm, &keys, &deny, &graph, &rows16, &sq16, &nrm16, &rr_packed, &seed_rows, &seed_sq, &seed_nrm, &seed_slots,
                                &seed16_rows, &seed16_sq, &seed16_nrm, &q16_rows, &q16_sq, &q16_nrm,
                                &q_in, &q_rows, &q_sq, &q_nrm, &part, &seed_part, &tmp_keys, &tmp_dists, &counters,
-                               &add_in, &allow, &cert_state, &fb_map, &fb_rows, &fb_sq, &fb_nrm};
+                               &add_in, &allow, &cert_state, &fb_map, &fb_rows, &fb_sq, &fb_nrm, &rows8, &sq8, &nrm8, &q8_rows,
+                               &q8_sq, &q8_nrm};
         size_t s = 0;
         for (auto* b : all) s += b->bytes;
         return s;
@@ -258,12 +264,17 @@ vsb_status vsb_index::reserve(uint64_t cap) {
     if (cap >= (1ull << 28)) return fail(VSB_EINVAL, "capacity %llu exceeds the 2^28 rows one shard holds", (unsigned long long)cap);
     CU(cudaSetDevice(device));
     const uint64_t words = (cap + 31) / 32;
-    DevBuf n_rows, n_sq, n_nrm, n_keys, n_deny, n_rows16, n_sq16, n_nrm16;
+    DevBuf n_rows, n_sq, n_nrm, n_keys, n_deny, n_rows16, n_sq16, n_nrm16, n_rows8, n_sq8, n_nrm8;
     auto alloc = [&](DevBuf& b, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(&b.p, bytes ? bytes : 16);
         if (e == cudaSuccess) b.bytes = bytes ? bytes : 16; else b.p = nullptr;
         return e;
     };
+    if (trav8) {
+        CU(alloc(n_rows8, cap * row_bytes8));
+        CU(alloc(n_sq8, cap * 4));
+        CU(alloc(n_nrm8, cap * 4));
+    }
     CU(alloc(n_rows, cap * row_bytes));
     CU(alloc(n_sq, cap * 4));
     CU(alloc(n_nrm, cap * 4));
@@ -287,8 +298,18 @@ vsb_status vsb_index::reserve(uint64_t cap) {
             CU(cudaMemcpyAsync(n_sq16.p, sq16.p, (size_t)n_slots * 4, cudaMemcpyDeviceToDevice, stream));
             CU(cudaMemcpyAsync(n_nrm16.p, nrm16.p, (size_t)n_slots * 4, cudaMemcpyDeviceToDevice, stream));
         }
+        if (trav8) {
+            CU(cudaMemcpyAsync(n_rows8.p, rows8.p, (size_t)n_slots * row_bytes8, cudaMemcpyDeviceToDevice, stream));
+            CU(cudaMemcpyAsync(n_sq8.p, sq8.p, (size_t)n_slots * 4, cudaMemcpyDeviceToDevice, stream));
+            CU(cudaMemcpyAsync(n_nrm8.p, nrm8.p, (size_t)n_slots * 4, cudaMemcpyDeviceToDevice, stream));
+        }
     }
     CU(cudaStreamSynchronize(stream));
+    if (trav8) {
+        std::swap(rows8, n_rows8);
+        std::swap(sq8, n_sq8);
+        std::swap(nrm8, n_nrm8);
+    }
     std::swap(rows, n_rows);
     std::swap(sq, n_sq);
     std::swap(nrm, n_nrm);
@@ -336,6 +357,11 @@ vsb_status vsb_index::add(const uint64_t* k, const float* r, uint64_t n) {
             vsb::launch_convert_rows(VSB_BF16, add_in.as<float>(), (uint32_t)nb, dim,
                                      rows16.as<uint8_t>() + (size_t)s0 * row_bytes16, row_bytes16, sq16.as<float>() + s0,
                                      nrm16.as<float>() + s0, stream);
+            CU(cudaGetLastError());
+        }
+        if (trav8) {
+            vsb::launch_convert_rows_i8s(add_in.as<float>(), (uint32_t)nb, dim, dim, rows8.as<uint8_t>() + (size_t)s0 * row_bytes8,
+                                         row_bytes8, sq8.as<float>() + s0, nrm8.as<float>() + s0, stream);
             CU(cudaGetLastError());
         }
         CU(cudaMemcpyAsync(keys.as<uint64_t>() + s0, k + b, nb * 8, cudaMemcpyHostToDevice, stream));
@@ -546,7 +572,7 @@ vsb_status vsb_index::compact() {
         if (!(h_deny[i >> 5] >> (i & 31) & 1u)) live_slots.push_back(i);
     const uint32_t m = (uint32_t)live_slots.size();
     if (m != n_slots) {
-        DevBuf d_slots, n_rows, n_sq, n_nrm, n_keys, n_rows16, n_sq16, n_nrm16;
+        DevBuf d_slots, n_rows, n_sq, n_nrm, n_keys, n_rows16, n_sq16, n_nrm16, n_rows8, n_sq8, n_nrm8;
         CU(d_slots.ensure(std::max<size_t>((size_t)m * 4, 16)));
         CU(cudaMemcpyAsync(d_slots.p, live_slots.data(), (size_t)m * 4, cudaMemcpyHostToDevice, stream));
         auto alloc = [&](DevBuf& b, size_t bytes) -> cudaError_t {
@@ -569,6 +595,13 @@ vsb_status vsb_index::compact() {
                                     d_slots.as<uint32_t>(), m, n_rows16.as<uint8_t>(), n_sq16.as<float>(),
                                     n_nrm16.as<float>(), stream);
         }
+        if (trav8) {
+            CU(alloc(n_rows8, (size_t)capacity * row_bytes8));
+            CU(alloc(n_sq8, (size_t)capacity * 4));
+            CU(alloc(n_nrm8, (size_t)capacity * 4));
+            vsb::launch_gather_rows(rows8.as<uint8_t>(), row_bytes8, sq8.as<float>(), nrm8.as<float>(), d_slots.as<uint32_t>(),
+                                    m, n_rows8.as<uint8_t>(), n_sq8.as<float>(), n_nrm8.as<float>(), stream);
+        }
         CU(cudaGetLastError());
         std::vector<uint64_t> h_keys(m);
         CU(cudaMemcpyAsync(h_keys.data(), n_keys.p, (size_t)m * 8, cudaMemcpyDeviceToHost, stream));
@@ -582,6 +615,11 @@ vsb_status vsb_index::compact() {
             std::swap(rows16, n_rows16);
             std::swap(sq16, n_sq16);
             std::swap(nrm16, n_nrm16);
+        }
+        if (trav8) {
+            std::swap(rows8, n_rows8);
+            std::swap(sq8, n_sq8);
+            std::swap(nrm8, n_nrm8);
         }
         std::fill(h_deny.begin(), h_deny.end(), 0u);
         key2slot.clear();
@@ -918,6 +956,25 @@ vsb_status vsb_index::graph_block(const vsb::RowsView& qv, uint32_t nb, uint32_t
         gp.x.nrm = nrm16.as<float>();
         gp.x.row_bytes = row_bytes16;
     }
+    const bool use8 = trav8 && rerank;  // searches only: the build keeps the bf16 traversal
+    if (use8) {
+        CU(q8_rows.ensure((size_t)nb * row_bytes8));
+        CU(q8_sq.ensure((size_t)nb * 4));
+        CU(q8_nrm.ensure((size_t)nb * 4));
+        vsb::launch_convert_rows_i8s(reinterpret_cast<const float*>(qv.rows), nb, dim, row_bytes / 4, q8_rows.as<uint8_t>(),
+                                     row_bytes8, q8_sq.as<float>(), q8_nrm.as<float>(), s);
+        CU(cudaGetLastError());
+        gp.storage = VSB_I8;
+        gp.q.rows = q8_rows.as<uint8_t>();
+        gp.q.sq = q8_sq.as<float>();
+        gp.q.nrm = q8_nrm.as<float>();
+        gp.q.row_bytes = row_bytes8;
+        gp.q.n = nb;
+        gp.x.rows = rows8.as<uint8_t>();
+        gp.x.sq = sq8.as<float>();
+        gp.x.nrm = nrm8.as<float>();
+        gp.x.row_bytes = row_bytes8;
+    }
     gp.graph = graph.as<uint32_t>();
     gp.graph_stride = graph_stride;
     gp.degree = degree;
@@ -945,7 +1002,9 @@ vsb_status vsb_index::graph_block(const vsb::RowsView& qv, uint32_t nb, uint32_t
         // hand the best kr bf16-ranked candidates to K3 for the canonical fp32 re-rank
         // (2k for small k, k + 32 + k/4 for large k, at least k + 6; bf16 ranking errors only reorder
         // candidates near the k-th distance and are far smaller than that margin)
-        const uint32_t kv = std::max(std::min(2 * k, k + 32 + k / 4), k + 6);
+        // int8 traversal ranks more coarsely: rr_mult8 * k candidates go to the re-rank
+        const uint32_t kv = use8 ? std::min<uint32_t>(std::max(rr_mult8 * k, k + 16), 256)
+                                 : std::max(std::min(2 * k, k + 32 + k / 4), k + 6);
         kr = std::min<uint32_t>(round_up(kv, 32), 256);
         if (kr < k) return fail(VSB_EINVAL, "k=%u too large for the bf16-traversal re-rank (max 256)", k);
         CU(rr_packed.ensure((size_t)nb * kr * 8));
@@ -1187,6 +1246,10 @@ vsb_status vsb_create(const vsb_options* o, vsb_index** out) {
     ix->itopk = std::min<uint32_t>(round_up(ef_search, 32), 1024);
     ix->trav16 = (o->flags & VSB_FLAG_BF16_TRAVERSAL) != 0 && o->storage == VSB_F32;
     ix->row_bytes16 = storage_row_bytes(VSB_BF16, o->dimensions);
+    ix->trav8 = (o->flags & VSB_FLAG_I8_TRAVERSAL) != 0 && o->storage == VSB_F32 && o->metric == VSB_COS;
+    if (ix->trav8) ix->trav16 = true;  // the bf16 copy feeds the build and the seed tiles
+    ix->row_bytes8 = storage_row_bytes(VSB_I8, o->dimensions);
+    if (const char* e = getenv("VSB_I8_RERANK_MULT")) ix->rr_mult8 = std::max<uint32_t>(2, (uint32_t)strtoul(e, nullptr, 10));
     if (const char* e = getenv("VSB_DISABLE_TC")) ix->tc_enabled = !(e[0] == '1');
     if (const char* e = getenv("VSB_DISABLE_CERT")) ix->cert_enabled = !(e[0] == '1');
     if (const char* e = getenv("VSB_CERT_KP")) ix->cert_kp = (uint32_t)strtoul(e, nullptr, 10);
@@ -1530,6 +1593,10 @@ extern "C" vsb_status vsb_load(const char* path, int32_t device, vsb_index** out
     if (ix->trav16 && n) {  // the bf16 traversal copy is derived data: regenerate instead of storing it
         vsb::launch_convert_rows(VSB_BF16, ix->rows.as<float>(), (uint32_t)n, ix->row_bytes / 4, ix->rows16.as<uint8_t>(),
                                  ix->row_bytes16, ix->sq16.as<float>(), ix->nrm16.as<float>(), ix->stream);
+    }
+    if (ix->trav8 && n) {
+        vsb::launch_convert_rows_i8s(ix->rows.as<float>(), (uint32_t)n, ix->dim, ix->row_bytes / 4, ix->rows8.as<uint8_t>(),
+                                     ix->row_bytes8, ix->sq8.as<float>(), ix->nrm8.as<float>(), ix->stream);
     }
     if (ix->n_graphed && ix->sample_seeds(ix->n_graphed) != VSB_OK) {
         vsb_destroy(ix);

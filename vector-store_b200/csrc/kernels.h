@@ -22,6 +22,9 @@ struct RowsView {
 // K0 ------------------------------------------------------------------------------------------
 void launch_convert_rows(int storage, const float* in, uint32_t n_rows, uint32_t dim, uint8_t* out,
                          uint32_t row_bytes, float* sq, float* nrm, cudaStream_t stream);
+// scaled int8 copy for the cosine traversal (per-row scale max|x|/127; nrm = |x| in units of the scale)
+void launch_convert_rows_i8s(const float* in, uint32_t n_rows, uint32_t dim, uint32_t in_stride, uint8_t* out,
+                             uint32_t row_bytes, float* sq, float* nrm, cudaStream_t stream);
 void launch_gather_rows(const uint8_t* rows, uint32_t row_bytes, const float* sq, const float* nrm,
                         const uint32_t* slots, uint32_t n, uint8_t* out_rows, float* out_sq, float* out_nrm,
                         cudaStream_t stream);

@@ -38,10 +38,11 @@ def _ptr(a):
 class GpuIndex:
     def __init__(self, dimensions: int, metric: Metric = Metric.Cos, storage: Scalar = Scalar.F32,
                  connectivity: int = 0, expansion_add: int = 0, expansion_search: int = 0, device: int = -1,
-                 seed: int = 0, bf16_traversal: bool = False):
+                 seed: int = 0, bf16_traversal: bool = False, i8_traversal: bool = False):
         self._lib = lib()
+        flags = (1 if bf16_traversal else 0) | (2 if i8_traversal else 0)  # VSB_FLAG_BF16_TRAVERSAL | VSB_FLAG_I8_TRAVERSAL
         opt = VsbOptions(dimensions, int(metric), int(storage), connectivity, expansion_add, expansion_search,
-                         device, 1 if bf16_traversal else 0, seed)
+                         device, flags, seed)
         h = C.c_void_p()
         check(self._lib.vsb_create(C.byref(opt), C.byref(h)))
         self._h = h
