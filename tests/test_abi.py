@@ -78,3 +78,29 @@ def test_header_compiles_as_c_and_links(tmp_path):
         assert "scenario passed" in r.stdout
     else:
         assert r.returncode == 77, (r.returncode, r.stdout, r.stderr)  # loud failure, no CPU fallback
+
+
+def test_struct_layouts_match_the_ctypes_mirror(tmp_path):
+    """sizeof() of every struct in include/vsb200.h (compiled as C) equals the ctypes mirror's, and vsb_stats
+    lists the same fields in the same order — the binding cannot drift from the header unnoticed."""
+    import ctypes
+    import re
+    import subprocess
+    from importlib import import_module
+    native = import_module("vector_store_b200.host.native")
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "vsb200.h"\nint main(void){printf("%zu %zu %zu\\n", '
+                   'sizeof(vsb_options), sizeof(vsb_search_params), sizeof(vsb_stats));return 0;}\n')
+    exe = str(tmp_path / "sizes")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe], check=True)
+    got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(native.VsbOptions), ctypes.sizeof(native.VsbSearchParams), ctypes.sizeof(native.VsbStats)]
+    assert got == want, (got, want)
+    header = open(os.path.join(ROOT, "include", "vsb200.h")).read()
+    body = header[:header.index("} vsb_stats;")]
+    body = body[body.rindex("typedef struct"):]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in re.findall(r"uint64_t\s+([^;]+);", body):
+        names += [n.strip() for n in decl.split(",")]
+    assert names == [n for n, _ in native.VsbStats._fields_], (names, [n for n, _ in native.VsbStats._fields_])
