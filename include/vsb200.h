@@ -109,6 +109,9 @@ typedef struct {
      * SIMT tiles) was PROVEN to contain the canonical top-k; queries the first stage could not certify; and
      * queries that went all the way to the canonical full scan (near-ties below fp32 summation noise) */
     uint64_t exact_certified, exact_fallback, exact_scanned;
+    /* entry points added because a graph component held no seed of the regular sample (every live graph node
+     * is reachable from the seed set after a build) */
+    uint64_t extra_seeds;
 } vsb_stats;
 
 /* usearch.rs:172  usearch::Index::new(&options) */

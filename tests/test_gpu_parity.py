@@ -773,3 +773,26 @@ def test_golden_fixture_file_through_the_c_abi():
             kk, dd, cc = idx.search_batch(q[None, :], c["k"], exact=exact)
             check_case(c, kk[0][:cc[0]], dd[0][:cc[0]], O.HAMMING if s == O.B1 else m)
         idx.close()
+
+
+def test_every_cluster_is_reachable_from_the_entry_points():
+    # well separated clusters give a kNN graph of disconnected components; a component without a seed of the regular
+    # sample used to be invisible to the search (recall 0 for its queries).  After a build every live node must be
+    # reachable: extra seeds are promoted, one per lost component.
+    rng = np.random.default_rng(12)
+    dim, per, n_clusters, k = 64, 120, 400, 10              # 48 000 rows, ~1 750 seeds: many clusters get no seed
+    centers = 20.0 * rng.standard_normal((n_clusters, dim)).astype(np.float32)
+    x = (centers[:, None, :] + rng.standard_normal((n_clusters, per, dim)).astype(np.float32)).reshape(-1, dim)
+    perm = rng.permutation(len(x))
+    x = np.ascontiguousarray(x[perm])
+    q = (centers + rng.standard_normal((n_clusters, dim)).astype(np.float32))   # one query per cluster
+    keys = np.arange(len(x), dtype=np.uint64)
+    idx = make_index(x, keys, O.L2SQ, O.F32)
+    idx.build()
+    st = idx.stats()
+    print(f"seed rows {st['n_seed_rows']}, extra seeds {st['extra_seeds']}")
+    tk, _, _ = idx.search_batch(q, k, exact=True)
+    gk, _, gc = idx.search_batch(q, k)
+    per_query = np.array([len(np.intersect1d(gk[i], tk[i])) for i in range(len(q))]) / k
+    assert st["extra_seeds"] > 0
+    assert per_query.min() >= 0.5 and per_query.mean() >= 0.95, (per_query.min(), per_query.mean())

@@ -260,4 +260,59 @@ void launch_stream_link(const uint64_t* cand, uint32_t n_new, uint32_t cand_stri
     stream_link_kernel<<<(n_new + 3) / 4, 128, 0, stream>>>(cand, n_new, cand_stride, first_slot, R, graph, graph_stride);
     g_kernel_launches += 1;
 }
+// ---- reachability of the graph from the entry-point sample -----------------------------------------------------
+// A kNN-derived graph over well separated clusters can fall apart into components; the beam search only ever sees
+// the components that hold a seed.  After every (re)sampling of the seeds the host runs this frontier expansion to
+// a fixed point and promotes one node of each unreached component to an extra seed (index.cu::sample_seeds).
+// state: 0 = unreached, 1 = reached / to expand, 2 = expanded.
+__global__ void reach_mark_kernel(uint8_t* state, const uint32_t* seeds, uint32_t n_seeds) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_seeds) state[seeds[i]] = 1;
+}
+
+__global__ void __launch_bounds__(256) reach_step_kernel(const uint32_t* __restrict__ graph, uint32_t n, uint32_t stride,
+                                                         uint32_t degree, uint8_t* state, uint32_t* changed) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (u >= n || state[u] != 1) return;
+    bool any = false;
+    for (uint32_t r = lane; r < degree; r += 32) {
+        const uint32_t v = graph[(size_t)u * stride + r];
+        if (v < n && state[v] == 0) {
+            state[v] = 1;  // benign race: every writer stores the same value
+            any = true;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) state[u] = 2;
+    if (__ballot_sync(kFullMask, any) != 0 && lane == 0) *changed = 1;
+}
+
+__global__ void first_unreached_kernel(const uint8_t* __restrict__ state, const uint32_t* __restrict__ deny, uint32_t n,
+                                       uint32_t* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || state[i] != 0) return;
+    if (deny != nullptr && bit_test(deny, i)) return;
+    atomicMin(out, i);
+}
+
+void launch_reach_mark(uint8_t* state, const uint32_t* seeds, uint32_t n_seeds, cudaStream_t stream) {
+    if (n_seeds == 0) return;
+    reach_mark_kernel<<<(n_seeds + 255) / 256, 256, 0, stream>>>(state, seeds, n_seeds);
+    g_kernel_launches += 1;
+}
+
+void launch_reach_step(const uint32_t* graph, uint32_t n, uint32_t stride, uint32_t degree, uint8_t* state,
+                       uint32_t* changed, cudaStream_t stream) {
+    if (n == 0) return;
+    reach_step_kernel<<<(n + 7) / 8, 256, 0, stream>>>(graph, n, stride, degree, state, changed);
+    g_kernel_launches += 1;
+}
+
+void launch_first_unreached(const uint8_t* state, const uint32_t* deny, uint32_t n, uint32_t* out, cudaStream_t stream) {
+    if (n == 0) return;
+    first_unreached_kernel<<<(n + 255) / 256, 256, 0, stream>>>(state, deny, n, out);
+    g_kernel_launches += 1;
+}
+
 }  // namespace vsb

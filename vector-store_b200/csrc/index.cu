@@ -136,6 +136,10 @@ struct vsb_index {
     // VSB_FLAG_I8_TRAVERSAL (f32 storage, cosine): K4 walks a scaled-int8 copy (a quarter of the f32 bytes, dp4a),
     // K3 re-ranks rr_mult8 * k candidates on the f32 rows.  The bf16 copy stays for the build and the seed tiles.
     DevBuf rows8, sq8, nrm8, q8_rows, q8_sq, q8_nrm;
+    DevBuf reach_state;             // sample_seeds: reachability of the graph from the seed set
+    bool reach_fix = true;          // VSB_DISABLE_REACH_FIX=1 turns the extra seeds off
+    uint32_t reach_budget = 1024;   // at most this many extra seeds (one per unreached component)
+    uint32_t n_extra_seeds = 0;
     bool trav8 = false;
     uint32_t row_bytes8 = 0, rr_mult8 = 4;
     DevBuf rr_packed;             // K4 -> K3 hand-over of the traversal shadow path
@@ -737,6 +741,7 @@ vsb_status vsb_index::build() {
         }
         if (refine_passes > 0) {
             for (uint32_t pass = 0; pass < refine_passes; ++pass) ST(refine_graph());
+            ST(sample_seeds(n_slots));  // reachability of the FINAL graph from the entry points
             if (btime) {
                 cudaEventRecord(ev[1], stream);
                 cudaEventSynchronize(ev[1]);
@@ -839,6 +844,47 @@ vsb_status vsb_index::sample_seeds(uint32_t n) {
         }
     }
     S = (uint32_t)h_seeds.size();
+    // every live graph node must be reachable from the seed set: expand the frontier from the sample to a fixed
+    // point, then promote the first unreached live node to an extra seed and continue, once per lost component
+    uint32_t extra_seeds = 0;
+    if (n_graphed >= n && n > 0 && S > 0 && reach_fix) {
+        CU(reach_state.ensure((size_t)n + 16));
+        uint8_t* st = reach_state.as<uint8_t>();
+        uint32_t* flag = reinterpret_cast<uint32_t*>(st + (((size_t)n + 7) / 8) * 8);  // [0] changed, [1] first unreached
+        CU(seed_slots.ensure((size_t)(S + reach_budget) * 4));
+        CU(cudaMemsetAsync(st, 0, n, stream));
+        CU(cudaMemcpyAsync(seed_slots.p, h_seeds.data(), (size_t)S * 4, cudaMemcpyHostToDevice, stream));
+        vsb::launch_reach_mark(st, seed_slots.as<uint32_t>(), S, stream);
+        const uint32_t* deny_bm = any_tombstone ? deny.as<uint32_t>() : nullptr;
+        auto expand = [&]() -> vsb_status {
+            for (int round = 0; round < 4096; ++round) {
+                CU(cudaMemsetAsync(flag, 0, 4, stream));
+                for (int i = 0; i < 4; ++i)
+                    vsb::launch_reach_step(graph.as<uint32_t>(), n, graph_stride, degree, st, flag, stream);
+                uint32_t changed = 0;
+                CU(cudaMemcpyAsync(&changed, flag, 4, cudaMemcpyDeviceToHost, stream));
+                CU(cudaStreamSynchronize(stream));
+                if (!changed) break;
+            }
+            return VSB_OK;
+        };
+        ST(expand());
+        while (extra_seeds < reach_budget) {
+            CU(cudaMemsetAsync(flag + 1, 0xFF, 4, stream));
+            vsb::launch_first_unreached(st, deny_bm, n, flag + 1, stream);
+            uint32_t first = 0xFFFFFFFFu;
+            CU(cudaMemcpyAsync(&first, flag + 1, 4, cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            if (first == 0xFFFFFFFFu) break;
+            h_seeds.push_back(first);
+            ++extra_seeds;
+            CU(cudaMemsetAsync(st + first, 1, 1, stream));
+            ST(expand());
+        }
+        CU(cudaGetLastError());
+        S = (uint32_t)h_seeds.size();
+    }
+    n_extra_seeds = extra_seeds;
     CU(seed_slots.ensure((size_t)S * 4));
     CU(seed_rows.ensure((size_t)S * row_bytes));
     CU(seed_sq.ensure((size_t)S * 4));
@@ -1252,6 +1298,7 @@ vsb_status vsb_create(const vsb_options* o, vsb_index** out) {
     if (const char* e = getenv("VSB_I8_RERANK_MULT")) ix->rr_mult8 = std::max<uint32_t>(2, (uint32_t)strtoul(e, nullptr, 10));
     if (const char* e = getenv("VSB_DISABLE_TC")) ix->tc_enabled = !(e[0] == '1');
     if (const char* e = getenv("VSB_DISABLE_CERT")) ix->cert_enabled = !(e[0] == '1');
+    if (const char* e = getenv("VSB_DISABLE_REACH_FIX")) ix->reach_fix = !(e[0] == '1');
     if (const char* e = getenv("VSB_CERT_KP")) ix->cert_kp = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("VSB_CERT_KP16")) ix->cert_kp16 = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("VSB_TC_MIN_ROWS")) ix->tc_min_rows = (uint32_t)strtoul(e, nullptr, 10);
@@ -1397,6 +1444,7 @@ vsb_status vsb_get_stats(vsb_index* ix, vsb_stats* out) {
     out->exact_certified = ix->cert_ok;
     out->exact_fallback = ix->cert_fallback;
     out->exact_scanned = ix->cert_scanned;
+    out->extra_seeds = ix->n_extra_seeds;
     return VSB_OK;
 }
 

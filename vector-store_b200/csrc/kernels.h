@@ -91,6 +91,12 @@ void launch_reverse_edges(const uint32_t* fwd, uint32_t n, uint32_t R, uint32_t*
 void launch_merge_graph(const uint32_t* fwd, const uint32_t* rev, const uint32_t* rev_cnt, uint32_t n,
                         uint32_t R, uint32_t* graph, uint32_t graph_stride, cudaStream_t stream);
 
+// reachability from the seed sample (graph_build.cu): state bytes 0 = unreached, 1 = frontier, 2 = expanded
+void launch_reach_mark(uint8_t* state, const uint32_t* seeds, uint32_t n_seeds, cudaStream_t stream);
+void launch_reach_step(const uint32_t* graph, uint32_t n, uint32_t stride, uint32_t degree, uint8_t* state,
+                       uint32_t* changed, cudaStream_t stream);
+void launch_first_unreached(const uint8_t* state, const uint32_t* deny, uint32_t n, uint32_t* out, cudaStream_t stream);
+
 // K7 (graph_build.cu): link a batch of already-searched new rows into the graph
 void launch_stream_link(const uint64_t* cand, uint32_t n_new, uint32_t cand_stride, uint32_t first_slot, uint32_t R,
                         uint32_t* graph, uint32_t graph_stride, cudaStream_t stream);

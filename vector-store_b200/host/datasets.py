@@ -53,3 +53,132 @@ def write_ibin(path: str, rows: np.ndarray) -> None:
     with open(path, "wb") as f:
         np.array(rows.shape, dtype="<u4").tofile(f)
         rows.tofile(f)
+
+
+# ---- N4: parquet datasets (crates/benchmark/src/data/parquet.rs: the VectorDBBench directory layout) ----
+# <dir>/*train*.parquet  : columns `id` (int64), `emb` (list<float32|float64>)          -> corpus rows
+# <dir>/test.parquet      : columns `id`, `emb`                                           -> queries
+# <dir>/neighbors.parquet : columns `id`, `neighbors_id` (list<int64>)                    -> ground truth per query id
+class ParquetConfig:
+    """Same fields and defaults as the reference's parquet `Config` (data/parquet.rs:34-103)."""
+
+    def __init__(self, ext: str = "parquet", train_file_pattern: str = "train", test_file_name: str = "test.parquet",
+                 neighbors_file_name: str = "neighbors.parquet", id_column: str = "id", embedding_column: str = "emb",
+                 neighbors_id_column: str = "neighbors_id"):
+        self.ext = ext
+        self.train_file_pattern = train_file_pattern
+        self.test_file_name = test_file_name
+        self.neighbors_file_name = neighbors_file_name
+        self.id_column = id_column
+        self.embedding_column = embedding_column
+        self.neighbors_id_column = neighbors_id_column
+
+
+def _pq():
+    import pyarrow.parquet as pq  # imported lazily: only dataset tooling needs pyarrow
+    return pq
+
+
+def _embeddings_to_f32(col) -> np.ndarray:
+    """list<float32|float64> (or large_list) column chunk -> [rows][dim] f32 (f64 is narrowed, parquet.rs:151-169)."""
+    import pyarrow as pa
+    col = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
+    if len(col) == 0:
+        return np.empty((0, 0), np.float32)
+    if col.null_count:
+        raise ValueError("null embedding")
+    values = col.flatten().to_numpy(zero_copy_only=False)
+    offsets = col.offsets.to_numpy()
+    dims = np.diff(offsets)
+    if not np.all(dims == dims[0]):
+        raise ValueError("ragged embeddings in one batch")
+    return np.ascontiguousarray(values.reshape(len(col), int(dims[0])), dtype=np.float32)
+
+
+def parquet_train_files(path: str, config: ParquetConfig | None = None) -> list[str]:
+    """Regular files in `path` whose name contains the train pattern and whose extension matches (parquet.rs:124-149)."""
+    import os
+    cfg = config or ParquetConfig()
+    out = []
+    for name in sorted(os.listdir(path)):
+        full = os.path.join(path, name)
+        if os.path.isfile(full) and cfg.train_file_pattern in name and name.rsplit(".", 1)[-1] == cfg.ext and "." in name:
+            out.append(full)
+    return out
+
+
+def parquet_dimension(path: str, config: ParquetConfig | None = None) -> int:
+    """Length of the first test embedding (parquet.rs:105-123)."""
+    import os
+    cfg = config or ParquetConfig()
+    f = _pq().ParquetFile(os.path.join(path, cfg.test_file_name))
+    batch = next(f.iter_batches(batch_size=1, columns=[cfg.embedding_column]))
+    return int(_embeddings_to_f32(batch.column(0)).shape[1])
+
+
+def parquet_vector_batches(path: str, config: ParquetConfig | None = None):
+    """Yields (ids int64 [n], rows f32 [n][dim]) per row group of every train file (parquet.rs:229-330): the
+    unit a caller hands to vsb_add."""
+    cfg = config or ParquetConfig()
+    for file in parquet_train_files(path, cfg):
+        f = _pq().ParquetFile(file)
+        for rg in range(f.num_row_groups):
+            t = f.read_row_group(rg, columns=[cfg.id_column, cfg.embedding_column])
+            if t.num_rows == 0:
+                continue
+            ids = t.column(cfg.id_column).combine_chunks().to_numpy(zero_copy_only=False).astype(np.int64)
+            yield ids, _embeddings_to_f32(t.column(cfg.embedding_column))
+
+
+def parquet_queries(path: str, config: ParquetConfig | None = None, id_ok=None, limit: int = 10):
+    """-> list of (query f32 [dim], set of ground-truth ids): test rows joined with neighbors.parquet by id; each
+    neighbour list is filtered by `id_ok`, cut to its first `limit` survivors and dropped when empty
+    (parquet.rs:332-433)."""
+    import os
+    cfg = config or ParquetConfig()
+    pq = _pq()
+    t = pq.read_table(os.path.join(path, cfg.test_file_name), columns=[cfg.id_column, cfg.embedding_column])
+    q_ids = t.column(cfg.id_column).combine_chunks().to_numpy(zero_copy_only=False).astype(np.int64)
+    q_rows = _embeddings_to_f32(t.column(cfg.embedding_column))
+    queries = {int(i): q_rows[n] for n, i in enumerate(q_ids)}
+    nt = pq.read_table(os.path.join(path, cfg.neighbors_file_name), columns=[cfg.id_column, cfg.neighbors_id_column])
+    n_ids = nt.column(cfg.id_column).combine_chunks().to_numpy(zero_copy_only=False).astype(np.int64)
+    neigh = nt.column(cfg.neighbors_id_column).combine_chunks()
+    offsets = neigh.offsets.to_numpy()
+    values = neigh.flatten().to_numpy(zero_copy_only=False).astype(np.int64)
+    truth = {}
+    for n, i in enumerate(n_ids):
+        ids = values[offsets[n]:offsets[n + 1]]
+        kept = [int(v) for v in ids if id_ok is None or id_ok(int(v))][:limit]
+        if kept:
+            truth[int(i)] = set(kept)
+    return [(queries[i], truth[i]) for i in queries if i in truth]
+
+
+def write_parquet_dataset(path: str, ids: np.ndarray, rows: np.ndarray, q_ids: np.ndarray, queries: np.ndarray,
+                          neighbors: np.ndarray, train_files: int = 1, row_group_rows: int | None = None,
+                          emb_type: str = "float32") -> None:
+    """Writes a dataset in the layout above (test fixture / export of a synthetic corpus)."""
+    import os
+    import pyarrow as pa
+    pq = _pq()
+    os.makedirs(path, exist_ok=True)
+    ft = pa.float32() if emb_type == "float32" else pa.float64()
+
+    def emb_col(m):
+        flat = pa.array(np.ascontiguousarray(m).reshape(-1).astype(np.float32 if emb_type == "float32" else np.float64), ft)
+        offs = pa.array(np.arange(0, (len(m) + 1) * m.shape[1], m.shape[1], dtype=np.int64))
+        return pa.LargeListArray.from_arrays(offs, flat)
+
+    per = (len(ids) + train_files - 1) // train_files
+    for f in range(train_files):
+        sl = slice(f * per, min(len(ids), (f + 1) * per))
+        tab = pa.table({"id": pa.array(ids[sl].astype(np.int64)), "emb": emb_col(rows[sl])})
+        name = "train.parquet" if train_files == 1 else f"shuffle_train-{f:02d}-of-{train_files:02d}.parquet"
+        pq.write_table(tab, os.path.join(path, name), row_group_size=row_group_rows or max(1, sl.stop - sl.start))
+    pq.write_table(pa.table({"id": pa.array(q_ids.astype(np.int64)), "emb": emb_col(queries)}),
+                   os.path.join(path, "test.parquet"))
+    noffs = pa.array(np.arange(0, (len(neighbors) + 1) * neighbors.shape[1], neighbors.shape[1], dtype=np.int64))
+    ncol = pa.LargeListArray.from_arrays(noffs, pa.array(neighbors.reshape(-1).astype(np.int64)))
+    pq.write_table(pa.table({"id": pa.array(q_ids.astype(np.int64)), "neighbors_id": ncol}),
+                   os.path.join(path, "neighbors.parquet"))

@@ -35,7 +35,7 @@ class VsbStats(C.Structure):
                                           "hbm_bytes", "convert_ns", "seed_ns", "graph_search_ns", "exact_ns",
                                           "merge_ns", "convert_launches", "seed_launches", "graph_search_launches",
                                           "exact_launches", "merge_launches", "tc_launches",
-                                          "exact_certified", "exact_fallback", "exact_scanned")]
+                                          "exact_certified", "exact_fallback", "exact_scanned", "extra_seeds")]
 
 
 # every symbol include/vsb200.h declares: (name, restype, argtypes)
