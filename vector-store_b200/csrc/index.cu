@@ -196,7 +196,7 @@ struct vsb_index {
                                &seed16_rows, &seed16_sq, &seed16_nrm, &q16_rows, &q16_sq, &q16_nrm,
                                &q_in, &q_rows, &q_sq, &q_nrm, &part, &seed_part, &tmp_keys, &tmp_dists, &counters,
                                &add_in, &allow, &cert_state, &fb_map, &fb_rows, &fb_sq, &fb_nrm, &rows8, &sq8, &nrm8, &q8_rows,
-                               &q8_sq, &q8_nrm};
+                               &q8_sq, &q8_nrm, &reach_state};
         size_t s = 0;
         for (auto* b : all) s += b->bytes;
         return s;
