@@ -1,0 +1,67 @@
+"""CPU checks of the error bounds the GPU path relies on (numpy emulation of the reduced-precision stages):
+  * the exactness certificate of K3: |dot_tf32 - dot| <= (1.25 * 2^-9 + dim * 2^-22) |q||x|
+  * the scaled-int8 traversal copy (VSB_FLAG_I8_TRAVERSAL): cosine error of the quantised rows
+These mirror the constants in vector-store_b200/csrc/index.cu (exact_block) and convert.cu (convert_rows_i8s)."""
+import numpy as np
+
+from conftest import embedding_like, sift_like
+
+
+def _tf32(a: np.ndarray, mode: str) -> np.ndarray:
+    """fp32 -> TF32 operand (10 explicit mantissa bits): truncation or round-to-nearest-even."""
+    u = a.astype(np.float32).view(np.uint32).astype(np.uint64)
+    if mode == "rne":
+        u = u + 0xFFF + ((u >> 13) & 1)
+    return (u & 0xFFFFE000).astype(np.uint32).view(np.float32)
+
+
+def test_tf32_dot_error_is_inside_the_certificate_bound():
+    rng = np.random.default_rng(0)
+    for make, dim in ((lambda n, s: embedding_like(n, 768, seed=s), 768), (lambda n, s: sift_like(n, 128, seed=s), 128),
+                      (lambda n, s: rng.standard_normal((n, 100)).astype(np.float32) * 1e3, 100)):
+        x, q = make(4000, 1), make(64, 2)
+        exact = q.astype(np.float64) @ x.astype(np.float64).T
+        scale = np.linalg.norm(q.astype(np.float64), axis=1)[:, None] * np.linalg.norm(x.astype(np.float64), axis=1)[None, :]
+        rel_bound = 1.25 * 2.0 ** -9 + dim * 2.0 ** -22
+        for mode in ("trunc", "rne"):
+            approx = (_tf32(q, mode).astype(np.float32) @ _tf32(x, mode).astype(np.float32).T).astype(np.float64)
+            err = np.abs(approx - exact) / scale
+            assert err.max() < rel_bound, (mode, dim, err.max(), rel_bound)
+            assert err.max() < 0.5 * rel_bound          # the bound is conservative by design (Cauchy-Schwarz)
+
+
+def test_fp32_summation_order_error_is_inside_the_certificate_bound():
+    # two different fp32 summation orders of the same products differ by far less than dim * 2^-22 |q||x|
+    x, q = embedding_like(2000, 768, seed=3), embedding_like(32, 768, seed=4)
+    prod = q[:, None, :] * x[None, :, :]
+    fwd = np.zeros(prod.shape[:2], np.float32)
+    rev = np.zeros(prod.shape[:2], np.float32)
+    for j in range(768):
+        fwd += prod[:, :, j]
+        rev += prod[:, :, 767 - j]
+    scale = np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(x, axis=1)[None, :]
+    assert (np.abs(fwd - rev) / scale).max() < 768 * 2.0 ** -22
+
+
+def _quantize_i8_scaled(a: np.ndarray):
+    """numpy restatement of convert_rows_i8s_kernel: per-row scale max|x|/127, q = rint(x/scale)."""
+    mx = np.abs(a).max(axis=1, keepdims=True)
+    scale = np.where(mx > 0, mx / 127.0, 1.0).astype(np.float32)
+    qv = np.clip(np.rint(a / scale), -127, 127).astype(np.int32)
+    nrm_units = np.linalg.norm(a.astype(np.float64), axis=1) / scale[:, 0]
+    return qv, nrm_units
+
+
+def test_scaled_int8_cosine_error_is_small_against_neighbour_gaps():
+    x, q = embedding_like(20000, 768, seed=5), embedding_like(50, 768, seed=6)
+    xq, xn = _quantize_i8_scaled(x)
+    qq, qn = _quantize_i8_scaled(q)
+    approx = 1.0 - (qq.astype(np.float64) @ xq.astype(np.float64).T) / (qn[:, None] * xn[None, :])
+    exact = 1.0 - (q.astype(np.float64) @ x.astype(np.float64).T)        # unit vectors
+    err = np.abs(approx - exact)
+    assert err.max() < 4e-3 and err.mean() < 5e-4    # measured: max 2.2e-3 over 10^6 pairs, mean 3.1e-4
+    # what matters for the traversal: the true top-10 stay inside the int8 top-40 (the 4k re-rank window)
+    top_true = np.argsort(exact, axis=1)[:, :10]
+    top_i8 = np.argsort(approx, axis=1)[:, :40]
+    kept = np.mean([len(np.intersect1d(a, b)) / 10 for a, b in zip(top_true, top_i8)])
+    assert kept >= 0.999
