@@ -19,6 +19,9 @@
  *     the query.
  *   - results: per query `k` slots, ascending by (distance, key); unused slots
  *     hold key = UINT64_MAX and distance = +inf; `counts[q]` = valid entries.
+ *   - k (the reference's `Limit`, an unbounded NonZeroUsize): vsb_search accepts k <= 1024 whether or not
+ *     un-graphed rows exist (of the brute-force tail at most its 200 best rows take part in a result);
+ *     vsb_search_exact and the exact bitmap scan accept k <= 200 and return VSB_EINVAL above that.
  *   - "_dev" variants take DEVICE pointers and a `cudaStream_t` (as void*) and
  *     never synchronise; they are what bench.py times for the in-HBM number
  *     and what the multi-GPU path feeds straight into the NCCL all-gather.
@@ -43,7 +46,7 @@ typedef enum {
     VSB_EFULL = 4,   /* usearch: "Reserve capacity ahead of insertions!"        */
     VSB_EOOM = 5,    /* HBM budget exhausted (reference: memory.rs Allocate::Cannot) */
     VSB_ECUDA = 6,   /* CUDA runtime/driver failure, incl. "no device"          */
-    VSB_ENCCL = 7
+    VSB_ENCCL = 7    /* multi-GPU plumbing: peer access / IPC mapping between shards unavailable */
 } vsb_status;
 
 /* usearch.rs:480-485  SpaceType -> MetricKind */
@@ -64,6 +67,13 @@ typedef struct {
     int32_t device;           /* CUDA device ordinal; -1 = current device */
     uint32_t flags;           /* VSB_FLAG_* */
     uint64_t seed;            /* seed for the entry-point sample; 0 = default */
+    /* Multi-GPU inside the library (the reference's analogue is the per-partition index map,
+     * usearch.rs:704-705).  n_devices <= 1: one index on `device`.  n_devices in 2..8: the handle is a ROUTER
+     * over one sub-index per listed device, all in this process: mutations are routed by a hash of the key,
+     * every search runs on every shard, each shard's kernels store their top-k straight into the gather
+     * buffer of device_ids[0] over NVLink peer memory, and one K8 merge on that device produces the answer. */
+    int32_t n_devices;
+    int32_t device_ids[8];
 } vsb_options;
 
 #define VSB_FLAG_NONE 0u
@@ -86,6 +96,10 @@ typedef struct {
     uint32_t search_width;     /* parents expanded per iteration, 1..4 */
     uint32_t stream_threshold; /* un-graphed rows that make vsb_add link them into the graph (K7);
                                   default 4096; UINT32_MAX = never (only vsb_insert_pending / vsb_build) */
+    uint32_t filter_exact_below_pct; /* filtered search: if fewer than this percentage of the live rows is
+                                  admissible the exact bitmap scan is used instead of the graph (default 2;
+                                  100 = always exact, UINT32_MAX = never) */
+    uint32_t expansion_add;    /* beam width of the streaming insert / refinement searches; 0 = keep */
 } vsb_search_params;
 
 /* Counters the roofline arithmetic is computed from. */
@@ -114,12 +128,37 @@ typedef struct {
     uint64_t extra_seeds;
 } vsb_stats;
 
+/* Work and CUDA-event time of each phase of the last vsb_build (plus the streaming inserts / refinements
+ * since): what bench.py's `build_roofline` is computed from (tensor part = 2*P^2*D flop of the
+ * all-pairs stage; HBM part = E * row_bytes of the K4 passes behind K7 and the refinement). */
+typedef struct {
+    uint64_t rows;                 /* rows the last vsb_build covered */
+    uint64_t allpairs_rows;        /* P: rows of the exact all-pairs kNN stage (K1 on tcgen05 + K3) */
+    uint64_t allpairs_flops;       /* 2 * P^2 * D */
+    uint64_t allpairs_ns;
+    uint64_t prune_ns;             /* K6: detour pruning + reverse edges + row assembly (all passes) */
+    uint64_t stream_rows;          /* rows linked by K7 */
+    uint64_t stream_evals;         /* K4 distance evaluations behind them */
+    uint64_t stream_parents;
+    uint64_t stream_ns;
+    uint64_t refine_rows;          /* rows searched by the refinement passes */
+    uint64_t refine_evals;
+    uint64_t refine_parents;
+    uint64_t refine_ns;
+    uint64_t seeds_ns;             /* entry-point sampling + reachability */
+    uint64_t compact_ns;           /* tombstone compaction */
+    uint64_t total_ns;             /* the whole vsb_build call, host clock */
+    uint64_t traversal_row_bytes;  /* bytes one K4 distance evaluation reads during the build */
+} vsb_build_stats;
+
 /* usearch.rs:172  usearch::Index::new(&options) */
 vsb_status vsb_create(const vsb_options* options, vsb_index** out);
 /* drop of ThreadedUsearchIndex / UsearchIndex::stop (usearch.rs:250) */
 void vsb_destroy(vsb_index* index);
 
-/* usearch.rs:181-185  reserve_capacity_and_threads(size, threads); never blocks searches */
+/* usearch.rs:181-185  reserve_capacity_and_threads(size, threads).  Exclusive in the reference (it drains every
+ * search, usearch.rs:601-605); here the grown buffers are filled on the mutator stream and published with a
+ * pointer swap, so searches keep running on the old buffers meanwhile. */
 vsb_status vsb_reserve(vsb_index* index, uint64_t capacity);
 /* usearch.rs:187-189  capacity() */
 uint64_t vsb_capacity(const vsb_index* index);
@@ -131,7 +170,14 @@ uint64_t vsb_size(const vsb_index* index);
  * whole call with VSB_EDUPKEY; size+n > capacity fails with VSB_EFULL.
  * Added vectors are searchable as soon as the call returns (brute-force tail). */
 vsb_status vsb_add(vsb_index* index, const uint64_t* keys, const float* rows, uint64_t n);
-/* usearch.rs:199-201  remove(key) -> usize.  Unknown keys are skipped. */
+/* Same, but row by row like the reference's one-message-per-vector ingest (usearch.rs:1020-1033): a duplicate
+ * or reserved key fails only its own row.  row_status (nullable) receives VSB_OK / VSB_EDUPKEY / VSB_EINVAL
+ * per row, *n_added (nullable) the number of rows inserted.  VSB_EFULL if the valid rows do not fit. */
+vsb_status vsb_add_each(vsb_index* index, const uint64_t* keys, const float* rows, uint64_t n,
+                        int32_t* row_status, uint64_t* n_added);
+/* usearch.rs:199-201  remove(key) -> usize.  Unknown keys are skipped.  The slot of a removed row is
+ * reclaimed by the next compaction (vsb_build, a refinement pass, or automatically when vsb_add finds the
+ * slot space exhausted while size < capacity), so capacity is accounted in LIVE rows like usearch's. */
 vsb_status vsb_remove(vsb_index* index, const uint64_t* keys, uint64_t n, uint64_t* n_removed);
 /* usearch has no equivalent: `contains` for the host-side mirror's duplicate checks. */
 int vsb_contains(const vsb_index* index, uint64_t key);
@@ -154,6 +200,9 @@ vsb_status vsb_export_graph(vsb_index* index, uint32_t* rows_out, uint64_t* keys
 
 vsb_status vsb_set_search_params(vsb_index* index, const vsb_search_params* params);
 vsb_status vsb_get_stats(vsb_index* index, vsb_stats* out);
+vsb_status vsb_get_build_stats(vsb_index* index, vsb_build_stats* out);
+/* the options the handle was created with (after a vsb_load: the snapshot's) */
+vsb_status vsb_get_options(vsb_index* index, vsb_options* out);
 /* Re-runs nothing: switches the graph-search kernel to its counting build for the
  * next searches (identical algorithm; counters off by default for timing runs). */
 vsb_status vsb_set_instrumented(vsb_index* index, int on);
@@ -169,7 +218,10 @@ vsb_status vsb_search_exact(vsb_index* index, const float* queries, uint64_t q, 
                             uint64_t* keys, float* distances, uint32_t* counts);
 /* usearch.rs:224-248  filtered_search(&[f32], k, |key| -> bool).  The host predicate
  * becomes a bitmap over the table's row ids: bit (key & (2^48-1)) set = admissible
- * (rows >= bitmap_bits are inadmissible).  Exact brute force over admissible rows. */
+ * (rows >= bitmap_bits are inadmissible).  Like the reference the graph is TRAVERSED through
+ * inadmissible rows and only admissible ones enter the result (K4 with the bitmap); when fewer than
+ * filter_exact_below_pct percent of the live rows are admissible, or no graph exists, the exact
+ * bitmap scan (K1+K3 under the bitmap, recall 1.0) answers instead. */
 vsb_status vsb_search_filtered(vsb_index* index, const float* queries, uint64_t q, uint32_t k,
                                const uint32_t* allow_bitmap, uint64_t bitmap_bits,
                                uint64_t* keys, float* distances, uint32_t* counts);
@@ -197,6 +249,37 @@ void vsb_batcher_destroy(vsb_batcher* batcher);
 vsb_status vsb_batcher_search(vsb_batcher* batcher, const float* query, uint32_t k, uint64_t* keys,
                               float* distances, uint32_t* count);
 vsb_status vsb_batcher_stats(vsb_batcher* batcher, uint64_t* n_queries, uint64_t* n_batches);
+
+/* single-vector ingest through the batcher (the reference's VsIndexModify::AddVector, one vector per message,
+ * monitor_items.rs:255-353): the row is copied into a staging block and the call returns; the dispatcher
+ * applies staged rows with ONE vsb_add_each per flush (max_batch rows or max_wait_us after the first), so the
+ * per-row H2D + stream sync of vsb_add(n=1) is paid once per block.  Like the reference's fire-and-forget add,
+ * failures of individual rows are counted, not returned.  vsb_batcher_flush waits until everything staged so
+ * far is searchable. */
+vsb_status vsb_batcher_add(vsb_batcher* batcher, uint64_t key, const float* row);
+vsb_status vsb_batcher_flush(vsb_batcher* batcher, uint64_t* n_added, uint64_t* n_failed);
+
+/* ---- multi-process sharding (one rank per GPU, e.g. under torchrun): exchange of the per-shard top-k over
+ * NVLink peer memory instead of an NCCL all-gather.  Every rank creates an exchange on its device, the ranks
+ * swap the 64-byte CUDA-IPC handles with whatever plumbing the host has (torch.distributed in bench.py), and
+ * vsb_xchg_allgather_merge then (1) stores this rank's [q][k] keys+distances into EVERY rank's gather buffer
+ * with plain peer stores, (2) raises a per-rank step flag, (3) runs the K8 merge, which spins on the flags of
+ * all ranks before it reads.  No collective library call and no host synchronisation in the step. */
+typedef struct vsb_xchg vsb_xchg;
+#define VSB_XCHG_HANDLE_BYTES 64
+vsb_status vsb_xchg_create(int32_t device, uint32_t world, uint32_t rank, uint64_t max_queries, uint32_t max_k,
+                           vsb_xchg** out);
+void vsb_xchg_destroy(vsb_xchg* x);
+/* writes VSB_XCHG_HANDLE_BYTES bytes: this rank's gather-buffer handle */
+vsb_status vsb_xchg_local_handle(vsb_xchg* x, void* handle_out);
+/* `handles` = world x VSB_XCHG_HANDLE_BYTES bytes in rank order (own entry ignored); VSB_ENCCL if a peer
+ * buffer cannot be mapped (no P2P / IPC between the devices) */
+vsb_status vsb_xchg_open(vsb_xchg* x, const void* handles);
+vsb_status vsb_xchg_allgather_merge(vsb_xchg* x, const uint64_t* d_keys, const float* d_distances, uint64_t q,
+                                    uint32_t k, uint64_t* d_out_keys, float* d_out_distances,
+                                    uint32_t* d_out_counts, void* stream);
+/* synchronises `stream` and reports VSB_ENCCL if the watchdog of a merge gave up on a rank (~2 s) */
+vsb_status vsb_xchg_check(vsb_xchg* x, void* stream);
 
 /* ---- N3: snapshot.  The reference rebuilds its in-memory index from a full table scan on every restart
  * (db_cdc/checkpoint_saver.rs:103-112); a flat file of keys / tombstones / rows / graph makes

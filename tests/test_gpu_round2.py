@@ -1,0 +1,567 @@
+"""GPU parity tests added in round 2: the CUDA path through the C ABI against the CPU oracle at BASELINE sizes
+(C2 full size, a 2M-row C3 slice), mutation under concurrent search (C5, reference: vs_index/usearch.rs:1526-1607),
+slot reuse under churn, filtered ANN on the graph (usearch.rs:224-248, tests/integration/vs_index.rs:718-1640),
+the micro-batcher against the oracle, the multi-GPU router and the peer-memory exchange."""
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import ROOT, embedding_like
+
+pytestmark = pytest.mark.gpu
+
+INVALID = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def V():
+    import vector_store_b200 as v
+    return v
+
+
+def n_gpus() -> int:
+    import torch
+    return torch.cuda.device_count()
+
+
+def assert_bit_equal(gk, gd, gc, ok, od, oc):
+    assert np.array_equal(gc, oc)
+    assert np.array_equal(gk, ok)
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+
+
+def chunked_corpus(n, dim, clusters=256):
+    """the bench's corpus stream: global row r comes from chunk r // 100000 (seed 1234 + chunk)"""
+    return np.concatenate([embedding_like(min(100_000, n - c0), dim, seed=1234 + c0 // 100_000, n_clusters=clusters)
+                           for c0 in range(0, n, 100_000)])
+
+
+# ---- parity at BASELINE sizes ------------------------------------------------------------------------------------
+def test_c2_full_size_exact_topk_vs_oracle():
+    """BASELINE configs[1] at full size: 64 queries' exact top-10 over 1M x 768 f32 cosine — keys AND fp32 distance
+    bits — through the certified TF32 tensor-core path vs oracle/exact.c.  This is the ground truth bench.py's recall
+    rests on (bench.py takes its `gt` from the same vsb_search_exact call on the same rows)."""
+    n, dim, k, nq = 1_000_000, 768, 10, 64
+    x = chunked_corpus(n, dim)
+    q = embedding_like(10_000, dim, seed=4321)[:: 10_000 // nq][:nq]  # spread over the bench's first query batch
+    keys = np.arange(n, dtype=np.uint64)
+    v = V()
+    idx = v.GpuIndex(dim, v.Metric.Cos, v.Scalar.F32, bf16_traversal=True)
+    idx.reserve(n)
+    for c0 in range(0, n, 100_000):
+        idx.add_batch(keys[c0:c0 + 100_000], x[c0:c0 + 100_000])
+    gk, gd, gc = idx.search_batch(q, k, exact=True)
+    st = idx.stats()
+    ok, od, oc, _ = O.exact_topk(x, q, k, O.COS, O.F32, keys=keys)
+    assert_bit_equal(gk, gd, gc, ok, od, oc)
+    assert st["tc_launches"] > 0 and st["exact_certified"] + st["exact_fallback"] >= nq
+    # the same queries inside a 10 000-query batch (the shape bench.py uses for its ground truth)
+    qb = embedding_like(10_000, dim, seed=4321)
+    bk, bd, _ = idx.search_batch(qb, k, exact=True)
+    sel = np.arange(0, 10_000, 10_000 // nq)[:nq]
+    assert np.array_equal(bk[sel], ok) and np.array_equal(bd[sel].view(np.uint32), od.view(np.uint32))
+    # ANN at the bench's operating point reaches the target against that oracle ground truth
+    idx.build()
+    idx.set_search_params(expansion_search=160, search_width=2)
+    ak, _, _ = idx.search_batch(q, k)
+    r = O.recall_at_k(ak, ok)
+    print(f"C2 1M x 768 f32: exact top-10 bit-equal to the oracle on {nq} queries; ANN recall@10 (ef 160) = {r:.4f}")
+    assert r >= 0.93
+    idx.close()
+
+
+def test_c3_slice_exact_topk_vs_oracle_and_ann_recall():
+    """BASELINE configs[2] (10M x 768 bf16 cosine) on a 2M-row slice: 32 queries' exact top-10 bit-equal to the oracle
+    on bf16 storage, and ANN recall >= 0.95 at the operating point the bench's sweep would pick."""
+    n, dim, k, nq = 2_000_000, 768, 10, 32
+    clusters = 512
+    x = chunked_corpus(n, dim, clusters)
+    q = embedding_like(2000, dim, seed=4321, n_clusters=clusters)
+    keys = np.arange(n, dtype=np.uint64) | np.uint64(3 << 48)
+    v = V()
+    idx = v.GpuIndex(dim, v.Metric.Cos, v.Scalar.BF16)
+    idx.reserve(n)
+    for c0 in range(0, n, 100_000):
+        idx.add_batch(keys[c0:c0 + 100_000], x[c0:c0 + 100_000])
+    gk, gd, gc = idx.search_batch(q[:nq], k, exact=True)
+    ok, od, oc, _ = O.exact_topk(x, q[:nq], k, O.COS, O.BF16, keys=keys)
+    assert_bit_equal(gk, gd, gc, ok, od, oc)
+    del x
+    idx.build()
+    tk, _, _ = idx.search_batch(q, k, exact=True)
+    recall = 0.0
+    for ef in (64, 96, 128, 160, 192, 256):
+        idx.set_search_params(expansion_search=ef, search_width=2)
+        ak, _, ac = idx.search_batch(q, k)
+        recall = O.recall_at_k(ak, tk)
+        if recall >= 0.95:
+            break
+    print(f"C3 slice 2M x 768 bf16: exact bit-equal on {nq} queries; ANN recall@10 = {recall:.4f} at ef={ef}")
+    assert recall >= 0.95 and np.all(ac == k)
+    bs = idx.build_stats()
+    assert bs["rows"] == n and bs["stream_rows"] > 0 and bs["refine_evals"] > 0 and bs["allpairs_flops"] > 0
+    idx.close()
+
+
+# ---- mutation semantics --------------------------------------------------------------------------------------------
+def test_churn_without_build_reuses_slots():
+    """an update stream (remove + add, live size flat) must never run out of slots.  Capacity is
+    accounted in live rows like usearch's (usearch.rs:655-665); the slot space is reclaimed by graph-preserving
+    compaction, no vsb_build in the loop."""
+    n, dim, k = 20_000, 64, 10
+    rng = np.random.default_rng(7)
+    x = embedding_like(n, dim, n_clusters=16)
+    v = V()
+    idx = v.GpuIndex(dim, v.Metric.Cos, v.Scalar.F32)
+    idx.reserve(n + 500)                       # 500 free slots, then 30 000 updates
+    keys = np.arange(n, dtype=np.uint64)
+    idx.add_batch(keys, x)
+    idx.build()
+    cur = x.copy()
+    epoch = np.zeros(n, dtype=np.uint64)
+    for step in range(30):
+        rows = rng.choice(n, 1000, replace=False)
+        old = keys[rows] | (epoch[rows] << np.uint64(48))
+        assert idx.remove_batch(old) == 1000
+        epoch[rows] += np.uint64(1)
+        cur[rows] = embedding_like(1000, dim, seed=100 + step, n_clusters=16)
+        idx.add_batch(keys[rows] | (epoch[rows] << np.uint64(48)), cur[rows])   # would be VSB_EFULL without reuse
+        assert idx.size() == n
+    st = idx.stats()
+    assert st["n_slots"] <= n + 500 and st["n_graphed"] > 0    # the graph survived the compactions
+    live_keys = keys | (epoch << np.uint64(48))
+    q = embedding_like(300, dim, seed=4321, n_clusters=16)
+    gk, gd, gc = idx.search_batch(q, k, exact=True)
+    ok, od, oc, _ = O.exact_topk(cur, q, k, O.COS, O.F32, keys=live_keys)
+    assert_bit_equal(gk, gd, gc, ok, od, oc)
+    idx.set_search_params(expansion_search=128)
+    ak, _, ac = idx.search_batch(q, k)
+    r = O.recall_at_k(ak, ok)
+    print(f"churn x1.5 of the index without vsb_build: ANN recall@10 = {r:.4f}, n_slots = {st['n_slots']}")
+    assert np.all(ac == k) and np.isin(ak, live_keys).all() and r >= 0.93
+    idx.close()
+
+
+def test_add_each_fails_only_the_offending_rows():
+    """the reference processes AddVector one at a time, only the offending row fails (usearch.rs:1020-1033)"""
+    dim = 16
+    rng = np.random.default_rng(1)
+    v = V()
+    idx = v.GpuIndex(dim, v.Metric.L2sq, v.Scalar.F32)
+    idx.reserve(100)
+    x = rng.standard_normal((10, dim)).astype(np.float32)
+    idx.add_batch(np.arange(5, dtype=np.uint64), x[:5])
+    keys = np.array([3, 10, 11, 11, 0xFFFFFFFFFFFFFFFF, 12], dtype=np.uint64)   # dup in index, dup in batch, reserved
+    n, status = idx.add_each(keys, x[:6])
+    assert n == 3 and list(status) == [3, 0, 0, 3, 1, 0]                        # EDUPKEY = 3, EINVAL = 1
+    assert idx.size() == 8 and idx.contains(10) and idx.contains(11) and idx.contains(12)
+    with pytest.raises(v.VsbError) as e:                                        # vsb_add stays all-or-nothing
+        idx.add_batch(np.array([20, 3], np.uint64), x[:2])
+    assert e.value.status == 3 and not idx.contains(20)
+    # the actor mirror keeps the unrelated rows of a batch with one bad key
+    a = v.IndexActor(v.VsIndexConfiguration("i", dim, space_type=v.SpaceType.Euclidean), reserve_increment=1000)
+    a.add_vectors(0, [1, 2, 3], x[:3])
+    a.add_vectors(0, [3, 4, 5], x[3:6])
+    assert a.count() == 5
+    a.stop()
+    idx.close()
+
+
+def test_ann_large_k_with_and_without_tail():
+    """k in (200, 1024] must behave the same whether or not un-graphed rows exist."""
+    n, dim = 30_000, 64
+    x = embedding_like(n + 300, dim, n_clusters=16)
+    q = embedding_like(50, dim, seed=4321, n_clusters=16)
+    v = V()
+    idx = v.GpuIndex(dim, v.Metric.Cos, v.Scalar.F32)
+    idx.reserve(n + 1000)
+    idx.add_batch(np.arange(n, dtype=np.uint64), x[:n])
+    idx.build()
+    idx.set_search_params(expansion_search=768)
+    k = 500
+    k0, d0, c0 = idx.search_batch(q, k)
+    assert np.all(c0 == k) and np.all(np.diff(d0, axis=1) >= 0)
+    idx.add_batch(np.arange(n, n + 300, dtype=np.uint64), x[n:])          # now a tail exists
+    assert idx.stats()["n_graphed"] == n
+    k1, d1, c1 = idx.search_batch(q, k)
+    assert np.all(c1 == k) and np.all(np.diff(d1, axis=1) >= 0)
+    for i in range(len(q)):
+        assert len(np.unique(k1[i])) == k
+    # tail rows that belong into the top-500 are there
+    dm = O.distance_matrix(x, q, O.COS, O.F32)
+    true = np.argsort(dm, axis=1, kind="stable")[:, :k]
+    want_tail = [set(t[t >= n]) for t in true]
+    got_tail = [set(int(a) for a in r[r >= n]) for r in k1]
+    assert sum(len(w & g) for w, g in zip(want_tail, got_tail)) >= 0.95 * sum(len(w) for w in want_tail)
+    with pytest.raises(v.VsbError):
+        idx.search_batch(q, 300, exact=True)                               # documented ceiling of the exact path
+    idx.close()
+
+
+def test_merge_drops_duplicate_keys():
+    import torch
+    v = V()
+    index_mod = sys.modules["vector_store_b200.host.index"]
+    q, k = 5, 4
+    keys = torch.tensor([[[1, 2, 3, 4]] * q, [[2, 9, 3, 7]] * q], dtype=torch.int64, device="cuda")
+    dists = torch.tensor([[[.1, .2, .3, .4]] * q, [[.2, .25, .3, .5]] * q], dtype=torch.float32, device="cuda")
+    ok = torch.empty((q, k), dtype=torch.int64, device="cuda")
+    od = torch.empty((q, k), dtype=torch.float32, device="cuda")
+    oc = torch.empty((q,), dtype=torch.int32, device="cuda")
+    index_mod.merge_topk_dev(keys.data_ptr(), dists.data_ptr(), 2, q, k, ok.data_ptr(), od.data_ptr(), oc.data_ptr(), 0, 0)
+    torch.cuda.synchronize()
+    assert ok.cpu().tolist() == [[1, 2, 9, 3]] * q and oc.cpu().tolist() == [4] * q
+    assert v.version().startswith("vsb200-")
+
+
+# ---- C5: search concurrent with mutation -----------------------------------------------------------------------------
+def test_c5_search_concurrent_with_mutation_and_refinement():
+    """One thread mutates at >= 10k ops/s (70 % insert / 20 % delete / 10 % update) and forces streaming
+    inserts and a refinement pass; another thread searches the whole time.  No call fails, every hit is a key that was
+    live at some point during the search, recall vs exact ground truth of the final live set >= 0.95, and searches keep
+    completing WHILE the refinement runs (the reference gate serialises them, usearch.rs:515-624)."""
+    n0, dim, k = 120_000, 96, 10
+    clusters = 64
+    extra = 60_000
+    x = embedding_like(n0 + extra, dim, n_clusters=clusters)
+    q = embedding_like(2000, dim, seed=4321, n_clusters=clusters)
+    v = V()
+    idx = v.GpuIndex(dim, v.Metric.Cos, v.Scalar.F32, bf16_traversal=True)
+    idx.reserve(n0 + extra + 1000)
+    idx.add_batch(np.arange(n0, dtype=np.uint64), x[:n0])
+    idx.build()
+    idx.set_search_params(expansion_search=128, search_width=2, stream_threshold=4096)
+    ever_live = set(range(n0 + extra))
+    stop = threading.Event()
+    errors, lat, done_at = [], [], []
+
+    def searcher():
+        try:
+            i = 0
+            while not stop.is_set():
+                t0 = time.perf_counter()
+                gk, gd, gc = idx.search_batch(q[i % 2000:i % 2000 + 1], k)
+                lat.append(time.perf_counter() - t0)
+                done_at.append(time.perf_counter())
+                assert gc[0] == k and np.all(np.diff(gd[0]) >= 0)
+                assert all(int(key) & 0xFFFFFFFFFFFF in ever_live for key in gk[0])
+                i += 1
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    th = threading.Thread(target=searcher)
+    th.start()
+    rng = np.random.default_rng(11)
+    live = np.ones(n0 + extra, dtype=bool)
+    live[n0:] = False
+    epoch = np.zeros(n0 + extra, dtype=np.uint64)
+    next_new = n0
+    t_start = time.perf_counter()
+    ops = 0
+    mut_windows = []
+    while next_new < n0 + extra:
+        nb = 1000
+        n_ins, n_del, n_upd = 700, 200, 100
+        ins = np.arange(next_new, min(next_new + n_ins, n0 + extra))
+        next_new += len(ins)
+        cand = np.flatnonzero(live[:next_new - len(ins)])
+        dele = rng.choice(cand, n_del, replace=False)
+        upd = rng.choice(np.setdiff1d(cand, dele), n_upd, replace=False)
+        t0 = time.perf_counter()
+        idx.remove_batch(np.concatenate([dele, upd]).astype(np.uint64) | (epoch[np.concatenate([dele, upd])] << np.uint64(48)))
+        epoch[upd] += np.uint64(1)
+        live[dele] = False
+        rows = np.concatenate([ins, upd])
+        idx.add_batch(rows.astype(np.uint64) | (epoch[rows] << np.uint64(48)), x[rows])
+        live[ins] = True
+        mut_windows.append((t0, time.perf_counter()))
+        ops += nb
+    t_mut = time.perf_counter() - t_start
+    idx.insert_pending()
+    stop.set()
+    th.join()
+    assert not errors, errors[:1]
+    rate = ops / t_mut
+    # searches that completed inside the slowest mutation call (the one that ran K7 + the refinement pass)
+    slow = max(mut_windows, key=lambda w: w[1] - w[0])
+    inside = sum(1 for t in done_at if slow[0] < t < slow[1])
+    p99 = float(np.percentile(lat, 99) * 1e3)
+    print(f"C5 concurrent: {ops} mutations at {rate:.0f} ops/s, {len(lat)} searches, p50 {np.percentile(lat, 50) * 1e3:.3f} ms, "
+          f"p99 {p99:.3f} ms; slowest mutation call {1e3 * (slow[1] - slow[0]):.0f} ms with {inside} searches completed inside it")
+    assert rate >= 10_000
+    assert inside >= 3 or slow[1] - slow[0] < 0.02, "searches stalled behind a mutation"
+    assert p99 < 20.0
+    # final state: exact results bit-equal to the oracle over the live set, ANN recall >= 0.95
+    live_rows = np.flatnonzero(live)
+    live_keys = live_rows.astype(np.uint64) | (epoch[live_rows] << np.uint64(48))
+    assert idx.size() == len(live_rows)
+    gk, gd, gc = idx.search_batch(q[:64], k, exact=True)
+    ok, od, oc, _ = O.exact_topk(x[live_rows], q[:64], k, O.COS, O.F32, keys=live_keys)
+    assert_bit_equal(gk, gd, gc, ok, od, oc)
+    tk, _, _ = idx.search_batch(q, k, exact=True)
+    ak, _, _ = idx.search_batch(q, k)
+    r = O.recall_at_k(ak, tk)
+    print(f"C5 concurrent: recall@10 after {ops} mutations = {r:.4f}")
+    assert r >= 0.95
+    idx.close()
+
+
+# ---- N1: filtered ANN on the graph -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("selectivity", [0.5, 0.05])
+def test_filtered_ann_traverses_the_graph(selectivity):
+    n, dim, k = 100_000, 96, 10
+    x = embedding_like(n, dim, n_clusters=64)
+    q = embedding_like(1000, dim, seed=4321, n_clusters=64)
+    rng = np.random.default_rng(5)
+    keys = np.arange(n, dtype=np.uint64) | np.uint64(2 << 48)       # epoch bits: the bitmap is over the row id
+    allow = rng.random(n) < selectivity
+    v = V()
+    idx = v.GpuIndex(dim, v.Metric.Cos, v.Scalar.F32)
+    idx.reserve(n)
+    idx.add_batch(keys, x)
+    # before a graph exists the filtered search is the exact bitmap scan: bit-equal to the oracle
+    alive = allow.astype(np.uint8)
+    ok, od, oc, _ = O.exact_topk(x, q[:100], k, O.COS, O.F32, keys=keys, alive=alive)
+    ek, ed, ec = idx.search_filtered(q[:100], k, allow)
+    assert_bit_equal(ek, ed, ec, ok, od, oc)
+    idx.build()
+    idx.set_kernel_timing(True)
+    idx.set_search_params(expansion_search=192, search_width=2)
+    gk, gd, gc = idx.search_filtered(q, k, allow)
+    st = idx.stats()
+    idx.set_kernel_timing(False)
+    assert st["graph_search_launches"] >= 1                         # K4 ran: ANN on the graph, not brute force
+    rows = (gk & np.uint64(0xFFFFFFFFFFFF)).astype(np.int64)
+    valid = gk != INVALID
+    assert allow[rows[valid]].all()                                 # results are a subset of the admissible set
+    assert np.all(gc == k) and np.all(np.diff(gd, axis=1) >= 0)
+    idx.set_search_params(filter_exact_below_pct=100)               # yardstick: exact bitmap scan on all 1000 queries
+    tk, td, _ = idx.search_filtered(q, k, allow)
+    r = O.recall_at_k(gk, tk)
+    print(f"filtered ANN at {selectivity:.0%} selectivity: recall@10 vs exact filtered = {r:.4f}")
+    assert r >= 0.95
+    # distances are the canonical ones
+    hit = {(int(a), np.float32(b).view(np.uint32)) for a, b in zip(tk.ravel(), td.ravel())}
+    same = sum((int(a), np.float32(b).view(np.uint32)) in hit for a, b in zip(gk[:50].ravel(), gd[:50].ravel()))
+    assert same >= 0.9 * 50 * k
+    idx.close()
+
+
+def test_filtered_low_selectivity_falls_back_to_exact_scan():
+    n, dim, k = 50_000, 64, 10
+    x = embedding_like(n, dim, n_clusters=16)
+    q = embedding_like(64, dim, seed=4321, n_clusters=16)
+    allow = np.zeros(n, dtype=bool)
+    allow[::200] = True                                             # 0.5 % admissible: below the 2 % default
+    v = V()
+    idx = v.GpuIndex(dim, v.Metric.L2sq, v.Scalar.F32)
+    idx.reserve(n)
+    keys = np.arange(n, dtype=np.uint64)
+    idx.add_batch(keys, x)
+    idx.build()
+    gk, gd, gc = idx.search_filtered(q, k, allow)
+    ok, od, oc, _ = O.exact_topk(x, q, k, O.L2SQ, O.F32, keys=keys, alive=allow.astype(np.uint8))
+    assert_bit_equal(gk, gd, gc, ok, od, oc)
+    idx.close()
+
+
+# ---- N2: micro-batcher against the oracle ------------------------------------------------------------------------------
+def test_micro_batcher_rows_match_the_oracle_and_adds_are_coalesced():
+    n, dim, k = 6000, 64, 10
+    x = embedding_like(n, dim, n_clusters=8)
+    q = embedding_like(16 * 25, dim, seed=4321, n_clusters=8)
+    keys = np.arange(n, dtype=np.uint64) | np.uint64(1 << 48)
+    v = V()
+    idx = v.GpuIndex(dim, v.Metric.Cos, v.Scalar.F32)
+    idx.reserve(n + 16)
+    idx.set_search_params(min_graph_size=10 ** 9)     # no graph: every batched row must be the exact answer
+    b = v.Batcher(idx, max_batch=512, max_wait_us=300)
+    # single-vector adds from 8 threads (the reference's one-message-per-vector ingest)
+    def adder(t):
+        for i in range(t, n, 8):
+            b.add(int(keys[i]), x[i])
+    ts = [threading.Thread(target=adder, args=(t,)) for t in range(8)]
+    launches0 = idx.stats()["kernel_launches"]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    b.add(int(keys[0]), x[0])                          # a duplicate: counted, not fatal
+    added, failed = b.flush()
+    launches = idx.stats()["kernel_launches"] - launches0
+    assert added == n and failed == 1 and idx.size() == n
+    print(f"batcher: {n} single-row adds applied with {launches} kernel launches")
+    assert launches < n / 8                            # coalesced: far fewer convert launches than rows
+    got = [None] * len(q)
+    errors = []
+
+    def worker(t):
+        try:
+            for i in range(t * 25, (t + 1) * 25):
+                got[i] = b.search(q[i], k)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(16)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors[:1]
+    nq, nb = b.stats()
+    assert nq == len(q) and nb < nq
+    ok, od, oc, _ = O.exact_topk(x, q, k, O.COS, O.F32, keys=keys)
+    for i in range(len(q)):
+        assert np.array_equal(got[i][0], ok[i]) and np.array_equal(got[i][1].view(np.uint32), od[i].view(np.uint32))
+    b.close()
+    idx.close()
+
+
+# ---- N3: snapshot validation ----------------------------------------------------------------------------------------------
+def test_snapshot_load_validates_header_and_restores_options(tmp_path):
+    n, dim = 9000, 48
+    x = embedding_like(n, dim, n_clusters=8)
+    v = V()
+    idx = v.GpuIndex(dim, v.Metric.L2sq, v.Scalar.BF16)
+    idx.reserve(n)
+    idx.add_batch(np.arange(n, dtype=np.uint64), x)
+    idx.build()
+    idx.set_search_params(expansion_search=96, search_width=2)
+    a0 = idx.search_batch(x[:50], 5)
+    path = str(tmp_path / "s.vsb")
+    idx.save(path)
+    idx.close()
+    idx2 = v.GpuIndex.load(path)
+    assert idx2.dimensions == dim and idx2.metric == v.Metric.L2sq and idx2.storage == v.Scalar.BF16
+    a1 = idx2.search_batch(x[:50], 5)              # runtime search parameters travel with the snapshot
+    for a, b in zip(a0, a1):
+        assert np.array_equal(a, b)
+    with pytest.raises(v.VsbError):
+        idx2.search_batch(x[:2, :10], 5)           # wrong dimension is caught on the host, never reaches the device
+    v.Batcher(idx2).close()                        # dimensions known after load
+    idx2.close()
+    raw = bytearray(open(path, "rb").read())
+    bad = str(tmp_path / "bad.vsb")
+    off = 8 + 80                                   # magic + vsb_options -> n_slots, n_graphed
+    corrupt = bytearray(raw)
+    corrupt[off + 8:off + 16] = (n + 5).to_bytes(8, "little")       # n_graphed > n_slots
+    open(bad, "wb").write(corrupt)
+    with pytest.raises(v.VsbError):
+        v.GpuIndex.load(bad)
+    corrupt = bytearray(raw)
+    corrupt[-4:] = (0x0FFFFFF0).to_bytes(4, "little")               # a graph edge far out of range
+    open(bad, "wb").write(corrupt)
+    with pytest.raises(v.VsbError):
+        v.GpuIndex.load(bad)
+
+
+# ---- stream hand-over -------------------------------------------------------------------------------
+def test_dev_search_on_the_legacy_default_stream_is_ordered():
+    import torch
+    n, dim, k = 30_000, 64, 10
+    x = embedding_like(n, dim, n_clusters=16)
+    q = embedding_like(4000, dim, seed=4321, n_clusters=16)
+    v = V()
+    idx = v.GpuIndex(dim, v.Metric.Cos, v.Scalar.F32)
+    idx.reserve(n)
+    idx.add_batch(np.arange(n, dtype=np.uint64), x)
+    idx.build()
+    want = idx.search_batch(q, k)
+    dq = torch.from_numpy(q).cuda()
+    outs = []
+    side = torch.cuda.Stream()
+    for it in range(6):      # alternate the legacy default stream (0) and a side stream without any host sync
+        dk = torch.empty((len(q), k), dtype=torch.int64, device="cuda")
+        dd = torch.empty((len(q), k), dtype=torch.float32, device="cuda")
+        s = 0 if it % 2 == 0 else side.cuda_stream
+        idx.search_dev(dq.data_ptr(), len(q), k, dk.data_ptr(), dd.data_ptr(), 0, s)
+        outs.append((dk, dd))
+    got_host = idx.search_batch(q, k)   # and a host call on the index's own stream right behind them
+    torch.cuda.synchronize()
+    for dk, dd in outs:
+        assert np.array_equal(dk.cpu().numpy().view(np.uint64), want[0]) and np.array_equal(dd.cpu().numpy(), want[1])
+    assert np.array_equal(got_host[0], want[0])
+    idx.close()
+
+
+# ---- multi-GPU inside the library ----------------------------------------------------------------------------------------
+@pytest.mark.skipif("n_gpus() < 2")
+def test_sharded_handle_matches_single_device():
+    g = min(n_gpus(), 8)
+    n, dim, k = 80_000, 96, 10
+    x = embedding_like(n, dim, n_clusters=32)
+    q = embedding_like(1000, dim, seed=4321, n_clusters=32)
+    keys = np.arange(n, dtype=np.uint64) | np.uint64(1 << 48)
+    v = V()
+    idx = v.GpuIndex(dim, v.Metric.Cos, v.Scalar.F32, devices=list(range(g)))
+    idx.reserve(n)
+    idx.add_batch(keys, x)
+    assert idx.size() == n and idx.contains(int(keys[5]))
+    gk, gd, gc = idx.search_batch(q, k, exact=True)
+    ok, od, oc, _ = O.exact_topk(x, q, k, O.COS, O.F32, keys=keys)
+    assert_bit_equal(gk, gd, gc, ok, od, oc)        # merge of per-shard exact results = global exact result
+    idx.build()
+    st = idx.stats()
+    assert st["n_graphed"] == n
+    idx.set_search_params(expansion_search=96)
+    ak, ad, ac = idx.search_batch(q, k)
+    r = O.recall_at_k(ak, ok)
+    print(f"sharded handle over {g} GPUs: exact bit-equal, ANN recall@10 = {r:.4f}")
+    assert r >= 0.95 and np.all(ac == k)
+    assert idx.remove_batch(keys[:100]) == 100 and idx.size() == n - 100
+    ak2, _, _ = idx.search_batch(q, k)
+    assert not np.isin(ak2, keys[:100]).any()
+    idx.close()
+
+
+_XCHG_CHILD = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import vector_store_b200 as v
+from importlib import import_module
+index_mod = import_module("vector_store_b200.host.index")
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dev = rank % torch.cuda.device_count()
+torch.cuda.set_device(dev)
+dist.init_process_group("gloo")
+def ag(b):
+    out = [None] * world
+    dist.all_gather_object(out, b)
+    return out
+q, k = 3000, 10
+x = index_mod.Exchange(dev, world, rank, q, k, ag)
+rng = np.random.default_rng(5)
+alld = np.sort(rng.random((world, q, k)).astype(np.float32), axis=2)
+allk = rng.permutation(world * q * k).astype(np.int64).reshape(world, q, k)
+for step in range(5):
+    dk = torch.from_numpy(allk[rank] + step).cuda()
+    dd = torch.from_numpy(alld[rank]).cuda()
+    ok = torch.empty((q, k), dtype=torch.int64, device="cuda")
+    od = torch.empty((q, k), dtype=torch.float32, device="cuda")
+    oc = torch.empty((q,), dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    x.allgather_merge(dk.data_ptr(), dd.data_ptr(), q, k, ok.data_ptr(), od.data_ptr(), oc.data_ptr(), s)
+    x.check(s)
+    cat_d = np.concatenate(list(alld), axis=1)
+    cat_k = np.concatenate(list(allk + step), axis=1)
+    order = np.lexsort((cat_k, cat_d), axis=1)[:, :k]
+    assert np.array_equal(ok.cpu().numpy(), np.take_along_axis(cat_k, order, 1)), (rank, step)
+    assert np.array_equal(od.cpu().numpy(), np.take_along_axis(cat_d, order, 1))
+dist.barrier()
+x.close()
+print("xchg ok", rank)
+"""
+
+
+def test_peer_memory_exchange_between_processes(tmp_path):
+    """vsb_xchg_*: two ranks (two processes; on one GPU if the box has only one) exchange per-shard top-k through
+    CUDA-IPC mapped buffers and merge — no NCCL call in the step."""
+    script = tmp_path / "xchg_child.py"
+    script.write_text(_XCHG_CHILD)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29631", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"xchg ok {r}" in o, o[-2000:]

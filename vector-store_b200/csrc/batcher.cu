@@ -6,8 +6,11 @@
 // in C++ behind the same C ABI: any number of threads call vsb_batcher_search() with one query each; a
 // single dispatcher thread drains the queue — up to `max_batch` requests or `max_wait_us` after the first —
 // into ONE vsb_search() call and fans the rows back out (the oneshot replies of actor.rs:137-147).
-// Searches keep priority over modifications exactly like the biased select: modifications go straight to
-// vsb_add/vsb_remove on the caller's thread and only contend on the index mutex between batches.
+// Searches keep priority over modifications exactly like the biased select (vs_index/mod.rs:39-42): a pending
+// search batch is always dispatched before staged adds are flushed.
+// Single-vector adds (VsIndexModify::AddVector, one vector per message, monitor_items.rs:255-353) are coalesced the
+// same way: vsb_batcher_add copies the row into a staging block and returns; the dispatcher applies a block with
+// ONE vsb_add_each (one H2D + one stream sync for the block instead of one per row).
 #include <chrono>
 #include <condition_variable>
 #include <cstring>
@@ -42,6 +45,38 @@ struct vsb_batcher {
     std::thread worker;
     uint64_t n_queries = 0, n_batches = 0;
     std::string last_error;
+    // staged single-row adds
+    std::vector<uint64_t> add_keys;
+    std::vector<float> add_rows;
+    std::chrono::steady_clock::time_point add_first;
+    uint64_t adds_staged = 0, adds_applied = 0, adds_ok = 0, adds_failed = 0;
+    std::condition_variable cv_flushed;
+
+    // mu held on entry and exit; released around the index call
+    void flush_adds(std::unique_lock<std::mutex>& lk) {
+        std::vector<uint64_t> k;
+        std::vector<float> r;
+        k.swap(add_keys);
+        r.swap(add_rows);
+        const uint64_t n = k.size();
+        if (n == 0) return;
+        lk.unlock();
+        uint64_t ok = 0;
+        std::vector<int32_t> st((size_t)n, 0);
+        vsb_status rc = vsb_add_each(index, k.data(), r.data(), n, st.data(), &ok);
+        if (rc == VSB_EFULL) {
+            // the reference's actor reserves ahead of the stream (usearch.rs:655-665); do the same and retry once
+            const uint64_t cap = vsb_capacity(index);
+            if (vsb_reserve(index, cap + std::max<uint64_t>(n, cap / 4) + 1024) == VSB_OK)
+                rc = vsb_add_each(index, k.data(), r.data(), n, st.data(), &ok);
+        }
+        lk.lock();
+        adds_applied += n;
+        adds_ok += ok;
+        adds_failed += n - ok;
+        if (rc != VSB_OK) last_error = vsb_last_error();
+        cv_flushed.notify_all();
+    }
 
     void run() {
         std::vector<Request*> batch;
@@ -51,8 +86,22 @@ struct vsb_batcher {
         std::vector<uint32_t> counts;
         std::unique_lock<std::mutex> lk(mu);
         while (true) {
-            cv_work.wait(lk, [&] { return stop || !queue.empty(); });
-            if (stop && queue.empty()) return;
+            if (add_keys.empty()) {
+                cv_work.wait(lk, [&] { return stop || !queue.empty() || !add_keys.empty(); });
+            } else {
+                // staged adds wait for company until max_wait_us after the first of them, searches permitting
+                const auto add_deadline = add_first + std::chrono::microseconds(max_wait_us);
+                cv_work.wait_until(lk, add_deadline, [&] { return stop || !queue.empty() || add_keys.size() >= max_batch; });
+                if (queue.empty() && (stop || add_keys.size() >= max_batch || std::chrono::steady_clock::now() >= add_deadline)) {
+                    flush_adds(lk);
+                    continue;
+                }
+            }
+            if (stop && queue.empty()) {
+                flush_adds(lk);
+                return;
+            }
+            if (queue.empty()) continue;
             // first request is in: give followers max_wait_us to arrive (or until the batch is full)
             const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(max_wait_us);
             while (!stop && queue.size() < max_batch && cv_work.wait_until(lk, deadline) != std::cv_status::timeout) {
@@ -136,6 +185,31 @@ vsb_status vsb_batcher_search(vsb_batcher* b, const float* query, uint32_t k, ui
     b->cv_work.notify_all();
     r.cv.wait(lk, [&] { return r.done; });
     return r.status;
+}
+
+vsb_status vsb_batcher_add(vsb_batcher* b, uint64_t key, const float* row) {
+    if (!b || !row) return VSB_EINVAL;
+    std::lock_guard<std::mutex> g(b->mu);
+    if (b->stop) return VSB_EINVAL;
+    if (b->add_keys.empty()) b->add_first = std::chrono::steady_clock::now();
+    b->add_keys.push_back(key);
+    b->add_rows.insert(b->add_rows.end(), row, row + b->dim);
+    b->adds_staged += 1;
+    if (b->add_keys.size() == 1 || b->add_keys.size() >= b->max_batch) b->cv_work.notify_all();
+    return VSB_OK;
+}
+
+vsb_status vsb_batcher_flush(vsb_batcher* b, uint64_t* n_added, uint64_t* n_failed) {
+    if (!b) return VSB_EINVAL;
+    std::unique_lock<std::mutex> lk(b->mu);
+    const uint64_t target = b->adds_staged;
+    // make the dispatcher flush now instead of waiting for company
+    b->add_first = std::chrono::steady_clock::now() - std::chrono::hours(1);
+    b->cv_work.notify_all();
+    b->cv_flushed.wait(lk, [&] { return b->adds_applied >= target || b->stop; });
+    if (n_added) *n_added = b->adds_ok;
+    if (n_failed) *n_failed = b->adds_failed;
+    return VSB_OK;
 }
 
 vsb_status vsb_batcher_stats(vsb_batcher* b, uint64_t* n_queries, uint64_t* n_batches) {

@@ -216,48 +216,175 @@ void launch_merge_graph(const uint32_t* fwd, const uint32_t* rev, const uint32_t
 }  // namespace vsb
 
 // ------------------------------------------------------------------------------------------------
-// K7: streaming insert (SURVEY §8a A5 "HNSW insert", config C5).  The batch of new rows has been
-// searched with K4 (beam = expansion_add) and `cand` holds each new row's best candidates (packed,
-// ascending, kInvalidPacked padded).  One warp per new row u:
-//   forward : row(u) = its R closest candidates
-//   reverse : each of the R/2 closest v gets u written into the reverse half of row(v) — an empty slot
-//             if one is hit, otherwise a pseudo-randomly chosen reverse edge is replaced (atomicExch,
-//             so concurrent inserts into the same row never tear it)
-// Rows of one batch do not link to each other; a periodic vsb_build() re-optimises the graph.
+// K7: streaming insert (SURVEY §8a A5 "HNSW insert", config C5).  The batch of new rows has been searched with
+// K4 (beam = expansion_add) and `cand` holds each new row's C best candidates (packed, ascending,
+// kInvalidPacked padded; C <= 128, normally 2R).  Two kernels, so that the row of a new node is complete before
+// any edge points at it (searches may be walking the same buffer, index_impl.h):
+//   stream_link_fwd : one warp per new row u.  Neighbour selection is the bulk build's rank-based detour count
+//                     with the GRAPH rows of the candidates standing in for their kNN lists:
+//                     detour[j] = #{ i < j : cand[j] is a neighbour of cand[i] }  (u -> cand[i] -> cand[j] exists),
+//                     keep the R candidates with the smallest (detour, j) — a diverse neighbourhood instead of
+//                     the R closest, which is what keeps recall from decaying between refinement passes.
+//   stream_link_rev : each of the R/2 first neighbours v of u gets u written into the reverse half of row(v):
+//                     an empty slot if there is one, otherwise a pseudo-randomly chosen one is replaced
+//                     (single-word atomics, so concurrent inserts into the same row never tear it).
+// Rows of one batch do not link to each other; refinement passes re-optimise the graph.
 namespace vsb {
 namespace {
-__global__ void __launch_bounds__(128) stream_link_kernel(const uint64_t* __restrict__ cand, uint32_t n_new,
-                                                          uint32_t cand_stride, uint32_t first_slot, uint32_t R,
-                                                          uint32_t* __restrict__ graph, uint32_t graph_stride) {
+constexpr int K7_WARPS = 4;
+
+__global__ void __launch_bounds__(K7_WARPS * 32) stream_link_fwd_kernel(const uint64_t* __restrict__ cand, uint32_t n_new,
+                                                                        uint32_t C, uint32_t first_slot, uint32_t R,
+                                                                        uint32_t* __restrict__ graph, uint32_t graph_stride) {
+    __shared__ uint32_t sL[K7_WARPS][K6_MAXK];
+    __shared__ uint32_t sDet[K7_WARPS][K6_MAXK];
+    __shared__ uint32_t sHid[K7_WARPS][K6_HASH];
+    __shared__ uint32_t sHrank[K7_WARPS][K6_HASH];
+    __shared__ uint64_t sOrd[K7_WARPS][K6_MAXK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * K7_WARPS + warp;
+    if (i >= n_new) return;
+    const uint32_t u = first_slot + i;
+    uint32_t* L = sL[warp];
+    uint32_t* det = sDet[warp];
+    uint32_t* hid = sHid[warp];
+    uint32_t* hrank = sHrank[warp];
+    uint64_t* ord = sOrd[warp];
+    for (int t = lane; t < K6_HASH; t += 32) hid[t] = kInvalidSlot;
+    const uint32_t k0 = C < (uint32_t)K6_MAXK ? C : (uint32_t)K6_MAXK;
+    for (uint32_t j = lane; j < K6_MAXK; j += 32) {
+        uint32_t v = kInvalidSlot;
+        if (j < k0) {
+            const uint64_t p = cand[(size_t)i * C + j];
+            if (p != kInvalidPacked && packed_lo(p) != u) v = packed_lo(p);
+        }
+        L[j] = v;  // holes (padding, u itself) are skipped everywhere below
+        det[j] = 0;
+        ord[j] = kInvalidPacked;
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < k0; j += 32) {
+        const uint32_t v = L[j];
+        if (v == kInvalidSlot) continue;
+        uint32_t h = (v * 0x9E3779B1u) >> 24;
+        while (true) {
+            const uint32_t old = atomicCAS(&hid[h], kInvalidSlot, v);
+            if (old == kInvalidSlot) {
+                hrank[h] = j;
+                break;
+            }
+            if (old == v) break;  // duplicate candidate: the first rank stands
+            h = (h + 1) & (K6_HASH - 1);
+        }
+    }
+    __syncwarp();
+    for (uint32_t a = 0; a < k0; ++a) {
+        if (L[a] == kInvalidSlot) continue;
+        const uint32_t* row = graph + (size_t)L[a] * graph_stride;
+        for (uint32_t t = lane; t < R; t += 32) {
+            const uint32_t y = row[t];
+            if (y == kInvalidSlot) continue;
+            uint32_t h = (y * 0x9E3779B1u) >> 24;
+            while (true) {
+                const uint32_t id = hid[h];
+                if (id == kInvalidSlot) break;
+                if (id == y) {
+                    const uint32_t j = hrank[h];
+                    if (j > a) atomicAdd(&det[j], 1u);
+                    break;
+                }
+                h = (h + 1) & (K6_HASH - 1);
+            }
+        }
+    }
+    __syncwarp();
+    const LessBySlot less;
+    for (uint32_t b = 0; b < K6_MAXK; b += 32) {
+        const uint32_t j = b + lane;
+        uint64_t v = (j < k0 && L[j] != kInvalidSlot) ? (((uint64_t)det[j] << 32) | j) : kInvalidPacked;
+        if (__ballot_sync(kFullMask, v != kInvalidPacked) == 0) continue;
+        v = warp_sort32(v, lane, less);
+        warp_list_merge(ord, K6_MAXK, v, lane, less);
+    }
+    __syncwarp();
+    // the kept edges go back into distance order (rank order), so the R/2 first ones are the closest kept ones
+    for (int t = lane; t < K6_HASH; t += 32) hid[t] = 0;  // the hash is done: reuse it as "kept" flags by rank
+    __syncwarp();
+    for (uint32_t r = lane; r < R && r < (uint32_t)K6_MAXK; r += 32) {
+        const uint64_t o = ord[r];
+        if (o != kInvalidPacked) hid[packed_lo(o)] = 1;
+    }
+    __syncwarp();
+    uint32_t* out = graph + (size_t)u * graph_stride;
+    uint32_t count = 0;
+    for (uint32_t b = 0; b < k0; b += 32) {
+        const uint32_t j = b + lane;
+        const bool kept = j < k0 && hid[j] == 1;
+        const uint32_t m = __ballot_sync(kFullMask, kept);
+        if (kept) out[count + __popc(m & ((1u << lane) - 1))] = L[j];
+        count += __popc(m);
+    }
+    for (uint32_t r = count + lane; r < graph_stride; r += 32) out[r] = kInvalidSlot;
+}
+
+__global__ void __launch_bounds__(128) stream_link_rev_kernel(uint32_t n_new, uint32_t first_slot, uint32_t R,
+                                                              uint32_t* __restrict__ graph, uint32_t graph_stride) {
     const int lane = threadIdx.x & 31;
     const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n_new) return;
     const uint32_t u = first_slot + i;
-    const uint64_t* c = cand + (size_t)i * cand_stride;
-    uint32_t* row = graph + (size_t)u * graph_stride;
     const uint32_t half = R / 2;
-    for (uint32_t r = lane; r < graph_stride; r += 32) {
-        uint32_t v = kInvalidSlot;
-        if (r < R && r < cand_stride) {
-            const uint64_t p = c[r];
-            if (p != kInvalidPacked) v = packed_lo(p);
+    const uint32_t* row = graph + (size_t)u * graph_stride;
+    for (uint32_t r = 0; r < half; ++r) {
+        const uint32_t v = row[r];
+        if (v == kInvalidSlot || v >= first_slot) continue;  // uniform across the warp
+        uint32_t* vrow = graph + (size_t)v * graph_stride;
+        const uint32_t pos = half + lane;
+        const uint32_t cur = pos < R ? vrow[pos] : 0u;
+        if (__ballot_sync(kFullMask, pos < R && cur == u) != 0) continue;  // already linked
+        const uint32_t empties = __ballot_sync(kFullMask, pos < R && cur == kInvalidSlot);
+        bool done = false;
+        if (empties != 0) {
+            const int src = __ffs(empties) - 1;
+            uint32_t old = kInvalidSlot;
+            if (lane == src) old = atomicCAS(&vrow[pos], kInvalidSlot, u);
+            old = __shfl_sync(kFullMask, old, src);
+            done = old == kInvalidSlot;
         }
-        if (v == u) v = kInvalidSlot;
-        row[r] = v;
-        if (v != kInvalidSlot && r < half) {
-            uint32_t* vrow = graph + (size_t)v * graph_stride;
-            const uint32_t pos = half + ((u * 0x9E3779B1u + r * 0x85EBCA6Bu) >> 16) % (R - half);
-            const uint32_t old = atomicCAS(&vrow[pos], kInvalidSlot, u);
-            if (old != kInvalidSlot && old != u) atomicExch(&vrow[pos], u);
+        if (!done && lane == 0) {
+            const uint32_t p = half + ((u * 0x9E3779B1u + r * 0x85EBCA6Bu) >> 16) % (R - half);
+            atomicExch(&vrow[p], u);
         }
     }
+}
+
+// compaction: new_graph[old2new[u]][r] = old2new[graph[u][r]] (edges to removed rows dropped)
+__global__ void remap_graph_kernel(const uint32_t* __restrict__ graph, uint32_t n_old, uint32_t stride,
+                                   const uint32_t* __restrict__ old2new, uint32_t* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n_old * stride) return;
+    const uint32_t u = (uint32_t)(t / stride), r = (uint32_t)(t % stride);
+    const uint32_t nu = old2new[u];
+    if (nu == kInvalidSlot) return;
+    const uint32_t v = graph[t];
+    out[(size_t)nu * stride + r] = (v == kInvalidSlot || v >= n_old) ? kInvalidSlot : old2new[v];
 }
 }  // namespace
 
 void launch_stream_link(const uint64_t* cand, uint32_t n_new, uint32_t cand_stride, uint32_t first_slot, uint32_t R,
                         uint32_t* graph, uint32_t graph_stride, cudaStream_t stream) {
     if (n_new == 0) return;
-    stream_link_kernel<<<(n_new + 3) / 4, 128, 0, stream>>>(cand, n_new, cand_stride, first_slot, R, graph, graph_stride);
+    stream_link_fwd_kernel<<<(n_new + K7_WARPS - 1) / K7_WARPS, K7_WARPS * 32, 0, stream>>>(cand, n_new, cand_stride, first_slot,
+                                                                                            R, graph, graph_stride);
+    stream_link_rev_kernel<<<(n_new + 3) / 4, 128, 0, stream>>>(n_new, first_slot, R, graph, graph_stride);
+    g_kernel_launches += 2;
+}
+
+void launch_remap_graph(const uint32_t* graph, uint32_t n_old, uint32_t stride, const uint32_t* old2new, uint32_t* out,
+                        cudaStream_t stream) {
+    if (n_old == 0) return;
+    const size_t m = (size_t)n_old * stride;
+    remap_graph_kernel<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(graph, n_old, stride, old2new, out);
     g_kernel_launches += 1;
 }
 // ---- reachability of the graph from the entry-point sample -----------------------------------------------------

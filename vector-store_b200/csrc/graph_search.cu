@@ -69,8 +69,12 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
     a.metric = p.metric;
     a.out_keys = p.out_keys; a.out_dists = p.out_dists; a.out_counts = p.out_counts; a.out_packed = p.out_packed; a.self_base = p.self_base; a.counters = p.counters;
     a.out_stride = p.out_stride ? p.out_stride : p.k;
+    a.allow = p.allow;
+    a.allow_bits = p.allow_bits;
+    a.rk = p.allow != nullptr ? ((p.k + 31) / 32) * 32 : 0;
     const int cpl = pick_cpl((int)(p.x.row_bytes / 16));
-    if (p.q.n <= graph_search_small_batch()) {
+    // filtered ANN always runs the warp-per-query kernel (the second list lives there)
+    if (p.q.n <= graph_search_small_batch() && p.allow == nullptr) {
         // CTA-per-query kernel: 8 warps and up to 8 parents per iteration for one query
         a.search_width = a.search_width < 4 ? 8 : (a.search_width > 8 ? 8 : a.search_width);
         a.max_iters = p.max_iters ? p.max_iters : (2 * a.itopk) / a.search_width + 8;
@@ -88,7 +92,7 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
         return;
     }
     dim3 grid((p.q.n + K4_WARPS - 1) / K4_WARPS);
-    const size_t smem = (size_t)K4_WARPS * ((size_t)a.itopk * 8 + ((size_t)2 << bits) + (size_t)a.queue_cap * 8);
+    const size_t smem = (size_t)K4_WARPS * ((size_t)a.itopk * 8 + ((size_t)2 << bits) + (size_t)a.queue_cap * 8 + (size_t)a.rk * 8);
     switch (p.storage) {
         case VSB_ST_F32: launch_k4_f32(a, cpl, grid, smem, stream); break;
         case VSB_ST_F16: launch_k4_f16(a, cpl, grid, smem, stream); break;

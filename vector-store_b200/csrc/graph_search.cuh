@@ -46,6 +46,9 @@ struct K4Args {
     long long self_base;   // >= 0: query i is row self_base + i of x and is left out of its own result
     uint32_t out_stride;   // entries per query in out_packed (>= k; the rest is padded with kInvalidPacked)
     unsigned long long* counters;
+    const uint32_t* allow;  // filtered ANN: admissibility bitmap over (key & 2^48-1); only the FILTER instantiation reads it
+    uint64_t allow_bits;
+    uint32_t rk;            // length of the result list of the FILTER instantiation (k rounded up to 32)
 };
 
 __device__ __forceinline__ bool hash_insert(uint32_t* tab, uint32_t mask, uint32_t bits, uint32_t slot) {
@@ -213,7 +216,10 @@ constexpr int K4_MAX_WIDTH = 4;  // parents expanded per iteration (search_width
 template <int ST, int CPL>
 constexpr int k4_min_blocks() { return (ST == VSB_ST_I8 && CPL <= 2) ? 4 : 3; }
 
-template <int ST, int CPL>
+// FILTER = true (vsb_search_filtered): the traversal is unchanged, but every evaluated row whose key is admissible is
+// ALSO folded into a second list of rk entries, and that list is what the kernel emits.  The beam still walks through
+// inadmissible rows, exactly like usearch's predicate search (usearch.rs:224-248).
+template <int ST, int CPL, bool FILTER>
 __global__ void __launch_bounds__(K4_WARPS * 32, k4_min_blocks<ST, CPL>()) graph_search_kernel(K4Args a) {
     constexpr int E = Storage<ST>::ELEMS;
     constexpr bool kFloat = Storage<ST>::kFloat;
@@ -227,11 +233,15 @@ __global__ void __launch_bounds__(K4_WARPS * 32, k4_min_blocks<ST, CPL>()) graph
 
     const uint32_t hsize = 1u << a.hash_bits, hmask = hsize - 1;
     const uint32_t qcap = a.queue_cap;
-    const size_t per_warp = (size_t)a.itopk * 8 + (size_t)hsize * 2 + (size_t)qcap * 8;
+    const size_t per_warp = (size_t)a.itopk * 8 + (size_t)hsize * 2 + (size_t)qcap * 8 + (FILTER ? (size_t)a.rk * 8 : 0);
     uint64_t* list = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warp * per_warp);
     uint16_t* hash = reinterpret_cast<uint16_t*>(list + a.itopk);  // [hsize] 16-bit tags
     uint32_t* newq = reinterpret_cast<uint32_t*>(hash + hsize);   // [qcap] un-visited neighbour slots of this iteration
     float* newd = reinterpret_cast<float*>(newq + qcap);     // [qcap] their raw sums
+    uint64_t* rlist = reinterpret_cast<uint64_t*>(newd + qcap);  // [rk] FILTER: best admissible rows seen so far
+    if constexpr (FILTER) {
+        for (uint32_t i = lane; i < a.rk; i += 32) rlist[i] = kInvalidPacked;
+    }
     const LessBySlot less;
     const bool is_l2 = a.metric == VSB_METRIC_L2SQ;
     const bool is_cos = a.metric == VSB_METRIC_COS;
@@ -286,6 +296,17 @@ __global__ void __launch_bounds__(K4_WARPS * 32, k4_min_blocks<ST, CPL>()) graph
                 const uint32_t slot = newq[base + lane];
                 const float xn = is_cos ? __ldg(a.x_nrm + slot) : 0.0f;
                 res = pack_ds(finish_raw<ST>(newd[base + lane], a.metric, qn, xn), slot);
+            }
+            if constexpr (FILTER) {
+                uint64_t adm = kInvalidPacked;
+                if (res != kInvalidPacked) {
+                    const uint64_t row_id = a.keys[packed_lo(res)] & kRowMask48;
+                    if (row_id < a.allow_bits && (a.allow[row_id >> 5] >> (row_id & 31) & 1u)) adm = res;
+                }
+                if (__ballot_sync(kFullMask, adm < rlist[a.rk - 1]) != 0) {
+                    adm = warp_sort32(adm, lane, less);
+                    warp_list_merge(rlist, (int)a.rk, adm, lane, less);
+                }
             }
             if (__ballot_sync(kFullMask, res < worst) == 0) continue;  // nothing here can enter the list
             res = warp_sort32(res, lane, less);
@@ -371,10 +392,13 @@ __global__ void __launch_bounds__(K4_WARPS * 32, k4_min_blocks<ST, CPL>()) graph
         evaluate_queue();
     }
 
-    // ---- emit the first k live entries ----
+    // ---- emit the first k live entries (of the admissible list when filtering) ----
+    __syncwarp();
+    const uint64_t* src_list = FILTER ? rlist : list;
+    const uint32_t src_len = FILTER ? a.rk : a.itopk;
     uint32_t count = 0;
-    for (uint32_t b = 0; b < a.itopk; b += 32) {
-        const uint64_t e = list[b + lane];
+    for (uint32_t b = 0; b < src_len; b += 32) {
+        const uint64_t e = src_list[b + lane];
         const uint32_t slot = packed_lo(e) & ~kExpandedBit;
         bool valid = e != kInvalidPacked;
         if (valid && a.deny != nullptr && bit_test(a.deny, slot)) valid = false;
@@ -762,8 +786,13 @@ __global__ void __launch_bounds__(SEED_SCAN_WARPS * 32) seed_scan_kernel(const u
 
 template <int ST, int CPL>
 void launch_k4_inst(const K4Args& a, dim3 grid, size_t smem, cudaStream_t stream) {
-    cudaFuncSetAttribute(graph_search_kernel<ST, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    graph_search_kernel<ST, CPL><<<grid, K4_WARPS * 32, smem, stream>>>(a);
+    if (a.allow != nullptr) {
+        cudaFuncSetAttribute(graph_search_kernel<ST, CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        graph_search_kernel<ST, CPL, true><<<grid, K4_WARPS * 32, smem, stream>>>(a);
+        return;
+    }
+    cudaFuncSetAttribute(graph_search_kernel<ST, CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    graph_search_kernel<ST, CPL, false><<<grid, K4_WARPS * 32, smem, stream>>>(a);
 }
 
 template <int ST, int CPL>

@@ -1,43 +1,28 @@
-// index.cu — host side of libvsb200: the index object behind the C ABI of include/vsb200.h.
-//
-// Mirrors what `ThreadedUsearchIndex` + `usearch::Index` are to the reference
-// (crates/vector-store/src/vs_index/usearch.rs:162-251): opaque u64 keys, unique keys
-// (multi=false), explicit capacity (`reserve`), add / remove / search, and a live count.
-//
-// HBM layout (all sized by `capacity`, grown by vsb_reserve with a stream-ordered copy):
-//   rows   [cap][row_bytes]  storage-typed vectors, rows padded to 16 bytes
-//   sq,nrm [cap] f32         canonical sum of squares and its sqrt (cosine / L2 norm trick)
-//   keys   [cap] u64         slot -> key
-//   deny   [cap/32] u32      tombstone bitmap (remove() never moves rows)
-//   graph  [n_graphed][stride] u32   fixed-degree neighbour rows (built by vsb_build)
-//   seed_* [S]               contiguous copy of the entry-point sample ("upper layer")
-// Slots are append-only; slots >= n_graphed form the brute-force tail, so an added vector is
-// searchable as soon as vsb_add returns (dropping AsyncInProgress promises that).
+// index.cu — lifecycle, mutations and the C ABI of libvsb200 (include/vsb200.h).
+// The object model and the concurrency contract are described in index_impl.h; the search building blocks
+// live in index_search.cu, the graph build in index_build.cu, snapshots in snapshot_io.cu, the multi-device
+// router in sharded.cu.
 #include <algorithm>
-#include <atomic>
+#include <chrono>
 #include <cmath>
-#include <cstdarg>
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <new>
-#include <string>
-#include <unordered_map>
 #include <unordered_set>
-#include <vector>
 
-#include "../../include/vsb200.h"
-#include "kernels.h"
+#include <nvtx3/nvToolsExt.h>
+
+#include "index_impl.h"
+#include "sharded.h"
 
 namespace vsb {
 std::atomic<uint64_t> g_kernel_launches{0};
 std::atomic<uint64_t> g_tc_launches{0};
-}
+}  // namespace vsb
 
-namespace {
+namespace vsbi {
 
-thread_local std::string g_last_error;
+static thread_local std::string g_last_error;
 
 vsb_status fail(vsb_status st, const char* fmt, ...) {
     char buf[512];
@@ -49,209 +34,7 @@ vsb_status fail(vsb_status st, const char* fmt, ...) {
     return st;
 }
 
-#define CU(expr)                                                                                      \
-    do {                                                                                              \
-        cudaError_t e_ = (expr);                                                                      \
-        if (e_ != cudaSuccess)                                                                        \
-            return fail(e_ == cudaErrorMemoryAllocation ? VSB_EOOM : VSB_ECUDA, "%s: %s (%s:%d)", #expr, \
-                        cudaGetErrorString(e_), __FILE__, __LINE__);                                  \
-    } while (0)
-
-#define ST(expr)                        \
-    do {                                \
-        vsb_status s_ = (expr);         \
-        if (s_ != VSB_OK) return s_;    \
-    } while (0)
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-    DevBuf() = default;
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) {
-        o.p = nullptr;
-        o.bytes = 0;
-    }
-    DevBuf& operator=(DevBuf&& o) noexcept {
-        if (this != &o) {
-            release();
-            p = o.p;
-            bytes = o.bytes;
-            o.p = nullptr;
-            o.bytes = 0;
-        }
-        return *this;
-    }
-    ~DevBuf() { release(); }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-    }
-    // grow-only scratch (contents not preserved)
-    cudaError_t ensure(size_t want) {
-        if (want <= bytes) return cudaSuccess;
-        release();
-        size_t sz = want + want / 4;
-        cudaError_t e = cudaMalloc(&p, sz);
-        if (e != cudaSuccess) {
-            p = nullptr;
-            return e;
-        }
-        bytes = sz;
-        return cudaSuccess;
-    }
-    template <class T>
-    T* as() const { return static_cast<T*>(p); }
-};
-
-uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
-
-}  // namespace
-
-struct vsb_index {
-    std::mutex mu;
-    vsb_options opt{};
-    uint32_t dim = 0, row_bytes = 0;
-    int metric = 0, storage = 0, device = 0, sm_count = 148;
-    uint32_t degree = 32, graph_stride = 32, k_init = 64;
-    uint32_t itopk = 64, max_iters = 0, n_seeds = 32, min_graph_size = 4096, search_width = 1;
-    bool instrumented = false;
-
-    cudaStream_t stream = nullptr;
-    cudaStream_t last_stream = nullptr;
-
-    uint64_t capacity = 0;
-    uint32_t n_slots = 0, n_graphed = 0, n_seed_rows = 0;
-    uint64_t live = 0;
-    std::atomic<uint64_t> live_atomic{0};
-    std::atomic<uint64_t> capacity_atomic{0};
-    bool any_tombstone = false;
-
-    DevBuf rows, sq, nrm, keys, deny, graph;
-    DevBuf rows16, sq16, nrm16;   // VSB_FLAG_BF16_TRAVERSAL: bf16 copy of the rows for K4
-    bool trav16 = false;
-    uint32_t row_bytes16 = 0;
-    // VSB_FLAG_I8_TRAVERSAL (f32 storage, cosine): K4 walks a scaled-int8 copy (a quarter of the f32 bytes, dp4a),
-    // K3 re-ranks rr_mult8 * k candidates on the f32 rows.  The bf16 copy stays for the build and the seed tiles.
-    DevBuf rows8, sq8, nrm8, q8_rows, q8_sq, q8_nrm;
-    DevBuf reach_state;             // sample_seeds: reachability of the graph from the seed set
-    bool reach_fix = true;          // VSB_DISABLE_REACH_FIX=1 turns the extra seeds off
-    uint32_t reach_budget = 1024;   // at most this many extra seeds (one per unreached component)
-    uint32_t n_extra_seeds = 0;
-    bool trav8 = false;
-    uint32_t row_bytes8 = 0, rr_mult8 = 4;
-    DevBuf rr_packed;             // K4 -> K3 hand-over of the traversal shadow path
-    DevBuf seed_rows, seed_sq, seed_nrm, seed_slots;
-    DevBuf seed16_rows, seed16_sq, seed16_nrm;   // bf16 shadow of the seed block (f32 storage only)
-    DevBuf q16_rows, q16_sq, q16_nrm;            // bf16 shadow of the converted queries (f32 storage only)
-    DevBuf q_in, q_rows, q_sq, q_nrm, part, seed_part, tmp_keys, tmp_dists, counters, add_in, allow;
-    // certified TF32 candidate stage for exact search on f32 rows (exact_block)
-    DevBuf cert_state, fb_map, fb_rows, fb_sq, fb_nrm;
-    bool cert_enabled = true;     // VSB_DISABLE_CERT=1: exact f32 search always on the SIMT tiles
-    uint32_t cert_kp = 128;       // candidate list length of the certified TF32 stage (VSB_CERT_KP)
-    uint32_t cert_kp16 = 32;      // ... of the certified f16/bf16 tensor-core stage (VSB_CERT_KP16)
-    uint64_t cert_ok = 0, cert_fallback = 0, cert_scanned = 0;
-    std::unordered_map<uint64_t, uint32_t> key2slot;
-    std::vector<uint32_t> h_deny;
-
-    uint64_t last_evals = 0, last_parents = 0, last_queries = 0;
-
-    // optional CUDA-event timing of the search phases
-    enum Phase { PH_CONVERT = 0, PH_SEED, PH_GRAPH, PH_EXACT, PH_MERGE, PH_COUNT };
-    bool timing = false;
-    struct Timed { cudaEvent_t a, b; int phase; };
-    std::vector<Timed> timed;
-    uint64_t phase_ns[PH_COUNT] = {0, 0, 0, 0, 0};
-    uint64_t phase_launches[PH_COUNT] = {0, 0, 0, 0, 0};
-    void t_begin(int phase, cudaStream_t s) {
-        if (!timing) return;
-        Timed t;
-        t.phase = phase;
-        cudaEventCreate(&t.a);
-        cudaEventCreate(&t.b);
-        cudaEventRecord(t.a, s);
-        timed.push_back(t);
-    }
-    void t_end(cudaStream_t s) {
-        if (!timing) return;
-        cudaEventRecord(timed.back().b, s);
-    }
-    void t_resolve() {
-        for (auto& t : timed) {
-            float ms = 0.f;
-            if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
-                phase_ns[t.phase] += (uint64_t)((double)ms * 1e6);
-                phase_launches[t.phase] += 1;
-            }
-            cudaEventDestroy(t.a);
-            cudaEventDestroy(t.b);
-        }
-        timed.clear();
-    }
-
-    size_t hbm_bytes() const {
-        const DevBuf* all[] = {&rows, &sq, &nrm, &keys, &deny, &graph, &rows16, &sq16, &nrm16, &rr_packed, &seed_rows, &seed_sq, &seed_nrm, &seed_slots,
-                               &seed16_rows, &seed16_sq, &seed16_nrm, &q16_rows, &q16_sq, &q16_nrm,
-                               &q_in, &q_rows, &q_sq, &q_nrm, &part, &seed_part, &tmp_keys, &tmp_dists, &counters,
-                               &add_in, &allow, &cert_state, &fb_map, &fb_rows, &fb_sq, &fb_nrm, &rows8, &sq8, &nrm8, &q8_rows,
-                               &q8_sq, &q8_nrm, &reach_state};
-        size_t s = 0;
-        for (auto* b : all) s += b->bytes;
-        return s;
-    }
-
-    vsb::RowsView corpus_view() const {
-        vsb::RowsView v;
-        v.rows = rows.as<uint8_t>();
-        v.sq = sq.as<float>();
-        v.nrm = nrm.as<float>();
-        v.row_bytes = row_bytes;
-        v.n = n_slots;
-        return v;
-    }
-
-    vsb_status use_stream(cudaStream_t s) {
-        if (last_stream != nullptr && last_stream != s) CU(cudaStreamSynchronize(last_stream));
-        last_stream = s;
-        return VSB_OK;
-    }
-
-    vsb_status reserve(uint64_t cap);
-    vsb_status add(const uint64_t* k, const float* r, uint64_t n);
-    vsb_status remove(const uint64_t* k, uint64_t n, uint64_t* removed);
-    vsb_status build();
-    vsb_status exact_block(const vsb::RowsView& q, const vsb::RowsView& x, uint32_t x_lo, uint32_t x_hi,
-                           const uint32_t* deny_bm, const uint64_t* key_arr, const uint32_t* allow_bm,
-                           uint64_t allow_bits, uint32_t k, uint64_t* out_keys, float* out_dists,
-                           uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t s,
-                           bool approx_ok, const vsb::RowsView* shadow_q = nullptr,
-                           const vsb::RowsView* shadow_x = nullptr);
-    bool tc_enabled = true;       // tcgen05 path for the dense distance tiles (VSB_DISABLE_TC=1 turns it off)
-    uint32_t tc_min_rows = 8192;  // below this the SIMT K1 is used (launch + pipeline fill dominate)
-    vsb_status graph_block(const vsb::RowsView& qv, uint32_t nb, uint32_t k, uint32_t itopk_eff, uint64_t* g_keys,
-                           float* g_dists, uint32_t* counts_out, uint64_t* packed_out, const vsb::RowsView* q16_in,
-                           cudaStream_t s, long long self_base = -1);
-    vsb_status graph_from_knn(const uint64_t* knn, uint32_t n, uint32_t kin, const uint32_t* deny_bm);
-    vsb_status refine_graph();
-    uint32_t allpairs_prefix = 131072;  // rows of the exact all-pairs pass when n > allpairs_max
-    vsb_status stream_insert();
-    bool in_build = false;  // vsb_build runs its own refinement after streaming
-    vsb_status compact();
-    vsb_status sample_seeds(uint32_t n_rows);
-    uint32_t allpairs_max = 262144;   // up to this many rows the graph comes from exact all-pairs kNN lists
-    uint32_t refine_passes = 1;       // refinement passes after a streamed build
-    uint64_t churn_since_refine = 0;  // rows streamed in + rows removed since the graph was last (re)built / refined
-    uint32_t stream_threshold = 4096;  // un-graphed tail rows that trigger an automatic streaming insert
-    vsb_status search_dev(const float* d_q, uint64_t nq, uint32_t k, uint64_t* d_keys, float* d_dists,
-                          uint32_t* d_counts, cudaStream_t s, bool exact, const uint32_t* d_allow,
-                          uint64_t allow_bits);
-    vsb_status search_host(const float* queries, uint64_t nq, uint32_t k, uint64_t* keys_out, float* dists_out,
-                           uint32_t* counts_out, bool exact, const uint32_t* allow_bitmap, uint64_t allow_bits);
-};
-
-static uint32_t storage_row_bytes(int storage, uint32_t dim) {
+uint32_t storage_row_bytes(int storage, uint32_t dim) {
     uint64_t bits = 0;
     switch (storage) {
         case VSB_F32: bits = (uint64_t)dim * 32; break;
@@ -263,1006 +46,365 @@ static uint32_t storage_row_bytes(int storage, uint32_t dim) {
     return (uint32_t)(((bits + 127) / 128) * 16);
 }
 
-vsb_status vsb_index::reserve(uint64_t cap) {
-    if (cap <= capacity) return VSB_OK;
-    if (cap >= (1ull << 28)) return fail(VSB_EINVAL, "capacity %llu exceeds the 2^28 rows one shard holds", (unsigned long long)cap);
-    CU(cudaSetDevice(device));
-    const uint64_t words = (cap + 31) / 32;
-    DevBuf n_rows, n_sq, n_nrm, n_keys, n_deny, n_rows16, n_sq16, n_nrm16, n_rows8, n_sq8, n_nrm8;
-    auto alloc = [&](DevBuf& b, size_t bytes) -> cudaError_t {
-        cudaError_t e = cudaMalloc(&b.p, bytes ? bytes : 16);
-        if (e == cudaSuccess) b.bytes = bytes ? bytes : 16; else b.p = nullptr;
-        return e;
-    };
-    if (trav8) {
-        CU(alloc(n_rows8, cap * row_bytes8));
-        CU(alloc(n_sq8, cap * 4));
-        CU(alloc(n_nrm8, cap * 4));
-    }
-    CU(alloc(n_rows, cap * row_bytes));
-    CU(alloc(n_sq, cap * 4));
-    CU(alloc(n_nrm, cap * 4));
-    CU(alloc(n_keys, cap * 8));
-    CU(alloc(n_deny, words * 4));
-    if (trav16) {
-        CU(alloc(n_rows16, cap * row_bytes16));
-        CU(alloc(n_sq16, cap * 4));
-        CU(alloc(n_nrm16, cap * 4));
-    }
-    ST(use_stream(stream));
-    CU(cudaMemsetAsync(n_deny.p, 0, words * 4, stream));
-    if (n_slots > 0) {
-        CU(cudaMemcpyAsync(n_rows.p, rows.p, (size_t)n_slots * row_bytes, cudaMemcpyDeviceToDevice, stream));
-        CU(cudaMemcpyAsync(n_sq.p, sq.p, (size_t)n_slots * 4, cudaMemcpyDeviceToDevice, stream));
-        CU(cudaMemcpyAsync(n_nrm.p, nrm.p, (size_t)n_slots * 4, cudaMemcpyDeviceToDevice, stream));
-        CU(cudaMemcpyAsync(n_keys.p, keys.p, (size_t)n_slots * 8, cudaMemcpyDeviceToDevice, stream));
-        CU(cudaMemcpyAsync(n_deny.p, deny.p, (size_t)((n_slots + 31) / 32) * 4, cudaMemcpyDeviceToDevice, stream));
-        if (trav16) {
-            CU(cudaMemcpyAsync(n_rows16.p, rows16.p, (size_t)n_slots * row_bytes16, cudaMemcpyDeviceToDevice, stream));
-            CU(cudaMemcpyAsync(n_sq16.p, sq16.p, (size_t)n_slots * 4, cudaMemcpyDeviceToDevice, stream));
-            CU(cudaMemcpyAsync(n_nrm16.p, nrm16.p, (size_t)n_slots * 4, cudaMemcpyDeviceToDevice, stream));
+}  // namespace vsbi
+
+using vsbi::DevBuf;
+using vsbi::fail;
+using vsbi::round_up;
+
+// ---- phase timing of the search path --------------------------------------------------------------------------
+void vsb_index::t_begin(int phase, cudaStream_t s) {
+    if (!timing) return;
+    Timed t;
+    t.phase = phase;
+    cudaEventCreate(&t.a);
+    cudaEventCreate(&t.b);
+    cudaEventRecord(t.a, s);
+    timed.push_back(t);
+}
+void vsb_index::t_end(cudaStream_t s) {
+    if (!timing) return;
+    cudaEventRecord(timed.back().b, s);
+}
+void vsb_index::t_resolve() {
+    for (auto& t : timed) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            phase_ns[t.phase] += (uint64_t)((double)ms * 1e6);
+            phase_launches[t.phase] += 1;
         }
-        if (trav8) {
-            CU(cudaMemcpyAsync(n_rows8.p, rows8.p, (size_t)n_slots * row_bytes8, cudaMemcpyDeviceToDevice, stream));
-            CU(cudaMemcpyAsync(n_sq8.p, sq8.p, (size_t)n_slots * 4, cudaMemcpyDeviceToDevice, stream));
-            CU(cudaMemcpyAsync(n_nrm8.p, nrm8.p, (size_t)n_slots * 4, cudaMemcpyDeviceToDevice, stream));
-        }
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
     }
-    CU(cudaStreamSynchronize(stream));
-    if (trav8) {
-        std::swap(rows8, n_rows8);
-        std::swap(sq8, n_sq8);
-        std::swap(nrm8, n_nrm8);
+    timed.clear();
+}
+
+// ---- search-side stream hand-over and view lifetime -------------------------------------------------------------
+// The scratch set is shared by consecutive searches: a search on another stream than the previous one waits
+// (on the device, not on the host) for the event the previous search recorded.  The legacy default stream
+// (nullptr) is a stream like any other here.
+void vsb_index::reap_inflight(bool wait) {
+    while (!inflight.empty()) {
+        InFlight& f = inflight.front();
+        if (wait) cudaEventSynchronize(f.done);
+        else if (cudaEventQuery(f.done) != cudaSuccess) break;
+        cudaEventDestroy(f.done);
+        inflight.pop_front();
     }
-    std::swap(rows, n_rows);
-    std::swap(sq, n_sq);
-    std::swap(nrm, n_nrm);
-    std::swap(keys, n_keys);
-    std::swap(deny, n_deny);
-    if (trav16) {
-        std::swap(rows16, n_rows16);
-        std::swap(sq16, n_sq16);
-        std::swap(nrm16, n_nrm16);
-    }
-    h_deny.resize(words, 0u);
-    capacity = cap;
-    capacity_atomic.store(cap);
-    key2slot.reserve((size_t)cap);
+}
+
+vsb_status vsb_index::begin_search(cudaStream_t s) {
+    reap_inflight(false);
+    if (!inflight.empty() && inflight.back().stream != s) CU(cudaStreamWaitEvent(s, inflight.back().done, 0));
     return VSB_OK;
 }
 
-vsb_status vsb_index::add(const uint64_t* k, const float* r, uint64_t n) {
+vsb_status vsb_index::end_search(cudaStream_t s, const vsbi::View& v) {
+    InFlight f;
+    CU(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+    CU(cudaEventRecord(f.done, s));
+    f.stream = s;
+    f.view = v;
+    inflight.push_back(std::move(f));
+    return VSB_OK;
+}
+
+size_t vsb_index::hbm_bytes() {
+    vsbi::View v = snapshot();
+    size_t s = ss.bytes() + ms.bytes();
+    if (v.st) s += v.st->bytes();
+    if (v.gr) s += v.gr->g.bytes;
+    if (v.sd) s += v.sd->bytes();
+    return s;
+}
+
+vsb::RowsView vsb_index::rows_view(const vsbi::View& v) const {
+    vsb::RowsView r;
+    r.rows = v.st->rows.as<uint8_t>();
+    r.sq = v.st->sq.as<float>();
+    r.nrm = v.st->nrm.as<float>();
+    r.row_bytes = row_bytes;
+    r.n = v.n_slots;
+    return r;
+}
+
+// ---- mutators (mut_mu held by the caller) -----------------------------------------------------------------------
+vsb_status vsb_index::new_store(uint64_t cap, std::shared_ptr<vsbi::Store>& out) {
+    auto st = std::make_shared<vsbi::Store>();
+    const uint64_t words = (cap + 31) / 32;
+    st->capacity = cap;
+    CU(st->rows.alloc((size_t)cap * row_bytes));
+    CU(st->sq.alloc((size_t)cap * 4));
+    CU(st->nrm.alloc((size_t)cap * 4));
+    CU(st->keys.alloc((size_t)cap * 8));
+    CU(st->deny.alloc((size_t)words * 4));
+    if (trav16) {
+        CU(st->rows16.alloc((size_t)cap * row_bytes16));
+        CU(st->sq16.alloc((size_t)cap * 4));
+        CU(st->nrm16.alloc((size_t)cap * 4));
+    }
+    if (trav8) {
+        CU(st->rows8.alloc((size_t)cap * row_bytes8));
+        CU(st->sq8.alloc((size_t)cap * 4));
+        CU(st->nrm8.alloc((size_t)cap * 4));
+    }
+    CU(cudaMemsetAsync(st->deny.p, 0, (size_t)words * 4, mstream));
+    out = std::move(st);
+    return VSB_OK;
+}
+
+vsb_status vsb_index::reserve(uint64_t cap) {
+    const uint64_t have = w.st ? w.st->capacity : 0;
+    if (cap <= have) return VSB_OK;
+    if (cap >= (1ull << 28)) return fail(VSB_EINVAL, "capacity %llu exceeds the 2^28 rows one shard holds", (unsigned long long)cap);
+    CU(cudaSetDevice(device));
+    nvtxRangePushA("vsb_reserve");
+    std::shared_ptr<vsbi::Store> ns;
+    vsb_status st = new_store(cap, ns);
+    if (st != VSB_OK) {
+        nvtxRangePop();
+        return st;
+    }
+    const size_t n = w.n_slots;
+    if (n > 0) {
+        const vsbi::Store& o = *w.st;
+        auto cp = [&](const DevBuf& dst, const DevBuf& src, size_t bytes) {
+            return cudaMemcpyAsync(dst.p, src.p, bytes, cudaMemcpyDeviceToDevice, mstream);
+        };
+        CU(cp(ns->rows, o.rows, n * row_bytes));
+        CU(cp(ns->sq, o.sq, n * 4));
+        CU(cp(ns->nrm, o.nrm, n * 4));
+        CU(cp(ns->keys, o.keys, n * 8));
+        CU(cp(ns->deny, o.deny, ((n + 31) / 32) * 4));
+        if (trav16) {
+            CU(cp(ns->rows16, o.rows16, n * row_bytes16));
+            CU(cp(ns->sq16, o.sq16, n * 4));
+            CU(cp(ns->nrm16, o.nrm16, n * 4));
+        }
+        if (trav8) {
+            CU(cp(ns->rows8, o.rows8, n * row_bytes8));
+            CU(cp(ns->sq8, o.sq8, n * 4));
+            CU(cp(ns->nrm8, o.nrm8, n * 4));
+        }
+    }
+    CU(cudaStreamSynchronize(mstream));
+    w.st = ns;
+    h_deny.resize((cap + 31) / 32, 0u);
+    {
+        std::lock_guard<std::mutex> g(map_mu);
+        key2slot.reserve((size_t)cap);
+    }
+    publish();
+    nvtxRangePop();
+    return VSB_OK;
+}
+
+// row_status == nullptr: all-or-nothing (vsb_add).  Otherwise per-row verdicts (vsb_add_each).
+vsb_status vsb_index::add(const uint64_t* k, const float* r, uint64_t n, int32_t* row_status, uint64_t* n_added) {
+    if (n_added) *n_added = 0;
     if (n == 0) return VSB_OK;
     if (k == nullptr || r == nullptr) return fail(VSB_EINVAL, "null keys/rows");
-    if (live + n > capacity || (uint64_t)n_slots + n > capacity)
-        return fail(VSB_EFULL, "size %llu + %llu exceeds capacity %llu: reserve capacity ahead of insertions",
-                    (unsigned long long)n_slots, (unsigned long long)n, (unsigned long long)capacity);
+    const uint64_t cap = w.st ? w.st->capacity : 0;
+    std::vector<uint64_t> take;  // indices of the rows to insert (each mode with rejects only)
+    uint64_t nv = n;
     {
         std::unordered_set<uint64_t> batch;
         if (n > 1) batch.reserve((size_t)n);
+        bool any_reject = false;
         for (uint64_t i = 0; i < n; ++i) {
-            if (k[i] == 0xFFFFFFFFFFFFFFFFull) return fail(VSB_EINVAL, "key UINT64_MAX is reserved");
-            if (key2slot.count(k[i]) || (n > 1 && !batch.insert(k[i]).second))
-                return fail(VSB_EDUPKEY, "duplicate key %llu", (unsigned long long)k[i]);
+            int32_t verdict = VSB_OK;
+            if (k[i] == 0xFFFFFFFFFFFFFFFFull) verdict = VSB_EINVAL;
+            else if (key2slot.count(k[i]) || (n > 1 && !batch.insert(k[i]).second)) verdict = VSB_EDUPKEY;
+            if (row_status == nullptr) {
+                if (verdict == VSB_EINVAL) return fail(VSB_EINVAL, "key UINT64_MAX is reserved");
+                if (verdict == VSB_EDUPKEY) return fail(VSB_EDUPKEY, "duplicate key %llu", (unsigned long long)k[i]);
+            } else {
+                row_status[i] = verdict;
+                any_reject |= verdict != VSB_OK;
+            }
+        }
+        if (any_reject) {
+            for (uint64_t i = 0; i < n; ++i)
+                if (row_status[i] == VSB_OK) take.push_back(i);
+            nv = take.size();
+            if (nv == 0) return VSB_OK;
         }
     }
+    if (live + nv > cap)
+        return fail(VSB_EFULL, "size %llu + %llu exceeds capacity %llu: reserve capacity ahead of insertions",
+                    (unsigned long long)live, (unsigned long long)nv, (unsigned long long)cap);
     CU(cudaSetDevice(device));
-    ST(use_stream(stream));
+    if ((uint64_t)w.n_slots + nv > cap) {
+        // usearch reuses the slots of removed vectors; here the slot space is reclaimed by a compaction that keeps the
+        // graph (edges are renumbered, edges to removed rows dropped) — a few ms of HBM copies per GB
+        ST(compact(true));
+    }
+    vsbi::Store& st = *w.st;
+    std::vector<float> gathered;
+    std::vector<uint64_t> gathered_keys;
+    const float* src = r;
+    const uint64_t* src_keys = k;
+    if (!take.empty()) {
+        gathered.resize((size_t)nv * dim);
+        gathered_keys.resize((size_t)nv);
+        for (uint64_t j = 0; j < nv; ++j) {
+            std::memcpy(&gathered[(size_t)j * dim], r + take[j] * dim, (size_t)dim * 4);
+            gathered_keys[j] = k[take[j]];
+        }
+        src = gathered.data();
+        src_keys = gathered_keys.data();
+    }
     const uint64_t chunk_rows = std::max<uint64_t>(1, (256ull << 20) / ((uint64_t)dim * 4));
-    for (uint64_t b = 0; b < n; b += chunk_rows) {
-        const uint64_t nb = std::min(chunk_rows, n - b);
-        CU(add_in.ensure(nb * dim * 4));
-        CU(cudaMemcpyAsync(add_in.p, r + b * dim, nb * dim * 4, cudaMemcpyHostToDevice, stream));
-        const uint32_t s0 = n_slots + (uint32_t)b;
-        vsb::launch_convert_rows(storage, add_in.as<float>(), (uint32_t)nb, dim, rows.as<uint8_t>() + (size_t)s0 * row_bytes,
-                                 row_bytes, sq.as<float>() + s0, nrm.as<float>() + s0, stream);
+    for (uint64_t b = 0; b < nv; b += chunk_rows) {
+        const uint64_t nb = std::min(chunk_rows, nv - b);
+        CU(ms.q_in.ensure(nb * dim * 4));
+        CU(cudaMemcpyAsync(ms.q_in.p, src + b * dim, nb * dim * 4, cudaMemcpyHostToDevice, mstream));
+        const uint32_t s0 = w.n_slots + (uint32_t)b;
+        vsb::launch_convert_rows(storage, ms.q_in.as<float>(), (uint32_t)nb, dim, st.rows.as<uint8_t>() + (size_t)s0 * row_bytes,
+                                 row_bytes, st.sq.as<float>() + s0, st.nrm.as<float>() + s0, mstream);
         CU(cudaGetLastError());
         if (trav16) {
-            vsb::launch_convert_rows(VSB_BF16, add_in.as<float>(), (uint32_t)nb, dim,
-                                     rows16.as<uint8_t>() + (size_t)s0 * row_bytes16, row_bytes16, sq16.as<float>() + s0,
-                                     nrm16.as<float>() + s0, stream);
+            vsb::launch_convert_rows(VSB_BF16, ms.q_in.as<float>(), (uint32_t)nb, dim,
+                                     st.rows16.as<uint8_t>() + (size_t)s0 * row_bytes16, row_bytes16, st.sq16.as<float>() + s0,
+                                     st.nrm16.as<float>() + s0, mstream);
             CU(cudaGetLastError());
         }
         if (trav8) {
-            vsb::launch_convert_rows_i8s(add_in.as<float>(), (uint32_t)nb, dim, dim, rows8.as<uint8_t>() + (size_t)s0 * row_bytes8,
-                                         row_bytes8, sq8.as<float>() + s0, nrm8.as<float>() + s0, stream);
+            vsb::launch_convert_rows_i8s(ms.q_in.as<float>(), (uint32_t)nb, dim, dim, st.rows8.as<uint8_t>() + (size_t)s0 * row_bytes8,
+                                         row_bytes8, st.sq8.as<float>() + s0, st.nrm8.as<float>() + s0, mstream);
             CU(cudaGetLastError());
         }
-        CU(cudaMemcpyAsync(keys.as<uint64_t>() + s0, k + b, nb * 8, cudaMemcpyHostToDevice, stream));
-        CU(cudaStreamSynchronize(stream));  // add_in is reused by the next chunk
+        CU(cudaMemcpyAsync(st.keys.as<uint64_t>() + s0, src_keys + b, nb * 8, cudaMemcpyHostToDevice, mstream));
+        CU(cudaStreamSynchronize(mstream));  // q_in is reused by the next chunk
     }
-    for (uint64_t i = 0; i < n; ++i) key2slot.emplace(k[i], n_slots + (uint32_t)i);
-    n_slots += (uint32_t)n;
-    live += n;
-    live_atomic.store(live);
-    if (n_graphed > 0 && stream_threshold > 0 && n_slots - n_graphed >= stream_threshold) ST(stream_insert());
+    {
+        std::lock_guard<std::mutex> g(map_mu);
+        for (uint64_t i = 0; i < nv; ++i) key2slot.emplace(src_keys[i], w.n_slots + (uint32_t)i);
+    }
+    w.n_slots += (uint32_t)nv;
+    live += nv;
+    if (n_added) *n_added = nv;
+    publish();  // searchable from here on (brute-force tail)
+    if (w.n_graphed > 0 && stream_threshold > 0 && w.n_slots - w.n_graphed >= stream_threshold) {
+        ST(stream_insert());
+        publish();
+    }
     return VSB_OK;
 }
 
 vsb_status vsb_index::remove(const uint64_t* k, uint64_t n, uint64_t* removed) {
     uint64_t cnt = 0;
     uint32_t lo_word = 0xFFFFFFFFu, hi_word = 0;
-    for (uint64_t i = 0; i < n; ++i) {
-        auto it = key2slot.find(k[i]);
-        if (it == key2slot.end()) continue;
-        const uint32_t slot = it->second;
-        h_deny[slot >> 5] |= 1u << (slot & 31);
-        lo_word = std::min(lo_word, slot >> 5);
-        hi_word = std::max(hi_word, slot >> 5);
-        key2slot.erase(it);
-        ++cnt;
+    {
+        std::lock_guard<std::mutex> g(map_mu);
+        for (uint64_t i = 0; i < n; ++i) {
+            auto it = key2slot.find(k[i]);
+            if (it == key2slot.end()) continue;
+            const uint32_t slot = it->second;
+            h_deny[slot >> 5] |= 1u << (slot & 31);
+            lo_word = std::min(lo_word, slot >> 5);
+            hi_word = std::max(hi_word, slot >> 5);
+            key2slot.erase(it);
+            ++cnt;
+        }
     }
     if (cnt) {
         CU(cudaSetDevice(device));
-        ST(use_stream(stream));
-        CU(cudaMemcpyAsync(deny.as<uint32_t>() + lo_word, h_deny.data() + lo_word, (size_t)(hi_word - lo_word + 1) * 4,
-                           cudaMemcpyHostToDevice, stream));
-        CU(cudaStreamSynchronize(stream));
+        // tombstones are a live bitmap: a search that runs concurrently sees either state of a word
+        CU(cudaMemcpyAsync(w.st->deny.as<uint32_t>() + lo_word, h_deny.data() + lo_word, (size_t)(hi_word - lo_word + 1) * 4,
+                           cudaMemcpyHostToDevice, mstream));
+        CU(cudaStreamSynchronize(mstream));
         live -= cnt;
-        live_atomic.store(live);
-        any_tombstone = true;
+        n_tombstones += cnt;
+        w.any_tombstone = true;
         churn_since_refine += cnt;
+        publish();
     }
     if (removed) *removed = cnt;
     return VSB_OK;
 }
 
-// exact top-k of the queries `q` against rows [x_lo, x_hi) of `x` (K1 + K3)
-vsb_status vsb_index::exact_block(const vsb::RowsView& q, const vsb::RowsView& x, uint32_t x_lo, uint32_t x_hi,
-                                  const uint32_t* deny_bm, const uint64_t* key_arr, const uint32_t* allow_bm,
-                                  uint64_t allow_bits, uint32_t k, uint64_t* out_keys, float* out_dists,
-                                  uint32_t* out_counts, uint64_t* out_packed, int64_t self_base, cudaStream_t s,
-                                  bool approx_ok, const vsb::RowsView* shadow_q, const vsb::RowsView* shadow_x) {
-    vsb::ExactParams p;
-    p.storage = storage;
-    p.metric = metric;
-    p.q = q;
-    p.x = x;
-    p.x_lo = x_lo;
-    p.x_hi = x_hi;
-    p.deny = deny_bm;
-    p.keys = key_arr;
-    p.allow = allow_bm;
-    p.allow_bits = allow_bits;
-    const uint32_t extra = std::max<uint32_t>(16, k / 4) + (self_base >= 0 ? 1 : 0);
-    p.kp = round_up(k + extra, 32);
-    if (p.kp > 256) return fail(VSB_EINVAL, "k=%u too large for the exact path (max 200)", k);
-    // Tensor-core tiles: 16-bit storages multiply exactly, f32 rows run as TF32.  Any tiled stage (tensor core
-    // or SIMT) sums in its own order, so its lists are candidate-grade; for exact results on float storages K3
-    // CERTIFIES each query (no dropped row can reach or tie into the canonical top-k) and the queries it
-    // cannot certify fall through: TF32 tiles -> fp32 SIMT tiles -> canonical scan (K1c, needs no certificate).
-    // Integer storages (i8, b1) are exact in every stage and ordered by (distance, key) throughout.
-    const bool tc_shape = tc_enabled && vsb::exact_tc_supported(storage, metric) && (x_hi - x_lo) >= tc_min_rows;
-    const bool is_float = storage == VSB_F32 || storage == VSB_F16 || storage == VSB_BF16;
-    const bool certify = is_float && !approx_ok && cert_enabled;
-    bool tc = tc_shape && (approx_ok || storage != VSB_F32 || certify);
-    const uint32_t kp_simt = p.kp;
-    if (certify && tc) p.kp = std::min<uint32_t>(256, std::max<uint32_t>(p.kp, round_up(storage == VSB_F32 ? cert_kp : cert_kp16, 32)));
-    p.n_splits = tc ? vsb::exact_tc_pick_splits(q.n, x_hi - x_lo, sm_count)
-                    : vsb::exact_pick_splits(q.n, x_hi - x_lo, sm_count);
-    CU(part.ensure(vsb::exact_part_elems(q.n, p.n_splits, p.kp) * 8));
-    p.part = part.as<uint64_t>();
-    if (tc) {
-        if (shadow_q != nullptr && shadow_x != nullptr && !certify) {
-            // candidate stage on the bf16 shadow (half the bytes, kind::f16 rate); K3 re-ranks on the real rows
-            vsb::ExactParams pc = p;
-            pc.storage = VSB_BF16;
-            pc.q = *shadow_q;
-            pc.x = *shadow_x;
-            tc = vsb::launch_exact_candidates_tc(pc, s);
-        } else {
-            tc = vsb::launch_exact_candidates_tc(p, s);
-        }
-    }
-    if (!tc) {
-        if (p.kp != kp_simt) {  // the tensor-core launch was refused: plain SIMT with its own list length
-            p.kp = kp_simt;
-            p.n_splits = vsb::exact_pick_splits(q.n, x_hi - x_lo, sm_count);
-            CU(part.ensure(vsb::exact_part_elems(q.n, p.n_splits, p.kp) * 8));
-            p.part = part.as<uint64_t>();
-        }
-        vsb::launch_exact_candidates(p, s);
-    }
-    CU(cudaGetLastError());
-    if (!certify) {
-        vsb::launch_exact_rerank(p, k, out_keys, out_dists, out_counts, out_packed, self_base, s);
-        CU(cudaGetLastError());
-        return VSB_OK;
-    }
-
-    // cert_state: [0] = max row norm of the block, [1] = number of flagged queries, [2..] flags
-    CU(cert_state.ensure((size_t)(q.n + 2) * 4));
-    float* d_xmax = cert_state.as<float>();
-    uint32_t* d_count = cert_state.as<uint32_t>() + 1;
-    uint32_t* d_flags = cert_state.as<uint32_t>() + 2;
-    vsb::launch_max_norm(x.nrm, x_lo, x_hi, d_xmax, s);
-    vsb::ExactCert cert;
-    cert.x_nrm_max = d_xmax;
-    cert.flags = d_flags;
-    cert.count = d_count;
-    // An fp32 sum of `dim` products, in any order, is within dim * 2^-24 |q||x| of the real dot product (2^-23 per
-    // add if the adder truncates); candidate and canonical evaluation together: dim * 2^-22 with margin.
-    // TF32 additionally keeps only 10 mantissa bits of each operand: <= 2^-10 relative each, 2^-9 on the product.
-    const float rel_fp32 = (float)dim * 0x1p-22f;
-    const float rel_tf32 = 1.25f * 0x1p-9f + rel_fp32;
-    cert.sum = (float)dim * 0x1p-23f;
-    cert.rel = (tc && storage == VSB_F32) ? rel_tf32 : rel_fp32;
-
-    // flagged queries of one stage -> compact map (indices into the caller's query block) + gathered rows
-    std::vector<uint32_t> map, flags;
-    auto collect = [&](uint32_t n_stage, const std::vector<uint32_t>* prev) -> vsb_status {
-        flags.resize(n_stage);
-        CU(cudaMemcpyAsync(flags.data(), d_flags, (size_t)n_stage * 4, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-        std::vector<uint32_t> next;
-        for (uint32_t i = 0; i < n_stage; ++i)
-            if (flags[i]) next.push_back(prev ? (*prev)[i] : i);
-        map.swap(next);
-        const uint32_t nf = (uint32_t)map.size();
-        CU(fb_map.ensure((size_t)nf * 4));
-        CU(fb_rows.ensure((size_t)nf * q.row_bytes));
-        CU(fb_sq.ensure((size_t)nf * 4));
-        CU(fb_nrm.ensure((size_t)nf * 4));
-        CU(cudaMemcpyAsync(fb_map.p, map.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, s));
-        vsb::launch_gather_rows(q.rows, q.row_bytes, q.sq, q.nrm, fb_map.as<uint32_t>(), nf, fb_rows.as<uint8_t>(),
-                                fb_sq.as<float>(), fb_nrm.as<float>(), s);
-        CU(cudaStreamSynchronize(s));  // `map` is pageable and is rebuilt by the next stage
-        return VSB_OK;
-    };
-    auto read_count = [&](uint32_t* out) -> vsb_status {
-        CU(cudaMemcpyAsync(out, d_count, 4, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-        return VSB_OK;
-    };
-
-    CU(cudaMemsetAsync(d_count, 0, 4, s));
-    vsb::launch_exact_rerank(p, k, out_keys, out_dists, out_counts, out_packed, self_base, s, &cert);
-    CU(cudaGetLastError());
-    uint32_t n_flagged = 0;
-    ST(read_count(&n_flagged));
-    cert_ok += q.n - n_flagged;
-    cert_fallback += n_flagged;
-    if (n_flagged == 0) return VSB_OK;
-    ST(collect(q.n, nullptr));
-
-    vsb::ExactParams pf = p;
-    pf.q.rows = fb_rows.as<uint8_t>();
-    pf.q.sq = fb_sq.as<float>();
-    pf.q.nrm = fb_nrm.as<float>();
-    pf.q.n = (uint32_t)map.size();
-    if (tc && storage == VSB_F32) {
-        // second stage: full fp32 products on the SIMT tiles, same certificate with the fp32 bound
-        pf.kp = kp_simt;
-        pf.n_splits = vsb::exact_pick_splits(pf.q.n, x_hi - x_lo, sm_count);
-        CU(part.ensure(vsb::exact_part_elems(pf.q.n, pf.n_splits, pf.kp) * 8));
-        pf.part = part.as<uint64_t>();
-        vsb::launch_exact_candidates(pf, s);
-        CU(cudaGetLastError());
-        cert.rel = rel_fp32;
-        CU(cudaMemsetAsync(d_count, 0, 4, s));
-        vsb::launch_exact_rerank(pf, k, out_keys, out_dists, out_counts, out_packed, self_base, s, &cert,
-                                 fb_map.as<uint32_t>());
-        CU(cudaGetLastError());
-        ST(read_count(&n_flagged));
-        if (n_flagged == 0) return VSB_OK;
-        const std::vector<uint32_t> prev = map;
-        ST(collect(pf.q.n, &prev));
-        pf.q.n = (uint32_t)map.size();
-    }
-
-    // last stage: canonical scan of the whole block for what is left
-    cert_scanned += pf.q.n;
-    pf.kp = round_up(k + (self_base >= 0 ? 1 : 0), 32);
-    const uint32_t scan_splits = vsb::exact_scan_pick_splits(pf.q.n, x_hi - x_lo, sm_count);
-    pf.n_splits = scan_splits;
-    const uint32_t lists = vsb::exact_scan_lists_per_query(scan_splits);
-    CU(part.ensure(vsb::exact_part_elems(pf.q.n, lists, pf.kp) * 8));
-    pf.part = part.as<uint64_t>();
-    vsb::launch_exact_scan(pf, k, s);
-    CU(cudaGetLastError());
-    pf.n_splits = lists;
-    vsb::launch_exact_rerank(pf, k, out_keys, out_dists, out_counts, out_packed, self_base, s, nullptr,
-                             fb_map.as<uint32_t>());
-    CU(cudaGetLastError());
-    return VSB_OK;
-}
-
-// Tombstone compaction (part of vsb_build): live rows are gathered to the front in slot order, the key map is
-// rebuilt and the tombstone bitmap cleared, so a long-running delete/update stream does not leak HBM.
-vsb_status vsb_index::compact() {
+// Tombstone compaction: live rows are gathered to the front in slot order into a NEW store (the old one keeps
+// serving running searches), the key map is renumbered, the tombstone bitmap cleared.  keep_graph: the graph rows
+// are renumbered too (edges to removed rows dropped), so the index stays navigable without a rebuild.
+vsb_status vsb_index::compact(bool keep_graph) {
+    const uint32_t n_old = w.n_slots;
     std::vector<uint32_t> live_slots;
     live_slots.reserve((size_t)live);
-    for (uint32_t i = 0; i < n_slots; ++i)
+    for (uint32_t i = 0; i < n_old; ++i)
         if (!(h_deny[i >> 5] >> (i & 31) & 1u)) live_slots.push_back(i);
     const uint32_t m = (uint32_t)live_slots.size();
-    if (m != n_slots) {
-        DevBuf d_slots, n_rows, n_sq, n_nrm, n_keys, n_rows16, n_sq16, n_nrm16, n_rows8, n_sq8, n_nrm8;
-        CU(d_slots.ensure(std::max<size_t>((size_t)m * 4, 16)));
-        CU(cudaMemcpyAsync(d_slots.p, live_slots.data(), (size_t)m * 4, cudaMemcpyHostToDevice, stream));
-        auto alloc = [&](DevBuf& b, size_t bytes) -> cudaError_t {
-            cudaError_t e = cudaMalloc(&b.p, bytes ? bytes : 16);
-            if (e == cudaSuccess) b.bytes = bytes ? bytes : 16; else b.p = nullptr;
-            return e;
-        };
-        CU(alloc(n_rows, (size_t)capacity * row_bytes));
-        CU(alloc(n_sq, (size_t)capacity * 4));
-        CU(alloc(n_nrm, (size_t)capacity * 4));
-        CU(alloc(n_keys, (size_t)capacity * 8));
-        vsb::launch_gather_rows(rows.as<uint8_t>(), row_bytes, sq.as<float>(), nrm.as<float>(), d_slots.as<uint32_t>(), m,
-                                n_rows.as<uint8_t>(), n_sq.as<float>(), n_nrm.as<float>(), stream);
-        vsb::launch_gather_u64(keys.as<uint64_t>(), d_slots.as<uint32_t>(), m, n_keys.as<uint64_t>(), stream);
-        if (trav16) {
-            CU(alloc(n_rows16, (size_t)capacity * row_bytes16));
-            CU(alloc(n_sq16, (size_t)capacity * 4));
-            CU(alloc(n_nrm16, (size_t)capacity * 4));
-            vsb::launch_gather_rows(rows16.as<uint8_t>(), row_bytes16, sq16.as<float>(), nrm16.as<float>(),
-                                    d_slots.as<uint32_t>(), m, n_rows16.as<uint8_t>(), n_sq16.as<float>(),
-                                    n_nrm16.as<float>(), stream);
-        }
-        if (trav8) {
-            CU(alloc(n_rows8, (size_t)capacity * row_bytes8));
-            CU(alloc(n_sq8, (size_t)capacity * 4));
-            CU(alloc(n_nrm8, (size_t)capacity * 4));
-            vsb::launch_gather_rows(rows8.as<uint8_t>(), row_bytes8, sq8.as<float>(), nrm8.as<float>(), d_slots.as<uint32_t>(),
-                                    m, n_rows8.as<uint8_t>(), n_sq8.as<float>(), n_nrm8.as<float>(), stream);
-        }
-        CU(cudaGetLastError());
-        std::vector<uint64_t> h_keys(m);
-        CU(cudaMemcpyAsync(h_keys.data(), n_keys.p, (size_t)m * 8, cudaMemcpyDeviceToHost, stream));
-        CU(cudaMemsetAsync(deny.p, 0, deny.bytes, stream));
-        CU(cudaStreamSynchronize(stream));
-        std::swap(rows, n_rows);
-        std::swap(sq, n_sq);
-        std::swap(nrm, n_nrm);
-        std::swap(keys, n_keys);
-        if (trav16) {
-            std::swap(rows16, n_rows16);
-            std::swap(sq16, n_sq16);
-            std::swap(nrm16, n_nrm16);
-        }
-        if (trav8) {
-            std::swap(rows8, n_rows8);
-            std::swap(sq8, n_sq8);
-            std::swap(nrm8, n_nrm8);
-        }
-        std::fill(h_deny.begin(), h_deny.end(), 0u);
-        key2slot.clear();
-        for (uint32_t i = 0; i < m; ++i) key2slot.emplace(h_keys[i], i);
-        n_slots = m;
-        n_graphed = 0;
-        n_seed_rows = 0;
-    }
-    any_tombstone = false;
-    return VSB_OK;
-}
-
-vsb_status vsb_index::build() {
-    CU(cudaSetDevice(device));
-    ST(use_stream(stream));
-    if (any_tombstone) ST(compact());
-    struct Flag {
-        bool& f;
-        explicit Flag(bool& r) : f(r) { f = true; }
-        ~Flag() { f = false; }
-    } building(in_build);
-    churn_since_refine = 0;
-    if (live < min_graph_size || !vsb::graph_search_supported(row_bytes)) {
-        n_graphed = 0;
-        n_seed_rows = 0;
+    if (m == n_old) {
+        w.any_tombstone = false;
+        n_tombstones = 0;
         return VSB_OK;
     }
-    // All-pairs kNN lists cost 2*n^2*D flop: above `allpairs_max` rows only the first `allpairs_max` rows are
-    // built that way and the remaining rows are linked in with the streaming insert (K7, O(n log n)).
-    const uint32_t n = n_slots <= allpairs_max ? n_slots : std::min<uint32_t>(n_slots, allpairs_prefix);
-    const uint32_t R = degree;
-    const uint32_t kin = std::min<uint32_t>(k_init, 128);
-    DevBuf knn;
-    CU(knn.ensure((size_t)n * kin * 8));
-    const vsb::RowsView x = corpus_view();
-    const uint32_t* deny_bm = any_tombstone ? deny.as<uint32_t>() : nullptr;
-    // f32 storage: the all-pairs candidate stage runs on a temporary bf16 copy (kNN lists only need
-    // candidate-grade distances; K3 re-evaluates the survivors on the f32 rows in the canonical order)
-    DevBuf sh_rows, sh_sq, sh_nrm;
-    vsb::RowsView shx;
-    const bool use_shadow = storage == VSB_F32 && tc_enabled && n >= tc_min_rows;
-    if (use_shadow) {
-        const uint32_t dim_pad = row_bytes / 4;
-        shx.row_bytes = ((dim_pad * 2 + 15) / 16) * 16;
-        shx.n = n;
-        CU(sh_rows.ensure((size_t)n * shx.row_bytes));
-        CU(sh_sq.ensure((size_t)n * 4));
-        CU(sh_nrm.ensure((size_t)n * 4));
-        vsb::launch_convert_rows(VSB_BF16, reinterpret_cast<const float*>(x.rows), n, dim_pad, sh_rows.as<uint8_t>(),
-                                 shx.row_bytes, sh_sq.as<float>(), sh_nrm.as<float>(), stream);
+    nvtxRangePushA("vsb_compact");
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, mstream);
+    const vsbi::Store& o = *w.st;
+    std::shared_ptr<vsbi::Store> ns;
+    ST(new_store(o.capacity, ns));
+    DevBuf d_slots, d_map;
+    CU(d_slots.alloc(std::max<size_t>((size_t)m * 4, 16)));
+    CU(cudaMemcpyAsync(d_slots.p, live_slots.data(), (size_t)m * 4, cudaMemcpyHostToDevice, mstream));
+    vsb::launch_gather_rows(o.rows.as<uint8_t>(), row_bytes, o.sq.as<float>(), o.nrm.as<float>(), d_slots.as<uint32_t>(), m,
+                            ns->rows.as<uint8_t>(), ns->sq.as<float>(), ns->nrm.as<float>(), mstream);
+    vsb::launch_gather_u64(o.keys.as<uint64_t>(), d_slots.as<uint32_t>(), m, ns->keys.as<uint64_t>(), mstream);
+    if (trav16)
+        vsb::launch_gather_rows(o.rows16.as<uint8_t>(), row_bytes16, o.sq16.as<float>(), o.nrm16.as<float>(),
+                                d_slots.as<uint32_t>(), m, ns->rows16.as<uint8_t>(), ns->sq16.as<float>(),
+                                ns->nrm16.as<float>(), mstream);
+    if (trav8)
+        vsb::launch_gather_rows(o.rows8.as<uint8_t>(), row_bytes8, o.sq8.as<float>(), o.nrm8.as<float>(), d_slots.as<uint32_t>(),
+                                m, ns->rows8.as<uint8_t>(), ns->sq8.as<float>(), ns->nrm8.as<float>(), mstream);
+    CU(cudaGetLastError());
+    std::vector<uint32_t> old2new((size_t)n_old, vsb::kInvalidSlot);
+    for (uint32_t i = 0; i < m; ++i) old2new[live_slots[i]] = i;
+    uint32_t new_graphed = 0;
+    std::shared_ptr<vsbi::Graph> ng;
+    if (keep_graph && w.n_graphed > 0) {
+        new_graphed = (uint32_t)(std::lower_bound(live_slots.begin(), live_slots.end(), w.n_graphed) - live_slots.begin());
+        CU(d_map.alloc((size_t)n_old * 4));
+        CU(cudaMemcpyAsync(d_map.p, old2new.data(), (size_t)n_old * 4, cudaMemcpyHostToDevice, mstream));
+        ng = std::make_shared<vsbi::Graph>();
+        ng->cap_rows = o.capacity;
+        CU(ng->g.alloc((size_t)o.capacity * graph_stride * 4));
+        vsb::launch_remap_graph(w.gr->g.as<uint32_t>(), w.n_graphed, graph_stride, d_map.as<uint32_t>(), ng->g.as<uint32_t>(), mstream);
         CU(cudaGetLastError());
-        shx.rows = sh_rows.as<uint8_t>();
-        shx.sq = sh_sq.as<float>();
-        shx.nrm = sh_nrm.as<float>();
     }
-    const bool btime = getenv("VSB_BUILD_TIMING") != nullptr;
-    cudaEvent_t ev[2];
-    if (btime) {
-        for (auto& e : ev) cudaEventCreate(&e);
-        cudaEventRecord(ev[0], stream);
-    }
-    const uint32_t QB = 16384;
-    for (uint32_t b0 = 0; b0 < n; b0 += QB) {
-        vsb::RowsView q;
-        q.n = std::min(QB, n - b0);
-        q.rows = x.rows + (size_t)b0 * row_bytes;
-        q.sq = x.sq + b0;
-        q.nrm = x.nrm + b0;
-        q.row_bytes = row_bytes;
-        vsb::RowsView shq = shx;
-        if (use_shadow) {
-            shq.n = q.n;
-            shq.rows = shx.rows + (size_t)b0 * shx.row_bytes;
-            shq.sq = shx.sq + b0;
-            shq.nrm = shx.nrm + b0;
-        }
-        ST(exact_block(q, x, 0, n, deny_bm, keys.as<uint64_t>(), nullptr, 0, kin, nullptr, nullptr, nullptr,
-                       knn.as<uint64_t>() + (size_t)b0 * kin, (int64_t)b0, stream, true, use_shadow ? &shq : nullptr,
-                       use_shadow ? &shx : nullptr));
-    }
-    sh_rows.release();
-    sh_sq.release();
-    sh_nrm.release();
-    if (btime) {
-        cudaEventRecord(ev[1], stream);
-        cudaEventSynchronize(ev[1]);
-        float t = 0.f;
-        cudaEventElapsedTime(&t, ev[0], ev[1]);
-        fprintf(stderr, "[vsb200 build] exact all-pairs kNN lists (K1+K3) over %u rows: %.1f ms\n", n, t);
-        cudaEventRecord(ev[0], stream);
-    }
-    ST(graph_from_knn(knn.as<uint64_t>(), n, kin, deny_bm));
-    knn.release();
-    ST(sample_seeds(n));
-    if (btime) {
-        cudaEventRecord(ev[1], stream);
-        cudaEventSynchronize(ev[1]);
-        float t = 0.f;
-        cudaEventElapsedTime(&t, ev[0], ev[1]);
-        fprintf(stderr, "[vsb200 build] prune + reverse + merge + seeds: %.1f ms\n", t);
-        cudaEventRecord(ev[0], stream);
-    }
-    if (n < n_slots) {
-        // large index: link the remaining rows with the streaming insert (K7), then rebuild every row's
-        // list from an ANN search over that navigable graph and prune it exactly like the all-pairs lists
-        ST(stream_insert());
-        ST(sample_seeds(n_slots));  // entry points drawn from every row, not only the all-pairs prefix
-        if (btime) {
-            cudaEventRecord(ev[1], stream);
-            cudaEventSynchronize(ev[1]);
-            float t = 0.f;
-            cudaEventElapsedTime(&t, ev[0], ev[1]);
-            fprintf(stderr, "[vsb200 build] streaming insert of %u rows (K7): %.1f ms\n", n_slots - n, t);
-            cudaEventRecord(ev[0], stream);
-        }
-        if (refine_passes > 0) {
-            for (uint32_t pass = 0; pass < refine_passes; ++pass) ST(refine_graph());
-            ST(sample_seeds(n_slots));  // reachability of the FINAL graph from the entry points
-            if (btime) {
-                cudaEventRecord(ev[1], stream);
-                cudaEventSynchronize(ev[1]);
-                float t = 0.f;
-                cudaEventElapsedTime(&t, ev[0], ev[1]);
-                fprintf(stderr, "[vsb200 build] %u refine pass(es) (K4 kNN lists + K6): %.1f ms\n", refine_passes, t);
-            }
-        }
-    }
-    if (btime)
-        for (auto& e : ev) cudaEventDestroy(e);
-    return VSB_OK;
-}
-
-// K6 pipeline: packed kNN lists [n][kin] -> fixed-degree graph rows (replaces `graph`, sets n_graphed = n)
-vsb_status vsb_index::graph_from_knn(const uint64_t* knn, uint32_t n, uint32_t kin, const uint32_t* deny_bm) {
-    const uint32_t R = degree;
-    DevBuf fwd, rev, rev_cnt, scratch;
-    CU(fwd.ensure((size_t)n * R * 4));
-    CU(rev.ensure((size_t)n * R * 4));
-    CU(rev_cnt.ensure((size_t)n * 4));
-    vsb::launch_prune_detour(knn, n, kin, R, deny_bm, fwd.as<uint32_t>(), stream);
-    CU(cudaGetLastError());
-    const size_t sb = vsb::reverse_edges_scratch_bytes(n, R);
-    CU(scratch.ensure(sb));
-    vsb::launch_reverse_edges(fwd.as<uint32_t>(), n, R, rev.as<uint32_t>(), rev_cnt.as<uint32_t>(), scratch.p,
-                              scratch.bytes, stream);
-    CU(cudaGetLastError());
-    scratch.release();
-    DevBuf new_graph;
-    CU(new_graph.ensure((size_t)std::max<uint64_t>(capacity, n) * graph_stride * 4));  // room for streamed rows
-    vsb::launch_merge_graph(fwd.as<uint32_t>(), rev.as<uint32_t>(), rev_cnt.as<uint32_t>(), n, R,
-                            new_graph.as<uint32_t>(), graph_stride, stream);
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(stream));
-    std::swap(graph, new_graph);
-    n_graphed = n;
-    return VSB_OK;
-}
-
-// One refinement pass over a complete (streamed) graph: every row searches the graph for its own
-// k_init nearest rows (K4, beam = expansion_add) and the lists go through the K6 pipeline again.
-vsb_status vsb_index::refine_graph() {
-    const uint32_t n = n_graphed;
-    if (n == 0) return VSB_OK;
-    const uint32_t kin = std::min<uint32_t>(k_init, 128);
-    const uint32_t ef_add = opt.expansion_add ? opt.expansion_add : 128;
-    const uint32_t ef = std::min<uint32_t>(round_up(std::max(ef_add, kin + 1), 32), 512);
-    const uint32_t* deny_bm = any_tombstone ? deny.as<uint32_t>() : nullptr;
-    DevBuf knn;
-    CU(knn.ensure((size_t)n * kin * 8));
-    const uint32_t QB = 16384;
-    for (uint32_t b0 = 0; b0 < n; b0 += QB) {
-        const uint32_t nb = std::min(QB, n - b0);
-        vsb::RowsView qv;
-        qv.rows = rows.as<uint8_t>() + (size_t)b0 * row_bytes;
-        qv.sq = sq.as<float>() + b0;
-        qv.nrm = nrm.as<float>() + b0;
-        qv.row_bytes = row_bytes;
-        qv.n = nb;
-        vsb::RowsView q16;
-        if (trav16) {
-            q16.rows = rows16.as<uint8_t>() + (size_t)b0 * row_bytes16;
-            q16.sq = sq16.as<float>() + b0;
-            q16.nrm = nrm16.as<float>() + b0;
-            q16.row_bytes = row_bytes16;
-            q16.n = nb;
-        }
-        ST(graph_block(qv, nb, kin, ef, nullptr, nullptr, nullptr, knn.as<uint64_t>() + (size_t)b0 * kin,
-                       trav16 ? &q16 : nullptr, stream, (long long)b0));
-    }
-    ST(graph_from_knn(knn.as<uint64_t>(), n, kin, deny_bm));
-    return VSB_OK;
-}
-
-// Entry-point sample ("upper layer"): a stride permutation of the live slots below n_rows
-// (deterministic, seed-shifted), gathered into a contiguous block (+ bf16 shadow for f32 storage).
-vsb_status vsb_index::sample_seeds(uint32_t n) {
-    const vsb::RowsView x = corpus_view();
-    uint64_t live_below = 0;
-    for (uint32_t w = 0; w < (n + 31) / 32; ++w) live_below += __builtin_popcount(~h_deny[w]);
-    if (n % 32) live_below -= 32 - (n % 32);
-    // entry-point sample: a stride permutation of the live slots (deterministic, seed-shifted)
-    uint32_t S = 256;
-    const double target = 4.0 * std::sqrt((double)live_below);
-    while (S < target && S < 8192) S <<= 1;
-    if (S > live_below / 4) S = (uint32_t)std::max<uint64_t>(32, live_below / 4);
-    std::vector<uint32_t> h_seeds;
-    h_seeds.reserve(S);
+    CU(cudaStreamSynchronize(mstream));
     {
-        uint64_t step = (uint64_t)((double)n * 0.6180339887498949) | 1ull;
-        auto gcd = [](uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; };
-        while (gcd(step, n) != 1) step += 2;
-        uint64_t pos = opt.seed % n;
-        for (uint32_t i = 0; i < n && h_seeds.size() < S; ++i) {
-            const uint32_t slot = (uint32_t)pos;
-            pos = (pos + step) % n;
-            if (h_deny[slot >> 5] >> (slot & 31) & 1u) continue;
-            h_seeds.push_back(slot);
-        }
+        std::lock_guard<std::mutex> g(map_mu);
+        for (auto& kv : key2slot) kv.second = old2new[kv.second];
     }
-    S = (uint32_t)h_seeds.size();
-    // every live graph node must be reachable from the seed set: expand the frontier from the sample to a fixed
-    // point, then promote the first unreached live node to an extra seed and continue, once per lost component
-    uint32_t extra_seeds = 0;
-    if (n_graphed >= n && n > 0 && S > 0 && reach_fix) {
-        CU(reach_state.ensure((size_t)n + 16));
-        uint8_t* st = reach_state.as<uint8_t>();
-        uint32_t* flag = reinterpret_cast<uint32_t*>(st + (((size_t)n + 7) / 8) * 8);  // [0] changed, [1] first unreached
-        CU(seed_slots.ensure((size_t)(S + reach_budget) * 4));
-        CU(cudaMemsetAsync(st, 0, n, stream));
-        CU(cudaMemcpyAsync(seed_slots.p, h_seeds.data(), (size_t)S * 4, cudaMemcpyHostToDevice, stream));
-        vsb::launch_reach_mark(st, seed_slots.as<uint32_t>(), S, stream);
-        const uint32_t* deny_bm = any_tombstone ? deny.as<uint32_t>() : nullptr;
-        auto expand = [&]() -> vsb_status {
-            for (int round = 0; round < 4096; ++round) {
-                CU(cudaMemsetAsync(flag, 0, 4, stream));
-                for (int i = 0; i < 4; ++i)
-                    vsb::launch_reach_step(graph.as<uint32_t>(), n, graph_stride, degree, st, flag, stream);
-                uint32_t changed = 0;
-                CU(cudaMemcpyAsync(&changed, flag, 4, cudaMemcpyDeviceToHost, stream));
-                CU(cudaStreamSynchronize(stream));
-                if (!changed) break;
-            }
-            return VSB_OK;
-        };
-        ST(expand());
-        while (extra_seeds < reach_budget) {
-            CU(cudaMemsetAsync(flag + 1, 0xFF, 4, stream));
-            vsb::launch_first_unreached(st, deny_bm, n, flag + 1, stream);
-            uint32_t first = 0xFFFFFFFFu;
-            CU(cudaMemcpyAsync(&first, flag + 1, 4, cudaMemcpyDeviceToHost, stream));
-            CU(cudaStreamSynchronize(stream));
-            if (first == 0xFFFFFFFFu) break;
-            h_seeds.push_back(first);
-            ++extra_seeds;
-            CU(cudaMemsetAsync(st + first, 1, 1, stream));
-            ST(expand());
-        }
-        CU(cudaGetLastError());
-        S = (uint32_t)h_seeds.size();
-    }
-    n_extra_seeds = extra_seeds;
-    CU(seed_slots.ensure((size_t)S * 4));
-    CU(seed_rows.ensure((size_t)S * row_bytes));
-    CU(seed_sq.ensure((size_t)S * 4));
-    CU(seed_nrm.ensure((size_t)S * 4));
-    CU(cudaMemcpyAsync(seed_slots.p, h_seeds.data(), (size_t)S * 4, cudaMemcpyHostToDevice, stream));
-    vsb::launch_gather_rows(x.rows, row_bytes, x.sq, x.nrm, seed_slots.as<uint32_t>(), S, seed_rows.as<uint8_t>(),
-                            seed_sq.as<float>(), seed_nrm.as<float>(), stream);
-    CU(cudaGetLastError());
-    if (storage == VSB_F32) {
-        const uint32_t dim_pad = row_bytes / 4;
-        const uint32_t rb16 = ((dim_pad * 2 + 15) / 16) * 16;
-        CU(seed16_rows.ensure((size_t)S * rb16));
-        CU(seed16_sq.ensure((size_t)S * 4));
-        CU(seed16_nrm.ensure((size_t)S * 4));
-        vsb::launch_convert_rows(VSB_BF16, seed_rows.as<float>(), S, dim_pad, seed16_rows.as<uint8_t>(), rb16,
-                                 seed16_sq.as<float>(), seed16_nrm.as<float>(), stream);
-        CU(cudaGetLastError());
-    }
-    CU(cudaStreamSynchronize(stream));
-    n_seed_rows = S;
-    return VSB_OK;
-}
-
-// Seeds + K4 (+ K3 re-rank on the bf16-traversal path) for `nb` converted queries `qv`.
-//   out_keys/out_dists/out_counts : user-facing top-k (nullable when packed_out is used)
-//   packed_out                    : raw K4 list (packed ord(dist)<<32|slot, [nb][k]) — used by the streaming insert
-//   q16_in                        : bf16 copy of the queries if the caller already has one (corpus rows), else built here
-vsb_status vsb_index::graph_block(const vsb::RowsView& qv, uint32_t nb, uint32_t k, uint32_t itopk_eff,
-                                  uint64_t* g_keys, float* g_dists, uint32_t* counts_out, uint64_t* packed_out,
-                                  const vsb::RowsView* q16_in, cudaStream_t s, long long self_base) {
-    const vsb::RowsView x = corpus_view();
-    const uint32_t* deny_bm = any_tombstone ? deny.as<uint32_t>() : nullptr;
-    const bool have_tail = counts_out == nullptr;  // the caller merges and counts later
-    uint32_t* o_counts = counts_out;
-    const bool rerank = trav16 && packed_out == nullptr;
-    // ---- bf16 shadow of the queries (f32 storage: tensor-core seed layer and/or bf16 traversal) ----
-    bool seed_tc = tc_enabled && vsb::exact_tc_supported(storage, metric) && nb >= 16;
-    vsb::RowsView q16v;
-    if (q16_in != nullptr) {
-        q16v = *q16_in;
-    } else if (storage == VSB_F32 && (seed_tc || trav16)) {
-        CU(q16_rows.ensure((size_t)nb * row_bytes16));
-        CU(q16_sq.ensure((size_t)nb * 4));
-        CU(q16_nrm.ensure((size_t)nb * 4));
-        vsb::launch_convert_rows(VSB_BF16, reinterpret_cast<const float*>(qv.rows), nb, row_bytes / 4, q16_rows.as<uint8_t>(),
-                                 row_bytes16, q16_sq.as<float>(), q16_nrm.as<float>(), s);
-        CU(cudaGetLastError());
-        q16v.rows = q16_rows.as<uint8_t>();
-        q16v.sq = q16_sq.as<float>();
-        q16v.nrm = q16_nrm.as<float>();
-        q16v.row_bytes = row_bytes16;
-        q16v.n = nb;
-    }
-    // ---- seed layer: distances to the contiguous entry-point sample ----
-    vsb::ExactParams sp;
-    sp.storage = storage;
-    sp.metric = metric;
-    sp.q = qv;
-    sp.x.rows = seed_rows.as<uint8_t>();
-    sp.x.sq = seed_sq.as<float>();
-    sp.x.nrm = seed_nrm.as<float>();
-    sp.x.row_bytes = row_bytes;
-    sp.x.n = n_seed_rows;
-    sp.x_lo = 0;
-    sp.x_hi = n_seed_rows;
-    sp.keys = nullptr;  // ties fall back to the seed index (LessByKey with null keys)
-    sp.kp = 32;
-    const vsb::ExactParams sp_native = sp;
-    if (seed_tc) {
-        // tensor cores: one winner per 256-row tile per query (no list maintenance);
-        // f32 storage multiplies the bf16 shadows of the queries and of the seed block
-        sp.n_splits = std::max(vsb::exact_tc_pick_splits(nb, n_seed_rows, sm_count),
-                               vsb::exact_tc_min_splits_tile_min(n_seed_rows, 32));
-        if (storage == VSB_F32) {
-            sp.storage = VSB_BF16;
-            sp.q = q16v;
-            sp.x.rows = seed16_rows.as<uint8_t>();
-            sp.x.sq = seed16_sq.as<float>();
-            sp.x.nrm = seed16_nrm.as<float>();
-            sp.x.row_bytes = row_bytes16;
-        }
-    } else {
-        sp.n_splits = vsb::exact_pick_splits(nb, n_seed_rows, sm_count);
-    }
-    const bool seed_scan = !seed_tc && nb <= vsb::graph_search_small_batch();
-    if (seed_scan) sp.n_splits = vsb::seed_scan_blocks(n_seed_rows);
-    CU(seed_part.ensure(vsb::exact_part_elems(nb, sp.n_splits, 32) * 8));
-    sp.part = seed_part.as<uint64_t>();
-    t_begin(PH_SEED, s);
-    if (seed_tc) seed_tc = vsb::launch_exact_candidates_tc(sp, s, true);
-    if (!seed_tc) {
-        const uint32_t splits = sp.n_splits;
-        sp = sp_native;
-        sp.n_splits = splits;
-        sp.part = seed_part.as<uint64_t>();
-        if (seed_scan) {
-            // tiny batch: one warp per 4 seed rows, one winner per CTA
-            CU(cudaMemsetAsync(seed_part.p, 0xFF, vsb::exact_part_elems(nb, sp.n_splits, 32) * 8, s));
-            vsb::launch_seed_scan(storage, metric, qv, sp.x, seed_part.as<uint64_t>(), s);
-        } else {
-            vsb::launch_exact_candidates(sp, s);
-        }
-    }
-    t_end(s);
-    CU(cudaGetLastError());
-    // ---- K4 beam search (on the bf16 traversal copy when VSB_FLAG_BF16_TRAVERSAL is set) ----
-    vsb::SearchParams gp;
-    gp.storage = trav16 ? VSB_BF16 : storage;
-    gp.metric = metric;
-    gp.q = trav16 ? q16v : qv;
-    gp.x = x;
-    if (trav16) {
-        gp.x.rows = rows16.as<uint8_t>();
-        gp.x.sq = sq16.as<float>();
-        gp.x.nrm = nrm16.as<float>();
-        gp.x.row_bytes = row_bytes16;
-    }
-    const bool use8 = trav8 && rerank;  // searches only: the build keeps the bf16 traversal
-    if (use8) {
-        CU(q8_rows.ensure((size_t)nb * row_bytes8));
-        CU(q8_sq.ensure((size_t)nb * 4));
-        CU(q8_nrm.ensure((size_t)nb * 4));
-        vsb::launch_convert_rows_i8s(reinterpret_cast<const float*>(qv.rows), nb, dim, row_bytes / 4, q8_rows.as<uint8_t>(),
-                                     row_bytes8, q8_sq.as<float>(), q8_nrm.as<float>(), s);
-        CU(cudaGetLastError());
-        gp.storage = VSB_I8;
-        gp.q.rows = q8_rows.as<uint8_t>();
-        gp.q.sq = q8_sq.as<float>();
-        gp.q.nrm = q8_nrm.as<float>();
-        gp.q.row_bytes = row_bytes8;
-        gp.q.n = nb;
-        gp.x.rows = rows8.as<uint8_t>();
-        gp.x.sq = sq8.as<float>();
-        gp.x.nrm = nrm8.as<float>();
-        gp.x.row_bytes = row_bytes8;
-    }
-    gp.graph = graph.as<uint32_t>();
-    gp.graph_stride = graph_stride;
-    gp.degree = degree;
-    gp.n_graphed = n_graphed;
-    gp.seed_lists = seed_part.as<uint64_t>();
-    gp.seed_stride = sp.n_splits * 32;
-    gp.n_seeds = n_seeds;
-    gp.seed_slots = seed_slots.as<uint32_t>();
-    gp.deny = deny_bm;
-    gp.keys = keys.as<uint64_t>();
-    gp.itopk = std::max(itopk_eff, k);
-    gp.max_iters = max_iters;
-    gp.search_width = search_width;
-    gp.k = k;
-    gp.out_keys = g_keys;
-    gp.out_dists = g_dists;
-    gp.out_counts = have_tail ? nullptr : o_counts;
-    gp.self_base = self_base;
-    uint32_t kr = 0;
-    if (packed_out != nullptr) {
-        gp.out_packed = packed_out;
-        gp.out_counts = nullptr;
-    }
-    if (rerank) {
-        // hand the best kr bf16-ranked candidates to K3 for the canonical fp32 re-rank
-        // (2k for small k, k + 32 + k/4 for large k, at least k + 6; bf16 ranking errors only reorder
-        // candidates near the k-th distance and are far smaller than that margin)
-        // int8 traversal ranks more coarsely: rr_mult8 * k candidates go to the re-rank
-        const uint32_t kv = use8 ? std::min<uint32_t>(std::max(rr_mult8 * k, k + 16), 256)
-                                 : std::max(std::min(2 * k, k + 32 + k / 4), k + 6);
-        kr = std::min<uint32_t>(round_up(kv, 32), 256);
-        if (kr < k) return fail(VSB_EINVAL, "k=%u too large for the bf16-traversal re-rank (max 256)", k);
-        CU(rr_packed.ensure((size_t)nb * kr * 8));
-        gp.k = std::min(kv, kr);
-        gp.out_stride = kr;
-        gp.out_packed = rr_packed.as<uint64_t>();
-        gp.out_counts = nullptr;
-    }
-    if (instrumented) {
-        CU(counters.ensure(16));
-        CU(cudaMemsetAsync(counters.p, 0, 16, s));
-        gp.counters = counters.as<unsigned long long>();
-    }
-    t_begin(PH_GRAPH, s);
-    vsb::launch_graph_search(gp, s);
-    t_end(s);
-    CU(cudaGetLastError());
-    if (rerank) {
-        vsb::ExactParams rp;
-        rp.storage = storage;
-        rp.metric = metric;
-        rp.q = qv;
-        rp.x = x;
-        rp.keys = keys.as<uint64_t>();
-        rp.part = rr_packed.as<uint64_t>();
-        rp.kp = kr;
-        rp.n_splits = 1;
-        t_begin(PH_EXACT, s);
-        vsb::launch_exact_rerank(rp, k, g_keys, g_dists, have_tail ? nullptr : o_counts, nullptr, -1, s);
-        t_end(s);
-        CU(cudaGetLastError());
-    }
-    if (instrumented) {
-        unsigned long long h[2];
-        CU(cudaMemcpyAsync(h, counters.p, 16, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-        last_evals = h[0];
-        last_parents = h[1];
-        last_queries = nb;
-    }
-    return VSB_OK;
-}
-
-// K7: link every un-graphed tail row into the existing graph (batched HNSW-style insert:
-// search with beam = expansion_add, connect to the R closest, add reverse edges).
-vsb_status vsb_index::stream_insert() {
-    if (n_graphed == 0 || n_graphed >= n_slots) return VSB_OK;
-    CU(cudaSetDevice(device));
-    ST(use_stream(stream));
-    const size_t need = (size_t)capacity * graph_stride * 4;
-    if (graph.bytes < need) {
-        DevBuf g2;
-        CU(g2.ensure(need));
-        CU(cudaMemcpyAsync(g2.p, graph.p, (size_t)n_graphed * graph_stride * 4, cudaMemcpyDeviceToDevice, stream));
-        CU(cudaStreamSynchronize(stream));
-        graph = std::move(g2);
-    }
-    const uint32_t R = degree;
-    const uint32_t ef_add = opt.expansion_add ? opt.expansion_add : 128;
-    const uint32_t ef = std::min<uint32_t>(round_up(std::max(ef_add, R), 32), 512);
-    DevBuf cand;
-    const uint32_t QB = 8192;
-    while (n_graphed < n_slots) {
-        const uint32_t t0 = n_graphed;
-        const uint32_t nb = std::min(QB, n_slots - t0);
-        vsb::RowsView qv;
-        qv.rows = rows.as<uint8_t>() + (size_t)t0 * row_bytes;
-        qv.sq = sq.as<float>() + t0;
-        qv.nrm = nrm.as<float>() + t0;
-        qv.row_bytes = row_bytes;
-        qv.n = nb;
-        vsb::RowsView q16;
-        if (trav16) {
-            q16.rows = rows16.as<uint8_t>() + (size_t)t0 * row_bytes16;
-            q16.sq = sq16.as<float>() + t0;
-            q16.nrm = nrm16.as<float>() + t0;
-            q16.row_bytes = row_bytes16;
-            q16.n = nb;
-        }
-        CU(cand.ensure((size_t)nb * R * 8));
-        ST(graph_block(qv, nb, R, ef, nullptr, nullptr, nullptr, cand.as<uint64_t>(), trav16 ? &q16 : nullptr, stream));
-        vsb::launch_stream_link(cand.as<uint64_t>(), nb, R, t0, R, graph.as<uint32_t>(), graph_stride, stream);
-        CU(cudaGetLastError());
-        n_graphed = t0 + nb;  // later batches may link to these rows (stream order)
-        churn_since_refine += nb;
-    }
-    CU(cudaStreamSynchronize(stream));
-    // Streamed links are a little worse than built ones and tombstoned rows keep occupying beam slots: once
-    // 10 % of the graph has churned, one refinement pass (K4 kNN lists of every row -> K6) restores the
-    // quality of a fresh build and drops the tombstoned rows from every list (~0.8 s per million rows).
-    if (!in_build && refine_passes > 0 && churn_since_refine * 10 >= n_graphed && n_graphed >= min_graph_size) {
-        ST(refine_graph());
-        ST(sample_seeds(n_graphed));
-        churn_since_refine = 0;
-    }
-    return VSB_OK;
-}
-
-vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint64_t* d_keys, float* d_dists,
-                                 uint32_t* d_counts, cudaStream_t s, bool exact, const uint32_t* d_allow,
-                                 uint64_t allow_bits) {
-    if (nq == 0) return VSB_OK;
-    if (k == 0) return fail(VSB_EINVAL, "k must be > 0");
-    if (d_q == nullptr || d_keys == nullptr || d_dists == nullptr) return fail(VSB_EINVAL, "null buffer");
-    CU(cudaSetDevice(device));
-    ST(use_stream(s));
-    const uint64_t QCHUNK = 65536;
-    for (uint64_t q0 = 0; q0 < nq; q0 += QCHUNK) {
-        const uint32_t nb = (uint32_t)std::min<uint64_t>(QCHUNK, nq - q0);
-        uint64_t* o_keys = d_keys + q0 * k;
-        float* o_dists = d_dists + q0 * k;
-        uint32_t* o_counts = d_counts ? d_counts + q0 : nullptr;
-        if (n_slots == 0) {
-            vsb::launch_fill_empty(o_keys, o_dists, o_counts, nb, k, s);
-            CU(cudaGetLastError());
-            continue;
-        }
-        CU(q_rows.ensure((size_t)nb * row_bytes));
-        CU(q_sq.ensure((size_t)nb * 4));
-        CU(q_nrm.ensure((size_t)nb * 4));
-        t_begin(PH_CONVERT, s);
-        vsb::launch_convert_rows(storage, d_q + q0 * dim, nb, dim, q_rows.as<uint8_t>(), row_bytes, q_sq.as<float>(),
-                                 q_nrm.as<float>(), s);
-        t_end(s);
-        CU(cudaGetLastError());
-        vsb::RowsView qv;
-        qv.rows = q_rows.as<uint8_t>();
-        qv.sq = q_sq.as<float>();
-        qv.nrm = q_nrm.as<float>();
-        qv.row_bytes = row_bytes;
-        qv.n = nb;
-        const vsb::RowsView x = corpus_view();
-        const uint32_t* deny_bm = any_tombstone ? deny.as<uint32_t>() : nullptr;
-        const bool use_graph = !exact && d_allow == nullptr && n_graphed > 0 && k <= 1024;
-        const uint32_t tail_lo = use_graph ? n_graphed : 0, tail_hi = n_slots;
-        const bool have_tail = tail_hi > tail_lo;
-        uint64_t* g_keys = o_keys;
-        float* g_dists = o_dists;
-        uint64_t* t_keys = o_keys;
-        float* t_dists = o_dists;
-        if (use_graph && have_tail) {
-            CU(tmp_keys.ensure((size_t)2 * nb * k * 8));
-            CU(tmp_dists.ensure((size_t)2 * nb * k * 4));
-            g_keys = tmp_keys.as<uint64_t>();
-            g_dists = tmp_dists.as<float>();
-            t_keys = g_keys + (size_t)nb * k;
-            t_dists = g_dists + (size_t)nb * k;
-        }
-        if (use_graph) {
-            ST(graph_block(qv, nb, k, itopk, g_keys, g_dists, have_tail ? nullptr : o_counts, nullptr, nullptr, s));
-        }
-        if (have_tail) {
-            t_begin(PH_EXACT, s);
-            vsb_status est = exact_block(qv, x, tail_lo, tail_hi, deny_bm, keys.as<uint64_t>(), d_allow, allow_bits, k,
-                                         t_keys, t_dists, use_graph ? nullptr : o_counts, nullptr, -1, s,
-                                         /*approx_ok=*/use_graph);  // the ANN tail needs no certificate (no host sync)
-            t_end(s);
-            ST(est);
-        }
-        if (use_graph && have_tail) {
-            t_begin(PH_MERGE, s);
-            vsb::launch_merge_topk(g_keys, g_dists, 2, nb, k, o_keys, o_dists, o_counts, s);
-            t_end(s);
-            CU(cudaGetLastError());
-        }
-    }
-    return VSB_OK;
-}
-
-vsb_status vsb_index::search_host(const float* queries, uint64_t nq, uint32_t k, uint64_t* keys_out,
-                                  float* dists_out, uint32_t* counts_out, bool exact, const uint32_t* allow_bitmap,
-                                  uint64_t allow_bits) {
-    if (nq == 0) return VSB_OK;
-    if (k == 0) return fail(VSB_EINVAL, "k must be > 0");
-    if (queries == nullptr || keys_out == nullptr || dists_out == nullptr) return fail(VSB_EINVAL, "null buffer");
-    CU(cudaSetDevice(device));
-    ST(use_stream(stream));
-    DevBuf& d_in = q_in;
-    const size_t in_bytes = (size_t)nq * dim * 4;
-    const size_t keys_bytes = (size_t)nq * k * 8, dists_bytes = (size_t)nq * k * 4, counts_bytes = (size_t)nq * 4;
-    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
-    CU(d_in.ensure(al(in_bytes) + al(keys_bytes) + al(dists_bytes) + al(counts_bytes)));
-    uint8_t* base = d_in.as<uint8_t>();
-    float* dq = reinterpret_cast<float*>(base);
-    uint64_t* dk = reinterpret_cast<uint64_t*>(base + al(in_bytes));
-    float* dd = reinterpret_cast<float*>(base + al(in_bytes) + al(keys_bytes));
-    uint32_t* dc = reinterpret_cast<uint32_t*>(base + al(in_bytes) + al(keys_bytes) + al(dists_bytes));
-    CU(cudaMemcpyAsync(dq, queries, in_bytes, cudaMemcpyHostToDevice, stream));
-    const uint32_t* d_allow = nullptr;
-    if (allow_bitmap != nullptr) {
-        const size_t words = (size_t)((allow_bits + 31) / 32);
-        CU(allow.ensure(std::max<size_t>(words * 4, 16)));
-        CU(cudaMemcpyAsync(allow.p, allow_bitmap, words * 4, cudaMemcpyHostToDevice, stream));
-        d_allow = allow.as<uint32_t>();
-    }
-    ST(search_dev(dq, nq, k, dk, dd, dc, stream, exact || allow_bitmap != nullptr, d_allow, allow_bits));
-    CU(cudaMemcpyAsync(keys_out, dk, keys_bytes, cudaMemcpyDeviceToHost, stream));
-    CU(cudaMemcpyAsync(dists_out, dd, dists_bytes, cudaMemcpyDeviceToHost, stream));
-    if (counts_out) CU(cudaMemcpyAsync(counts_out, dc, counts_bytes, cudaMemcpyDeviceToHost, stream));
-    CU(cudaStreamSynchronize(stream));
+    std::fill(h_deny.begin(), h_deny.end(), 0u);
+    w.st = ns;
+    w.n_slots = m;
+    w.n_graphed = new_graphed;
+    w.gr = ng;
+    w.any_tombstone = false;
+    n_tombstones = 0;
+    if (new_graphed > 0) ST(sample_seeds(new_graphed));
+    else w.sd.reset();
+    cudaEventRecord(e1, mstream);
+    cudaEventSynchronize(e1);
+    float ms_ = 0.f;
+    cudaEventElapsedTime(&ms_, e0, e1);
+    bstats.compact_ns += (uint64_t)((double)ms_ * 1e6);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    nvtxRangePop();
     return VSB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-extern "C" {
+namespace vsbi {
 
-vsb_status vsb_create(const vsb_options* o, vsb_index** out) {
-    if (o == nullptr || out == nullptr) return fail(VSB_EINVAL, "null options/out");
+vsb_status create_single(const vsb_options* o, vsb_index** out) {
     *out = nullptr;
-    if (o->dimensions == 0) return fail(VSB_EINVAL, "dimensions must be > 0");
-    if (o->storage < VSB_F32 || o->storage > VSB_B1) return fail(VSB_EINVAL, "unknown storage scalar %d", o->storage);
-    if (o->metric < VSB_L2SQ || o->metric > VSB_HAMMING) return fail(VSB_EINVAL, "unknown metric %d", o->metric);
     int metric = o->metric;
     // usearch.rs:450-464: B1 always uses Hamming; Hamming without B1 is rejected (usearch.rs:480-485)
     if (o->storage == VSB_B1) metric = VSB_HAMMING;
@@ -1278,6 +420,7 @@ vsb_status vsb_create(const vsb_options* o, vsb_index** out) {
     vsb_index* ix = new (std::nothrow) vsb_index();
     if (!ix) return fail(VSB_EOOM, "host allocation failed");
     ix->opt = *o;
+    ix->opt.n_devices = 0;
     ix->dim = o->dimensions;
     ix->metric = metric;
     ix->storage = o->storage;
@@ -1295,49 +438,107 @@ vsb_status vsb_create(const vsb_options* o, vsb_index** out) {
     ix->trav8 = (o->flags & VSB_FLAG_I8_TRAVERSAL) != 0 && o->storage == VSB_F32 && o->metric == VSB_COS;
     if (ix->trav8) ix->trav16 = true;  // the bf16 copy feeds the build and the seed tiles
     ix->row_bytes8 = storage_row_bytes(VSB_I8, o->dimensions);
-    if (const char* e = getenv("VSB_I8_RERANK_MULT")) ix->rr_mult8 = std::max<uint32_t>(2, (uint32_t)strtoul(e, nullptr, 10));
-    if (const char* e = getenv("VSB_DISABLE_TC")) ix->tc_enabled = !(e[0] == '1');
-    if (const char* e = getenv("VSB_DISABLE_CERT")) ix->cert_enabled = !(e[0] == '1');
-    if (const char* e = getenv("VSB_DISABLE_REACH_FIX")) ix->reach_fix = !(e[0] == '1');
-    if (const char* e = getenv("VSB_CERT_KP")) ix->cert_kp = (uint32_t)strtoul(e, nullptr, 10);
-    if (const char* e = getenv("VSB_CERT_KP16")) ix->cert_kp16 = (uint32_t)strtoul(e, nullptr, 10);
-    if (const char* e = getenv("VSB_TC_MIN_ROWS")) ix->tc_min_rows = (uint32_t)strtoul(e, nullptr, 10);
-    if (const char* e = getenv("VSB_ALLPAIRS_MAX")) ix->allpairs_max = (uint32_t)strtoul(e, nullptr, 10);
-    if (const char* e = getenv("VSB_ALLPAIRS_PREFIX")) ix->allpairs_prefix = (uint32_t)strtoul(e, nullptr, 10);
-    if (const char* e = getenv("VSB_REFINE_PASSES")) ix->refine_passes = (uint32_t)strtoul(e, nullptr, 10);
+    if (const char* v = getenv("VSB_I8_RERANK_MULT")) ix->rr_mult8 = std::max<uint32_t>(2, (uint32_t)strtoul(v, nullptr, 10));
+    if (const char* v = getenv("VSB_DISABLE_TC")) ix->tc_enabled = !(v[0] == '1');
+    if (const char* v = getenv("VSB_DISABLE_CERT")) ix->cert_enabled = !(v[0] == '1');
+    if (const char* v = getenv("VSB_DISABLE_REACH_FIX")) ix->reach_fix = !(v[0] == '1');
+    if (const char* v = getenv("VSB_CERT_KP")) ix->cert_kp = (uint32_t)strtoul(v, nullptr, 10);
+    if (const char* v = getenv("VSB_CERT_KP16")) ix->cert_kp16 = (uint32_t)strtoul(v, nullptr, 10);
+    if (const char* v = getenv("VSB_TC_MIN_ROWS")) ix->tc_min_rows = (uint32_t)strtoul(v, nullptr, 10);
+    if (const char* v = getenv("VSB_ALLPAIRS_MAX")) ix->allpairs_max = (uint32_t)strtoul(v, nullptr, 10);
+    if (const char* v = getenv("VSB_ALLPAIRS_PREFIX")) ix->allpairs_prefix = (uint32_t)strtoul(v, nullptr, 10);
+    if (const char* v = getenv("VSB_REFINE_PASSES")) ix->refine_passes = (uint32_t)strtoul(v, nullptr, 10);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
-    e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    // searches on a high-priority stream, mutators (build, streaming insert, refinement) on a low-priority one:
+    // when both have CTAs pending, the block scheduler serves the search first
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    e = cudaStreamCreateWithPriority(&ix->stream, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ix->mstream, cudaStreamNonBlocking, prio_lo);
     if (e != cudaSuccess) {
-        delete ix;
+        destroy_single(ix);
         return fail(VSB_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
+    ix->w.st = std::make_shared<Store>();
+    ix->publish();
     *out = ix;
     return VSB_OK;
 }
 
-void vsb_destroy(vsb_index* ix) {
+void destroy_single(vsb_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     cudaDeviceSynchronize();
     ix->t_resolve();
+    ix->reap_inflight(true);
     if (ix->stream) cudaStreamDestroy(ix->stream);
+    if (ix->mstream) cudaStreamDestroy(ix->mstream);
     delete ix;
+}
+
+}  // namespace vsbi
+
+extern "C" {
+
+vsb_status vsb_create(const vsb_options* o, vsb_index** out) {
+    if (o == nullptr || out == nullptr) return fail(VSB_EINVAL, "null options/out");
+    *out = nullptr;
+    if (o->dimensions == 0) return fail(VSB_EINVAL, "dimensions must be > 0");
+    if (o->storage < VSB_F32 || o->storage > VSB_B1) return fail(VSB_EINVAL, "unknown storage scalar %d", o->storage);
+    if (o->metric < VSB_L2SQ || o->metric > VSB_HAMMING) return fail(VSB_EINVAL, "unknown metric %d", o->metric);
+    if (o->n_devices < 0 || o->n_devices > 8) return fail(VSB_EINVAL, "n_devices must be in 0..8");
+    if (o->n_devices > 1) return vsbi::create_sharded(o, out);
+    vsb_options one = *o;
+    if (o->n_devices == 1) one.device = o->device_ids[0];
+    return vsbi::create_single(&one, out);
+}
+
+void vsb_destroy(vsb_index* ix) {
+    if (!ix) return;
+    if (ix->sharded) {
+        vsbi::destroy_sharded(ix);
+        return;
+    }
+    vsbi::destroy_single(ix);
 }
 
 vsb_status vsb_reserve(vsb_index* ix, uint64_t capacity) {
     if (!ix) return fail(VSB_EINVAL, "null index");
-    std::lock_guard<std::mutex> g(ix->mu);
+    if (ix->sharded) return vsbi::sharded_reserve(ix, capacity);
+    std::lock_guard<std::mutex> g(ix->mut_mu);
     return ix->reserve(capacity);
 }
 
-uint64_t vsb_capacity(const vsb_index* ix) { return ix ? ix->capacity_atomic.load() : 0; }
-uint64_t vsb_size(const vsb_index* ix) { return ix ? ix->live_atomic.load() : 0; }
+uint64_t vsb_capacity(const vsb_index* ix) {
+    if (!ix) return 0;
+    if (ix->sharded) return vsbi::sharded_capacity(ix);
+    return ix->capacity_atomic.load();
+}
+uint64_t vsb_size(const vsb_index* ix) {
+    if (!ix) return 0;
+    if (ix->sharded) return vsbi::sharded_size(ix);
+    return ix->live_atomic.load();
+}
 
 vsb_status vsb_add(vsb_index* ix, const uint64_t* keys, const float* rows, uint64_t n) {
     if (!ix) return fail(VSB_EINVAL, "null index");
-    std::lock_guard<std::mutex> g(ix->mu);
-    return ix->add(keys, rows, n);
+    if (ix->sharded) return vsbi::sharded_add(ix, keys, rows, n, nullptr, nullptr);
+    std::lock_guard<std::mutex> g(ix->mut_mu);
+    return ix->add(keys, rows, n, nullptr, nullptr);
+}
+
+vsb_status vsb_add_each(vsb_index* ix, const uint64_t* keys, const float* rows, uint64_t n, int32_t* row_status,
+                        uint64_t* n_added) {
+    if (!ix) return fail(VSB_EINVAL, "null index");
+    std::vector<int32_t> local;
+    if (row_status == nullptr) {
+        local.resize((size_t)n);
+        row_status = local.data();
+    }
+    if (ix->sharded) return vsbi::sharded_add(ix, keys, rows, n, row_status, n_added);
+    std::lock_guard<std::mutex> g(ix->mut_mu);
+    return ix->add(keys, rows, n, row_status, n_added);
 }
 
 vsb_status vsb_remove(vsb_index* ix, const uint64_t* keys, uint64_t n, uint64_t* n_removed) {
@@ -1345,67 +546,88 @@ vsb_status vsb_remove(vsb_index* ix, const uint64_t* keys, uint64_t n, uint64_t*
     if (n_removed) *n_removed = 0;
     if (n == 0) return VSB_OK;
     if (!keys) return fail(VSB_EINVAL, "null keys");
-    std::lock_guard<std::mutex> g(ix->mu);
+    if (ix->sharded) return vsbi::sharded_remove(ix, keys, n, n_removed);
+    std::lock_guard<std::mutex> g(ix->mut_mu);
     return ix->remove(keys, n, n_removed);
 }
 
-int vsb_contains(const vsb_index* ix, uint64_t key) {
-    if (!ix) return 0;
-    std::lock_guard<std::mutex> g(const_cast<vsb_index*>(ix)->mu);
+int vsb_contains(const vsb_index* cix, uint64_t key) {
+    if (!cix) return 0;
+    vsb_index* ix = const_cast<vsb_index*>(cix);
+    if (ix->sharded) return vsbi::sharded_contains(ix, key);
+    std::lock_guard<std::mutex> g(ix->map_mu);
     return ix->key2slot.count(key) ? 1 : 0;
 }
 
 vsb_status vsb_build(vsb_index* ix) {
     if (!ix) return fail(VSB_EINVAL, "null index");
-    std::lock_guard<std::mutex> g(ix->mu);
-    return ix->build();
+    if (ix->sharded) return vsbi::sharded_build(ix);
+    std::lock_guard<std::mutex> g(ix->mut_mu);
+    nvtxRangePushA("vsb_build");
+    const auto t0 = std::chrono::steady_clock::now();
+    const vsb_status st = ix->build();
+    ix->bstats.total_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    if (st == VSB_OK) ix->publish();
+    else ix->w = ix->snapshot();  // a failed build leaves the published generation in charge
+    nvtxRangePop();
+    return st;
 }
 
 vsb_status vsb_insert_pending(vsb_index* ix) {
     if (!ix) return fail(VSB_EINVAL, "null index");
-    std::lock_guard<std::mutex> g(ix->mu);
-    return ix->stream_insert();
+    if (ix->sharded) return vsbi::sharded_insert_pending(ix);
+    std::lock_guard<std::mutex> g(ix->mut_mu);
+    const vsb_status st = ix->stream_insert();
+    if (st == VSB_OK) ix->publish();
+    return st;
 }
 
 vsb_status vsb_export_graph(vsb_index* ix, uint32_t* rows_out, uint64_t* keys_out, uint64_t* n_graphed,
                             uint32_t* stride) {
     if (!ix) return fail(VSB_EINVAL, "null index");
-    std::lock_guard<std::mutex> g(ix->mu);
-    if (n_graphed) *n_graphed = ix->n_graphed;
+    if (ix->sharded) return fail(VSB_EINVAL, "vsb_export_graph works on one shard; a sharded handle has one graph per device");
+    const vsbi::View v = ix->snapshot();
+    if (n_graphed) *n_graphed = v.n_graphed;
     if (stride) *stride = ix->graph_stride;
     CU(cudaSetDevice(ix->device));
-    ST(ix->use_stream(ix->stream));
-    if (rows_out && ix->n_graphed)
-        CU(cudaMemcpyAsync(rows_out, ix->graph.p, (size_t)ix->n_graphed * ix->graph_stride * 4, cudaMemcpyDeviceToHost,
-                           ix->stream));
-    if (keys_out && ix->n_graphed)
-        CU(cudaMemcpyAsync(keys_out, ix->keys.p, (size_t)ix->n_graphed * 8, cudaMemcpyDeviceToHost, ix->stream));
-    CU(cudaStreamSynchronize(ix->stream));
+    if (rows_out && v.n_graphed)
+        CU(cudaMemcpy(rows_out, v.gr->g.p, (size_t)v.n_graphed * ix->graph_stride * 4, cudaMemcpyDeviceToHost));
+    if (keys_out && v.n_graphed) CU(cudaMemcpy(keys_out, v.st->keys.p, (size_t)v.n_graphed * 8, cudaMemcpyDeviceToHost));
     return VSB_OK;
 }
 
 vsb_status vsb_set_search_params(vsb_index* ix, const vsb_search_params* p) {
     if (!ix || !p) return fail(VSB_EINVAL, "null argument");
-    std::lock_guard<std::mutex> g(ix->mu);
-    if (p->expansion_search) ix->itopk = std::min<uint32_t>(round_up(p->expansion_search, 32), 1024);
-    if (p->max_iterations) ix->max_iters = p->max_iterations >= 1000000u ? 0 : p->max_iterations;  // >= 1e6: back to auto
-    if (p->n_seeds) ix->n_seeds = std::min<uint32_t>(p->n_seeds, 32);
-    if (p->min_graph_size) ix->min_graph_size = p->min_graph_size;
-    if (p->search_width) ix->search_width = std::min<uint32_t>(p->search_width, 4);
-    if (p->stream_threshold) ix->stream_threshold = p->stream_threshold == 0xFFFFFFFFu ? 0 : p->stream_threshold;
+    if (ix->sharded) return vsbi::sharded_set_search_params(ix, p);
+    {
+        std::lock_guard<std::mutex> g(ix->search_mu);
+        if (p->expansion_search) ix->itopk = std::min<uint32_t>(round_up(p->expansion_search, 32), 1024);
+        if (p->max_iterations) ix->max_iters = p->max_iterations >= 1000000u ? 0 : p->max_iterations;  // >= 1e6: back to auto
+        if (p->n_seeds) ix->n_seeds = std::min<uint32_t>(p->n_seeds, 32);
+        if (p->min_graph_size) ix->min_graph_size = p->min_graph_size;
+        if (p->search_width) ix->search_width = std::min<uint32_t>(p->search_width, 4);
+        if (p->filter_exact_below_pct) ix->filter_min_pct = p->filter_exact_below_pct == 0xFFFFFFFFu ? 0 : std::min<uint32_t>(p->filter_exact_below_pct, 101);
+    }
+    if (p->stream_threshold || p->expansion_add) {
+        std::lock_guard<std::mutex> g(ix->mut_mu);
+        if (p->stream_threshold) ix->stream_threshold = p->stream_threshold == 0xFFFFFFFFu ? 0 : p->stream_threshold;
+        if (p->expansion_add) ix->ef_add_rt = p->expansion_add;
+    }
     return VSB_OK;
 }
 
 vsb_status vsb_set_instrumented(vsb_index* ix, int on) {
     if (!ix) return fail(VSB_EINVAL, "null index");
-    std::lock_guard<std::mutex> g(ix->mu);
+    if (ix->sharded) return vsbi::sharded_set_instrumented(ix, on);
+    std::lock_guard<std::mutex> g(ix->search_mu);
     ix->instrumented = on != 0;
     return VSB_OK;
 }
 
 vsb_status vsb_set_kernel_timing(vsb_index* ix, int on) {
     if (!ix) return fail(VSB_EINVAL, "null index");
-    std::lock_guard<std::mutex> g(ix->mu);
+    if (ix->sharded) return vsbi::sharded_set_kernel_timing(ix, on);
+    std::lock_guard<std::mutex> g(ix->search_mu);
     cudaSetDevice(ix->device);
     ix->t_resolve();
     ix->timing = on != 0;
@@ -1417,16 +639,18 @@ vsb_status vsb_set_kernel_timing(vsb_index* ix, int on) {
 
 vsb_status vsb_get_stats(vsb_index* ix, vsb_stats* out) {
     if (!ix || !out) return fail(VSB_EINVAL, "null argument");
-    std::lock_guard<std::mutex> g(ix->mu);
+    if (ix->sharded) return vsbi::sharded_get_stats(ix, out);
+    std::lock_guard<std::mutex> g(ix->search_mu);
+    const vsbi::View v = ix->snapshot();
     out->kernel_launches = vsb::g_kernel_launches.load();
     out->distance_evals = ix->last_evals;
     out->parent_expansions = ix->last_parents;
     out->queries = ix->last_queries;
-    out->n_slots = ix->n_slots;
-    out->n_graphed = ix->n_graphed;
+    out->n_slots = v.n_slots;
+    out->n_graphed = v.n_graphed;
     out->graph_degree = ix->degree;
     out->row_bytes = ix->row_bytes;
-    out->n_seed_rows = ix->n_seed_rows;
+    out->n_seed_rows = v.sd ? v.sd->n : 0;
     out->hbm_bytes = ix->hbm_bytes();
     cudaSetDevice(ix->device);
     ix->t_resolve();
@@ -1444,21 +668,35 @@ vsb_status vsb_get_stats(vsb_index* ix, vsb_stats* out) {
     out->exact_certified = ix->cert_ok;
     out->exact_fallback = ix->cert_fallback;
     out->exact_scanned = ix->cert_scanned;
-    out->extra_seeds = ix->n_extra_seeds;
+    out->extra_seeds = v.sd ? v.sd->extra : 0;
+    return VSB_OK;
+}
+
+vsb_status vsb_get_build_stats(vsb_index* ix, vsb_build_stats* out) {
+    if (!ix || !out) return fail(VSB_EINVAL, "null argument");
+    if (ix->sharded) return vsbi::sharded_get_build_stats(ix, out);
+    std::lock_guard<std::mutex> g(ix->mut_mu);
+    *out = ix->bstats;
+    return VSB_OK;
+}
+
+vsb_status vsb_get_options(vsb_index* ix, vsb_options* out) {
+    if (!ix || !out) return fail(VSB_EINVAL, "null argument");
+    *out = ix->opt;
     return VSB_OK;
 }
 
 vsb_status vsb_search(vsb_index* ix, const float* queries, uint64_t q, uint32_t k, uint64_t* keys, float* distances,
                       uint32_t* counts) {
     if (!ix) return fail(VSB_EINVAL, "null index");
-    std::lock_guard<std::mutex> g(ix->mu);
+    if (ix->sharded) return vsbi::sharded_search_host(ix, queries, q, k, keys, distances, counts, false, nullptr, 0);
     return ix->search_host(queries, q, k, keys, distances, counts, false, nullptr, 0);
 }
 
 vsb_status vsb_search_exact(vsb_index* ix, const float* queries, uint64_t q, uint32_t k, uint64_t* keys,
                             float* distances, uint32_t* counts) {
     if (!ix) return fail(VSB_EINVAL, "null index");
-    std::lock_guard<std::mutex> g(ix->mu);
+    if (ix->sharded) return vsbi::sharded_search_host(ix, queries, q, k, keys, distances, counts, true, nullptr, 0);
     return ix->search_host(queries, q, k, keys, distances, counts, true, nullptr, 0);
 }
 
@@ -1467,16 +705,19 @@ vsb_status vsb_search_filtered(vsb_index* ix, const float* queries, uint64_t q, 
                                uint32_t* counts) {
     if (!ix) return fail(VSB_EINVAL, "null index");
     if (!allow_bitmap) return fail(VSB_EINVAL, "null bitmap");
-    std::lock_guard<std::mutex> g(ix->mu);
-    return ix->search_host(queries, q, k, keys, distances, counts, true, allow_bitmap, bitmap_bits);
+    if (ix->sharded)
+        return vsbi::sharded_search_host(ix, queries, q, k, keys, distances, counts, false, allow_bitmap, bitmap_bits);
+    return ix->search_host(queries, q, k, keys, distances, counts, false, allow_bitmap, bitmap_bits);
 }
 
 vsb_status vsb_search_dev(vsb_index* ix, const float* d_queries, uint64_t q, uint32_t k, uint64_t* d_keys,
                           float* d_distances, uint32_t* d_counts, void* stream, int exact) {
     if (!ix) return fail(VSB_EINVAL, "null index");
-    std::lock_guard<std::mutex> g(ix->mu);
-    return ix->search_dev(d_queries, q, k, d_keys, d_distances, d_counts, static_cast<cudaStream_t>(stream),
-                          exact != 0, nullptr, 0);
+    if (ix->sharded)
+        return vsbi::sharded_search_dev(ix, d_queries, q, k, d_keys, d_distances, d_counts, static_cast<cudaStream_t>(stream), exact != 0);
+    std::lock_guard<std::mutex> g(ix->search_mu);
+    return ix->search_dev(d_queries, q, k, d_keys, d_distances, d_counts, static_cast<cudaStream_t>(stream), exact != 0,
+                          nullptr, 0, 0);
 }
 
 vsb_status vsb_merge_topk_dev(const uint64_t* d_keys, const float* d_distances, uint32_t parts, uint64_t q, uint32_t k,
@@ -1514,143 +755,7 @@ void vsb_f32_to_b1x8(const float* v, uint64_t n, uint8_t* out) {
     }
 }
 
-const char* vsb_last_error(void) { return g_last_error.c_str(); }
-const char* vsb_version(void) { return "vsb200-0.1.0"; }
+const char* vsb_last_error(void) { return vsbi::g_last_error.c_str(); }
+const char* vsb_version(void) { return "vsb200-0.2.0"; }
 
 }  // extern "C"
-
-// ---- N3: snapshot ------------------------------------------------------------------------------
-namespace {
-struct SnapHeader {
-    char magic[8];  // "VSB200S1"
-    vsb_options opt;
-    uint64_t n_slots, n_graphed, capacity;
-    uint32_t row_bytes, graph_stride, degree, reserved;
-};
-
-bool write_dev(FILE* f, const void* dptr, size_t bytes, std::vector<uint8_t>& stage, cudaStream_t s) {
-    const size_t CH = stage.size();
-    for (size_t off = 0; off < bytes; off += CH) {
-        const size_t nb = std::min(CH, bytes - off);
-        if (cudaMemcpyAsync(stage.data(), static_cast<const uint8_t*>(dptr) + off, nb, cudaMemcpyDeviceToHost, s) != cudaSuccess)
-            return false;
-        if (cudaStreamSynchronize(s) != cudaSuccess) return false;
-        if (fwrite(stage.data(), 1, nb, f) != nb) return false;
-    }
-    return true;
-}
-bool read_dev(FILE* f, void* dptr, size_t bytes, std::vector<uint8_t>& stage, cudaStream_t s) {
-    const size_t CH = stage.size();
-    for (size_t off = 0; off < bytes; off += CH) {
-        const size_t nb = std::min(CH, bytes - off);
-        if (fread(stage.data(), 1, nb, f) != nb) return false;
-        if (cudaMemcpyAsync(static_cast<uint8_t*>(dptr) + off, stage.data(), nb, cudaMemcpyHostToDevice, s) != cudaSuccess)
-            return false;
-        if (cudaStreamSynchronize(s) != cudaSuccess) return false;
-    }
-    return true;
-}
-}  // namespace
-
-extern "C" vsb_status vsb_save(vsb_index* ix, const char* path) {
-    if (!ix || !path) return fail(VSB_EINVAL, "null argument");
-    std::lock_guard<std::mutex> g(ix->mu);
-    CU(cudaSetDevice(ix->device));
-    ST(ix->use_stream(ix->stream));
-    FILE* f = fopen(path, "wb");
-    if (!f) return fail(VSB_EINVAL, "cannot open %s for writing", path);
-    SnapHeader h{};
-    memcpy(h.magic, "VSB200S1", 8);
-    h.opt = ix->opt;
-    h.n_slots = ix->n_slots;
-    h.n_graphed = ix->n_graphed;
-    h.capacity = ix->capacity;
-    h.row_bytes = ix->row_bytes;
-    h.graph_stride = ix->graph_stride;
-    h.degree = ix->degree;
-    std::vector<uint8_t> stage((size_t)64 << 20);
-    const size_t n = ix->n_slots;
-    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
-    ok = ok && fwrite(ix->h_deny.data(), 4, (n + 31) / 32, f) == (n + 31) / 32;
-    ok = ok && write_dev(f, ix->keys.p, n * 8, stage, ix->stream);
-    ok = ok && write_dev(f, ix->rows.p, n * ix->row_bytes, stage, ix->stream);
-    ok = ok && write_dev(f, ix->sq.p, n * 4, stage, ix->stream);
-    ok = ok && write_dev(f, ix->nrm.p, n * 4, stage, ix->stream);
-    ok = ok && write_dev(f, ix->graph.p, (size_t)ix->n_graphed * ix->graph_stride * 4, stage, ix->stream);
-    ok = (fclose(f) == 0) && ok;
-    if (!ok) return fail(VSB_ECUDA, "short write or copy failure while saving %s", path);
-    return VSB_OK;
-}
-
-extern "C" vsb_status vsb_load(const char* path, int32_t device, vsb_index** out) {
-    if (!path || !out) return fail(VSB_EINVAL, "null argument");
-    *out = nullptr;
-    FILE* f = fopen(path, "rb");
-    if (!f) return fail(VSB_EINVAL, "cannot open %s", path);
-    SnapHeader h{};
-    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "VSB200S1", 8) != 0) {
-        fclose(f);
-        return fail(VSB_EINVAL, "%s is not a vsb200 snapshot", path);
-    }
-    h.opt.device = device;
-    vsb_index* ix = nullptr;
-    vsb_status st = vsb_create(&h.opt, &ix);
-    if (st != VSB_OK) {
-        fclose(f);
-        return st;
-    }
-    auto bail = [&](vsb_status code, const char* what) {
-        fclose(f);
-        vsb_destroy(ix);
-        return fail(code, "%s while loading %s", what, path);
-    };
-    if (h.row_bytes != ix->row_bytes || h.graph_stride != ix->graph_stride) return bail(VSB_EINVAL, "layout mismatch");
-    const size_t n = h.n_slots;  // nobody else holds this handle yet: no locking needed
-    if (ix->reserve(std::max<uint64_t>(h.capacity, std::max<uint64_t>(n, 1))) != VSB_OK) return bail(VSB_EOOM, "reserve failed");
-    std::vector<uint8_t> stage((size_t)64 << 20);
-    std::vector<uint64_t> h_keys(n);
-    bool ok = fread(ix->h_deny.data(), 4, (n + 31) / 32, f) == (n + 31) / 32;
-    ok = ok && fread(h_keys.data(), 8, n, f) == n;
-    if (!ok) return bail(VSB_EINVAL, "truncated file");
-    if (cudaMemcpy(ix->keys.p, h_keys.data(), n * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(ix->deny.p, ix->h_deny.data(), ((n + 31) / 32) * 4, cudaMemcpyHostToDevice) != cudaSuccess)
-        return bail(VSB_ECUDA, "upload failed");
-    ok = read_dev(f, ix->rows.p, n * ix->row_bytes, stage, ix->stream);
-    ok = ok && read_dev(f, ix->sq.p, n * 4, stage, ix->stream);
-    ok = ok && read_dev(f, ix->nrm.p, n * 4, stage, ix->stream);
-    if (ok && h.n_graphed) {
-        if (ix->graph.ensure((size_t)std::max<uint64_t>(ix->capacity, h.n_graphed) * ix->graph_stride * 4) != cudaSuccess)
-            return bail(VSB_EOOM, "graph allocation failed");
-        ok = read_dev(f, ix->graph.p, (size_t)h.n_graphed * ix->graph_stride * 4, stage, ix->stream);
-    }
-    if (!ok) return bail(VSB_EINVAL, "truncated file or copy failure");
-    fclose(f);
-    ix->n_slots = (uint32_t)n;
-    ix->n_graphed = (uint32_t)h.n_graphed;
-    uint64_t live = 0;
-    for (size_t i = 0; i < n; ++i) {
-        if (ix->h_deny[i >> 5] >> (i & 31) & 1u) {
-            ix->any_tombstone = true;
-            continue;
-        }
-        ix->key2slot.emplace(h_keys[i], (uint32_t)i);
-        ++live;
-    }
-    ix->live = live;
-    ix->live_atomic.store(live);
-    if (ix->trav16 && n) {  // the bf16 traversal copy is derived data: regenerate instead of storing it
-        vsb::launch_convert_rows(VSB_BF16, ix->rows.as<float>(), (uint32_t)n, ix->row_bytes / 4, ix->rows16.as<uint8_t>(),
-                                 ix->row_bytes16, ix->sq16.as<float>(), ix->nrm16.as<float>(), ix->stream);
-    }
-    if (ix->trav8 && n) {
-        vsb::launch_convert_rows_i8s(ix->rows.as<float>(), (uint32_t)n, ix->dim, ix->row_bytes / 4, ix->rows8.as<uint8_t>(),
-                                     ix->row_bytes8, ix->sq8.as<float>(), ix->nrm8.as<float>(), ix->stream);
-    }
-    if (ix->n_graphed && ix->sample_seeds(ix->n_graphed) != VSB_OK) {
-        vsb_destroy(ix);
-        return VSB_ECUDA;
-    }
-    cudaStreamSynchronize(ix->stream);
-    *out = ix;
-    return VSB_OK;
-}

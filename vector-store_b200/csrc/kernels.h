@@ -97,7 +97,12 @@ void launch_reach_step(const uint32_t* graph, uint32_t n, uint32_t stride, uint3
                        uint32_t* changed, cudaStream_t stream);
 void launch_first_unreached(const uint8_t* state, const uint32_t* deny, uint32_t n, uint32_t* out, cudaStream_t stream);
 
-// K7 (graph_build.cu): link a batch of already-searched new rows into the graph
+// compaction: renumber the rows and the edges of a graph through old2new (kInvalidSlot = removed)
+void launch_remap_graph(const uint32_t* graph, uint32_t n_old, uint32_t stride, const uint32_t* old2new, uint32_t* out,
+                        cudaStream_t stream);
+
+// K7 (graph_build.cu): link a batch of already-searched new rows into the graph (detour-pruned forward rows,
+// then reverse edges); cand = [n_new][cand_stride] packed ascending candidates
 void launch_stream_link(const uint64_t* cand, uint32_t n_new, uint32_t cand_stride, uint32_t first_slot, uint32_t R,
                         uint32_t* graph, uint32_t graph_stride, cudaStream_t stream);
 
@@ -122,6 +127,10 @@ struct SearchParams {
     long long self_base = -1;                // >= 0: query i is row self_base + i (excluded from its own list)
     uint32_t out_stride = 0;                 // packed entries per query (0 = k)
     unsigned long long* counters = nullptr;  // [2]: distance evals, parent expansions (instrumented only)
+    // filtered ANN (usearch.rs:224-248): every row is traversed, only rows whose bit (key & 2^48-1) is set enter the
+    // result list (a second list next to the traversal list)
+    const uint32_t* allow = nullptr;
+    uint64_t allow_bits = 0;
 };
 void launch_graph_search(const SearchParams& p, cudaStream_t stream);
 bool graph_search_supported(uint32_t row_bytes);  // rows up to 6144 bytes

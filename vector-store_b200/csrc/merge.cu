@@ -58,21 +58,29 @@ __global__ void __launch_bounds__(K8_THREADS) merge_topk_kernel(const uint64_t* 
             __syncthreads();
         }
     }
-    uint32_t cnt = 0;
-    for (uint32_t i = threadIdx.x; i < k; i += K8_THREADS) {
-        const uint64_t key = sk[i];
-        const bool valid = key != 0xFFFFFFFFFFFFFFFFull;
-        out_keys[q * k + i] = key;
-        out_dists[q * k + i] = valid ? ord_to_f32(sd[i]) : __int_as_float(0x7F800000);
-        cnt += valid ? 1u : 0u;
-    }
-    if (out_counts != nullptr) {
-        __shared__ uint32_t total_cnt;
-        if (threadIdx.x == 0) total_cnt = 0;
-        __syncthreads();
-        if (cnt) atomicAdd(&total_cnt, cnt);
-        __syncthreads();
-        if (threadIdx.x == 0) out_counts[q] = total_cnt;
+    // emit the first k DISTINCT keys: a row may legitimately arrive twice (graph result + brute-force tail while a
+    // streaming insert is linking that row) and then carries the same canonical distance, so the copies are adjacent
+    if (threadIdx.x < 32) {
+        const uint32_t lane = threadIdx.x;
+        uint32_t count = 0;
+        for (uint32_t b = 0; b < n_pow2 && count < k; b += 32) {
+            const uint32_t i = b + lane;
+            const uint64_t key = i < n_pow2 ? sk[i] : 0xFFFFFFFFFFFFFFFFull;
+            const bool valid = key != 0xFFFFFFFFFFFFFFFFull && !(i > 0 && sk[i - 1] == key);
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, valid);
+            const uint32_t pos = count + __popc(m & ((1u << lane) - 1));
+            if (valid && pos < k) {
+                out_keys[q * k + pos] = key;
+                out_dists[q * k + pos] = ord_to_f32(sd[i]);
+            }
+            count += __popc(m);
+        }
+        if (count > k) count = k;
+        for (uint32_t i = count + lane; i < k; i += 32) {
+            out_keys[q * k + i] = 0xFFFFFFFFFFFFFFFFull;
+            out_dists[q * k + i] = __int_as_float(0x7F800000);
+        }
+        if (out_counts != nullptr && lane == 0) out_counts[q] = count;
     }
 }
 

@@ -142,12 +142,18 @@ class IndexActor:
         p = self._partition(partition_id)
         try:
             self._grow(p, emb.shape[0])
-            p.idx.add_batch(np.asarray(primary_ids, dtype=np.uint64), emb)
+            # row-by-row verdicts like the reference's one-message-per-vector loop (usearch.rs:1020-1033): a duplicate or
+            # reserved key fails only its own row, the rest of the batch is indexed
+            added, status = p.idx.add_each(np.asarray(primary_ids, dtype=np.uint64), emb)
         except native.VsbError as e:  # logged and swallowed, usearch.rs:1028-1030
             log.warning("add_vector failed for index %s: %s", self.config.key, e)
             return
-        p.size += emb.shape[0]
-        self.size += emb.shape[0]
+        if added != emb.shape[0]:
+            bad = np.flatnonzero(status)
+            log.warning("add_vector: %d of %d rows rejected for index %s (first: key %s, status %d)", len(bad),
+                        emb.shape[0], self.config.key, np.asarray(primary_ids)[bad[0]], int(status[bad[0]]))
+        p.size += added
+        self.size += added
 
     def remove_vector(self, partition_id: int, primary_id: int) -> None:
         p = self.partitions.get(partition_id)
@@ -187,13 +193,16 @@ class IndexActor:
             out_d.append(d)
         return out_k, out_d
 
+    MAX_LIMIT = 1024  # vsb_search's k ceiling (include/vsb200.h); the reference's Limit is unbounded
+
     def ann(self, embedding, limit: int, partition_id: int = GLOBAL_PARTITION):
         e = np.asarray(embedding, dtype=np.float32)
         self._validate(e)
         p = self.partitions.get(partition_id)
         if p is None:
             return [], []
-        keys, dists, counts = p.idx.search_batch(e[None, :], limit)
+        # a Limit above the engine's ceiling is served with the ceiling (never an error: usearch returns what it has)
+        keys, dists, counts = p.idx.search_batch(e[None, :], min(limit, self.MAX_LIMIT))
         return self._to_hits(keys[0], dists[0], counts[0])
 
     def ann_batch(self, embeddings, limit: int, partition_id: int = GLOBAL_PARTITION):
@@ -208,7 +217,11 @@ class IndexActor:
     def filtered_ann(self, embedding, limit: int, predicate, max_row_id: int,
                      partition_id: int = GLOBAL_PARTITION):
         """`predicate(primary_id) -> bool` mirrors the reference closure (usearch.rs:1108-1154); it is
-        evaluated per table row id (low 48 bits of the key, table/primary_id.rs:27-62) into a bitmap."""
+        evaluated per table row id (low 48 bits of the key, table/primary_id.rs:27-62) into a bitmap.
+        `predicate=None` is the reference's downgrade: a FilteredAnn whose restrictions are fully consumed by the
+        local partition key becomes a plain Ann on that partition (usearch.rs:844-862)."""
+        if predicate is None:
+            return self.ann(embedding, limit, partition_id)
         e = np.asarray(embedding, dtype=np.float32)
         self._validate(e)
         p = self.partitions.get(partition_id)

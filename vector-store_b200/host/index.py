@@ -10,7 +10,7 @@ import enum
 import numpy as np
 
 from . import native
-from .native import VsbOptions, VsbSearchParams, VsbStats, check, lib
+from .native import VsbBuildStats, VsbOptions, VsbSearchParams, VsbStats, check, lib
 
 
 class Metric(enum.IntEnum):  # usearch MetricKind as mapped at usearch.rs:480-501
@@ -38,11 +38,13 @@ def _ptr(a):
 class GpuIndex:
     def __init__(self, dimensions: int, metric: Metric = Metric.Cos, storage: Scalar = Scalar.F32,
                  connectivity: int = 0, expansion_add: int = 0, expansion_search: int = 0, device: int = -1,
-                 seed: int = 0, bf16_traversal: bool = False, i8_traversal: bool = False):
+                 seed: int = 0, bf16_traversal: bool = False, i8_traversal: bool = False, devices=None):
+        """devices: list of 2..8 CUDA ordinals -> ONE handle over one shard per device (vsb_options.n_devices)."""
         self._lib = lib()
         flags = (1 if bf16_traversal else 0) | (2 if i8_traversal else 0)  # VSB_FLAG_BF16_TRAVERSAL | VSB_FLAG_I8_TRAVERSAL
+        devs = list(devices) if devices else []
         opt = VsbOptions(dimensions, int(metric), int(storage), connectivity, expansion_add, expansion_search,
-                         device, flags, seed)
+                         device, flags, seed, len(devs), (C.c_int32 * 8)(*(devs + [0] * (8 - len(devs)))))
         h = C.c_void_p()
         check(self._lib.vsb_create(C.byref(opt), C.byref(h)))
         self._h = h
@@ -89,8 +91,6 @@ class GpuIndex:
 
     # ---- batched ABI ----
     def _check_dim(self, a: np.ndarray) -> None:
-        if self.dimensions is None:  # loaded from a snapshot: the library validates sizes
-            self.dimensions = a.shape[1]
         if a.ndim != 2 or a.shape[1] != self.dimensions:
             raise native.VsbError(native.VSB_EDIM, f"expected dimension {self.dimensions}, got {a.shape}")
 
@@ -110,6 +110,19 @@ class GpuIndex:
         if keys.shape[0] != rows.shape[0]:
             raise native.VsbError(native.VSB_EINVAL, "keys/rows length mismatch")
         check(self._lib.vsb_add(self._h, _ptr(keys), _ptr(rows), rows.shape[0]))
+
+    def add_each(self, keys, rows):
+        """Row-by-row semantics of the reference's one-message-per-vector ingest (usearch.rs:1020-1033): a duplicate
+        or reserved key fails only its own row.  -> (n_added, per-row status array)."""
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        self._check_dim(rows)
+        if keys.shape[0] != rows.shape[0]:
+            raise native.VsbError(native.VSB_EINVAL, "keys/rows length mismatch")
+        status = np.zeros(rows.shape[0], dtype=np.int32)
+        n = C.c_uint64(0)
+        check(self._lib.vsb_add_each(self._h, _ptr(keys), _ptr(rows), rows.shape[0], _ptr(status), C.byref(n)))
+        return int(n.value), status
 
     def remove_batch(self, keys) -> int:
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
@@ -135,8 +148,10 @@ class GpuIndex:
         return rows, keys
 
     def set_search_params(self, expansion_search: int = 0, max_iterations: int = 0, n_seeds: int = 0,
-                          min_graph_size: int = 0, search_width: int = 0, stream_threshold: int = 0) -> None:
-        p = VsbSearchParams(expansion_search, max_iterations, n_seeds, min_graph_size, search_width, stream_threshold)
+                          min_graph_size: int = 0, search_width: int = 0, stream_threshold: int = 0,
+                          filter_exact_below_pct: int = 0, expansion_add: int = 0) -> None:
+        p = VsbSearchParams(expansion_search, max_iterations, n_seeds, min_graph_size, search_width, stream_threshold,
+                            filter_exact_below_pct, expansion_add)
         check(self._lib.vsb_set_search_params(self._h, C.byref(p)))
 
     def set_instrumented(self, on: bool) -> None:
@@ -149,6 +164,11 @@ class GpuIndex:
         s = VsbStats()
         check(self._lib.vsb_get_stats(self._h, C.byref(s)))
         return {n: int(getattr(s, n)) for n, _ in VsbStats._fields_}
+
+    def build_stats(self) -> dict:
+        s = VsbBuildStats()
+        check(self._lib.vsb_get_build_stats(self._h, C.byref(s)))
+        return {n: int(getattr(s, n)) for n, _ in VsbBuildStats._fields_}
 
     def search_batch(self, queries, k: int, exact: bool = False, out=None):
         q = np.ascontiguousarray(queries, dtype=np.float32)
@@ -201,10 +221,11 @@ class GpuIndex:
         check(l.vsb_load(path.encode(), device, C.byref(h)))
         self = cls.__new__(cls)
         self._lib, self._h = l, h
-        st = VsbStats()
-        check(l.vsb_get_stats(h, C.byref(st)))
-        self.dimensions = None  # filled from the snapshot header by the caller if needed
-        self.metric = self.storage = None
+        opt = VsbOptions()
+        check(l.vsb_get_options(h, C.byref(opt)))  # dimensions / metric / storage come from the snapshot header
+        self.dimensions = int(opt.dimensions)
+        self.storage = Scalar(opt.storage)
+        self.metric = Metric.Hamming if self.storage == Scalar.B1 else Metric(opt.metric)
         return self
 
     def close(self) -> None:
@@ -235,6 +256,19 @@ class Batcher:
         check(self._lib.vsb_batcher_create(index._h, index.dimensions, max_batch, max_wait_us, C.byref(b)))
         self._b = b
         self._dim = index.dimensions
+
+    def add(self, key: int, row) -> None:
+        """fire-and-forget single-vector add (VsIndexModify::AddVector): staged, applied in blocks"""
+        r = np.ascontiguousarray(row, dtype=np.float32).ravel()
+        if r.shape[0] != self._dim:
+            raise native.VsbError(native.VSB_EDIM, f"expected dimension {self._dim}, got {r.shape[0]}")
+        check(self._lib.vsb_batcher_add(self._b, int(key), _ptr(r)))
+
+    def flush(self):
+        """-> (rows added, rows rejected) since creation; returns once everything staged so far is searchable"""
+        ok, bad = C.c_uint64(0), C.c_uint64(0)
+        check(self._lib.vsb_batcher_flush(self._b, C.byref(ok), C.byref(bad)))
+        return int(ok.value), int(bad.value)
 
     def search(self, query, k: int):
         q = np.ascontiguousarray(query, dtype=np.float32).ravel()
@@ -268,3 +302,33 @@ def merge_topk_strided_dev(d_keys: int, d_dists: int, parts: int, key_part_strid
                            stream: int) -> None:
     check(lib().vsb_merge_topk_strided_dev(d_keys, d_dists, parts, key_part_stride, dist_part_stride, q, k, d_out_keys,
                                            d_out_dists, d_out_counts or None, device, stream or None))
+
+
+class Exchange:
+    """Per-shard top-k exchange between one-process-per-GPU ranks over NVLink peer memory (vsb_xchg_*, csrc/xchg.cu).
+    `allgather_bytes(local: bytes) -> list[bytes]` is the host plumbing that swaps the 64-byte IPC handles
+    (torch.distributed.all_gather_object in bench.py)."""
+
+    def __init__(self, device: int, world: int, rank: int, max_queries: int, max_k: int, allgather_bytes):
+        self._lib = lib()
+        x = C.c_void_p()
+        check(self._lib.vsb_xchg_create(device, world, rank, max_queries, max_k, C.byref(x)))
+        self._x = x
+        mine = C.create_string_buffer(native.XCHG_HANDLE_BYTES)
+        check(self._lib.vsb_xchg_local_handle(self._x, mine))
+        handles = allgather_bytes(mine.raw)
+        blob = C.create_string_buffer(b"".join(handles), world * native.XCHG_HANDLE_BYTES)
+        check(self._lib.vsb_xchg_open(self._x, blob))
+
+    def allgather_merge(self, d_keys: int, d_dists: int, q: int, k: int, d_out_keys: int, d_out_dists: int,
+                        d_out_counts: int, stream: int) -> None:
+        check(self._lib.vsb_xchg_allgather_merge(self._x, d_keys, d_dists, q, k, d_out_keys, d_out_dists,
+                                                 d_out_counts or None, stream or None))
+
+    def check(self, stream: int) -> None:
+        check(self._lib.vsb_xchg_check(self._x, stream or None))
+
+    def close(self) -> None:
+        if getattr(self, "_x", None):
+            self._lib.vsb_xchg_destroy(self._x)
+            self._x = None

@@ -21,12 +21,14 @@ class VsbError(RuntimeError):
 class VsbOptions(C.Structure):
     _fields_ = [("dimensions", C.c_uint32), ("metric", C.c_int32), ("storage", C.c_int32),
                 ("connectivity", C.c_uint32), ("expansion_add", C.c_uint32), ("expansion_search", C.c_uint32),
-                ("device", C.c_int32), ("flags", C.c_uint32), ("seed", C.c_uint64)]
+                ("device", C.c_int32), ("flags", C.c_uint32), ("seed", C.c_uint64),
+                ("n_devices", C.c_int32), ("device_ids", C.c_int32 * 8)]
 
 
 class VsbSearchParams(C.Structure):
     _fields_ = [("expansion_search", C.c_uint32), ("max_iterations", C.c_uint32), ("n_seeds", C.c_uint32),
-                ("min_graph_size", C.c_uint32), ("search_width", C.c_uint32), ("stream_threshold", C.c_uint32)]
+                ("min_graph_size", C.c_uint32), ("search_width", C.c_uint32), ("stream_threshold", C.c_uint32),
+                ("filter_exact_below_pct", C.c_uint32), ("expansion_add", C.c_uint32)]
 
 
 class VsbStats(C.Structure):
@@ -38,6 +40,15 @@ class VsbStats(C.Structure):
                                           "exact_certified", "exact_fallback", "exact_scanned", "extra_seeds")]
 
 
+class VsbBuildStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rows", "allpairs_rows", "allpairs_flops", "allpairs_ns", "prune_ns",
+                                          "stream_rows", "stream_evals", "stream_parents", "stream_ns",
+                                          "refine_rows", "refine_evals", "refine_parents", "refine_ns", "seeds_ns",
+                                          "compact_ns", "total_ns", "traversal_row_bytes")]
+
+
+XCHG_HANDLE_BYTES = 64
+
 # every symbol include/vsb200.h declares: (name, restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = [
@@ -47,6 +58,7 @@ SYMBOLS = [
     ("vsb_capacity", C.c_uint64, [_P]),
     ("vsb_size", C.c_uint64, [_P]),
     ("vsb_add", C.c_int, [_P, _P, _P, C.c_uint64]),
+    ("vsb_add_each", C.c_int, [_P, _P, _P, C.c_uint64, _P, C.POINTER(C.c_uint64)]),
     ("vsb_remove", C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     ("vsb_contains", C.c_int, [_P, C.c_uint64]),
     ("vsb_build", C.c_int, [_P]),
@@ -54,6 +66,8 @@ SYMBOLS = [
     ("vsb_export_graph", C.c_int, [_P, _P, _P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     ("vsb_set_search_params", C.c_int, [_P, C.POINTER(VsbSearchParams)]),
     ("vsb_get_stats", C.c_int, [_P, C.POINTER(VsbStats)]),
+    ("vsb_get_build_stats", C.c_int, [_P, C.POINTER(VsbBuildStats)]),
+    ("vsb_get_options", C.c_int, [_P, C.POINTER(VsbOptions)]),
     ("vsb_set_instrumented", C.c_int, [_P, C.c_int]),
     ("vsb_set_kernel_timing", C.c_int, [_P, C.c_int]),
     ("vsb_search", C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P, _P, _P]),
@@ -65,6 +79,14 @@ SYMBOLS = [
     ("vsb_batcher_destroy", None, [_P]),
     ("vsb_batcher_search", C.c_int, [_P, _P, C.c_uint32, _P, _P, _P]),
     ("vsb_batcher_stats", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("vsb_batcher_add", C.c_int, [_P, C.c_uint64, _P]),
+    ("vsb_batcher_flush", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("vsb_xchg_create", C.c_int, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.POINTER(_P)]),
+    ("vsb_xchg_destroy", None, [_P]),
+    ("vsb_xchg_local_handle", C.c_int, [_P, _P]),
+    ("vsb_xchg_open", C.c_int, [_P, _P]),
+    ("vsb_xchg_allgather_merge", C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint32, _P, _P, _P, _P]),
+    ("vsb_xchg_check", C.c_int, [_P, _P]),
     ("vsb_save", C.c_int, [_P, C.c_char_p]),
     ("vsb_load", C.c_int, [C.c_char_p, C.c_int32, C.POINTER(_P)]),
     ("vsb_merge_topk_strided_dev", C.c_int, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _P, _P,
