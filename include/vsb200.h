@@ -100,6 +100,9 @@ typedef struct {
                                   admissible the exact bitmap scan is used instead of the graph (default 2;
                                   100 = always exact, UINT32_MAX = never) */
     uint32_t expansion_add;    /* beam width of the streaming insert / refinement searches; 0 = keep */
+    uint32_t traversal;        /* 0 = keep, 1 = the traversal copy the index was created with (default),
+                                  2 = walk the stored rows themselves (native scalar) although a copy exists */
+    uint32_t reserved;
 } vsb_search_params;
 
 /* Counters the roofline arithmetic is computed from. */
@@ -170,6 +173,10 @@ uint64_t vsb_size(const vsb_index* index);
  * whole call with VSB_EDUPKEY; size+n > capacity fails with VSB_EFULL.
  * Added vectors are searchable as soon as the call returns (brute-force tail). */
 vsb_status vsb_add(vsb_index* index, const uint64_t* keys, const float* rows, uint64_t n);
+/* Same as vsb_add, with the n x dimensions f32 rows already resident in HBM on the index's device (`d_rows` is a
+ * device pointer; `keys` stays a host pointer).  For bulk loads whose vectors are produced on the GPU (bench.py's
+ * on-device corpus generator, config C4: a billion rows never exist in host memory).  Single-device handles only. */
+vsb_status vsb_add_dev(vsb_index* index, const uint64_t* keys, const float* d_rows, uint64_t n);
 /* Same, but row by row like the reference's one-message-per-vector ingest (usearch.rs:1020-1033): a duplicate
  * or reserved key fails only its own row.  row_status (nullable) receives VSB_OK / VSB_EDUPKEY / VSB_EINVAL
  * per row, *n_added (nullable) the number of rows inserted.  VSB_EFULL if the valid rows do not fit. */
@@ -268,7 +275,7 @@ vsb_status vsb_batcher_flush(vsb_batcher* batcher, uint64_t* n_added, uint64_t* 
 typedef struct vsb_xchg vsb_xchg;
 #define VSB_XCHG_HANDLE_BYTES 64
 vsb_status vsb_xchg_create(int32_t device, uint32_t world, uint32_t rank, uint64_t max_queries, uint32_t max_k,
-                           vsb_xchg** out);
+                           uint64_t aux_bytes_per_rank, vsb_xchg** out);
 void vsb_xchg_destroy(vsb_xchg* x);
 /* writes VSB_XCHG_HANDLE_BYTES bytes: this rank's gather-buffer handle */
 vsb_status vsb_xchg_local_handle(vsb_xchg* x, void* handle_out);
@@ -278,6 +285,12 @@ vsb_status vsb_xchg_open(vsb_xchg* x, const void* handles);
 vsb_status vsb_xchg_allgather_merge(vsb_xchg* x, const uint64_t* d_keys, const float* d_distances, uint64_t q,
                                     uint32_t k, uint64_t* d_out_keys, float* d_out_distances,
                                     uint32_t* d_out_counts, void* stream);
+/* All-gather of one opaque block per rank over the same peer stores (bench.py's e2e leg: every rank uploads 1/N of
+ * the query batch over its own PCIe link and the slices are exchanged over NVLink).  bytes_per_rank: multiple of 16,
+ * <= aux_bytes_per_rank of vsb_xchg_create.  *d_gathered = device pointer to the world blocks in rank order,
+ * aux_bytes_per_rank apart, valid (stream-ordered) until the second-next call. */
+vsb_status vsb_xchg_allgather_bytes(vsb_xchg* x, const void* d_src, uint64_t bytes_per_rank, void** d_gathered,
+                                    void* stream);
 /* synchronises `stream` and reports VSB_ENCCL if the watchdog of a merge gave up on a rank (~2 s) */
 vsb_status vsb_xchg_check(vsb_xchg* x, void* stream);
 

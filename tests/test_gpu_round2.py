@@ -565,3 +565,35 @@ def test_peer_memory_exchange_between_processes(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"xchg ok {r}" in o, o[-2000:]
+
+
+# ---- bench tooling: the on-device corpus generator and its NumPy twin ------------------------------------------------
+def test_device_corpus_generator_matches_its_numpy_twin():
+    import torch
+    from importlib import import_module
+    ds = import_module("vector_store_b200.host.datasets")
+    for n, dim, row0, clusters, seed in [(5000, 768, 1_234_567, 2560, 1234), (3000, 128, 999_999_000, 1000, 4321),
+                                         (777, 100, 0, 16, 7)]:
+        buf = torch.empty((n, dim), dtype=torch.float32, device="cuda")
+        ds.embedding_mix_dev(buf.data_ptr(), n, dim, row0=row0, seed=seed, n_clusters=clusters)
+        torch.cuda.synchronize()
+        got = buf.cpu().numpy()
+        want = ds.embedding_mix(n, dim, row0=row0, seed=seed, n_clusters=clusters)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (n, dim)
+        assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+    # vsb_add_dev ingests rows straight from HBM: same index as the host path fed with the twin's rows
+    n, dim, k = 20_000, 96, 10
+    buf = torch.empty((n, dim), dtype=torch.float32, device="cuda")
+    ds.embedding_mix_dev(buf.data_ptr(), n, dim, row0=0, seed=1234, n_clusters=32)
+    torch.cuda.synchronize()
+    x = ds.embedding_mix(n, dim, n_clusters=32)
+    q = ds.embedding_mix(64, dim, seed=4321, n_clusters=32)
+    v = V()
+    keys = np.arange(n, dtype=np.uint64)
+    idx = v.GpuIndex(dim, v.Metric.Cos, v.Scalar.BF16)
+    idx.reserve(n)
+    idx.add_dev(keys, buf.data_ptr(), n)
+    gk, gd, gc = idx.search_batch(q, k, exact=True)
+    ok, od, oc, _ = O.exact_topk(x, q, k, O.COS, O.BF16, keys=keys)
+    assert_bit_equal(gk, gd, gc, ok, od, oc)
+    idx.close()

@@ -36,7 +36,7 @@ def _worker(rank, world, port, n, dim, nq, k, out_dir):
     q = ds.embedding_like(nq, dim, seed=4321, n_clusters=8)
     keys = (np.arange(n, dtype=np.uint64) * 7919) % np.uint64(1 << 40)
     lo, hi = shard.shard_range(n, rank, world)
-    lk, ld, _, _ = O.exact_topk(x[lo:hi], q, shard.local_k(k, world), O.COS, O.F32, keys=keys[lo:hi])
+    lk, ld, _, _ = O.exact_topk(x[lo:hi], q, k, O.COS, O.F32, keys=keys[lo:hi])
     gk, gd = shard.allgather_topk(torch.from_numpy(lk.view(np.int64)), torch.from_numpy(ld), world)
     mk, md = shard.merge_topk_host(gk.numpy().view(np.uint64), gd.numpy(), k)
     np.save(os.path.join(out_dir, f"k{rank}.npy"), mk)

@@ -111,7 +111,7 @@ vsb_status vsb_index::end_search(cudaStream_t s, const vsbi::View& v) {
 
 size_t vsb_index::hbm_bytes() {
     vsbi::View v = snapshot();
-    size_t s = ss.bytes() + ms.bytes();
+    size_t s = ss.bytes() + ms.bytes() + slots[0].buf.bytes + slots[1].buf.bytes;
     if (v.st) s += v.st->bytes();
     if (v.gr) s += v.gr->g.bytes;
     if (v.sd) s += v.sd->bytes();
@@ -200,7 +200,8 @@ vsb_status vsb_index::reserve(uint64_t cap) {
 }
 
 // row_status == nullptr: all-or-nothing (vsb_add).  Otherwise per-row verdicts (vsb_add_each).
-vsb_status vsb_index::add(const uint64_t* k, const float* r, uint64_t n, int32_t* row_status, uint64_t* n_added) {
+vsb_status vsb_index::add(const uint64_t* k, const float* r, uint64_t n, int32_t* row_status, uint64_t* n_added,
+                          bool rows_on_device) {
     if (n_added) *n_added = 0;
     if (n == 0) return VSB_OK;
     if (k == nullptr || r == nullptr) return fail(VSB_EINVAL, "null keys/rows");
@@ -245,6 +246,7 @@ vsb_status vsb_index::add(const uint64_t* k, const float* r, uint64_t n, int32_t
     const float* src = r;
     const uint64_t* src_keys = k;
     if (!take.empty()) {
+        if (rows_on_device) return fail(VSB_EINVAL, "vsb_add_dev is all-or-nothing");
         gathered.resize((size_t)nv * dim);
         gathered_keys.resize((size_t)nv);
         for (uint64_t j = 0; j < nv; ++j) {
@@ -254,23 +256,28 @@ vsb_status vsb_index::add(const uint64_t* k, const float* r, uint64_t n, int32_t
         src = gathered.data();
         src_keys = gathered_keys.data();
     }
-    const uint64_t chunk_rows = std::max<uint64_t>(1, (256ull << 20) / ((uint64_t)dim * 4));
+    // rows already in HBM (vsb_add_dev): one pass; host rows: 256 MB chunks through the staging buffer
+    const uint64_t chunk_rows = rows_on_device ? nv : std::max<uint64_t>(1, (256ull << 20) / ((uint64_t)dim * 4));
     for (uint64_t b = 0; b < nv; b += chunk_rows) {
         const uint64_t nb = std::min(chunk_rows, nv - b);
-        CU(ms.q_in.ensure(nb * dim * 4));
-        CU(cudaMemcpyAsync(ms.q_in.p, src + b * dim, nb * dim * 4, cudaMemcpyHostToDevice, mstream));
+        const float* d_src = src + b * dim;
+        if (!rows_on_device) {
+            CU(ms.q_in.ensure(nb * dim * 4));
+            CU(cudaMemcpyAsync(ms.q_in.p, src + b * dim, nb * dim * 4, cudaMemcpyHostToDevice, mstream));
+            d_src = ms.q_in.as<float>();
+        }
         const uint32_t s0 = w.n_slots + (uint32_t)b;
-        vsb::launch_convert_rows(storage, ms.q_in.as<float>(), (uint32_t)nb, dim, st.rows.as<uint8_t>() + (size_t)s0 * row_bytes,
+        vsb::launch_convert_rows(storage, d_src, (uint32_t)nb, dim, st.rows.as<uint8_t>() + (size_t)s0 * row_bytes,
                                  row_bytes, st.sq.as<float>() + s0, st.nrm.as<float>() + s0, mstream);
         CU(cudaGetLastError());
         if (trav16) {
-            vsb::launch_convert_rows(VSB_BF16, ms.q_in.as<float>(), (uint32_t)nb, dim,
+            vsb::launch_convert_rows(VSB_BF16, d_src, (uint32_t)nb, dim,
                                      st.rows16.as<uint8_t>() + (size_t)s0 * row_bytes16, row_bytes16, st.sq16.as<float>() + s0,
                                      st.nrm16.as<float>() + s0, mstream);
             CU(cudaGetLastError());
         }
         if (trav8) {
-            vsb::launch_convert_rows_i8s(ms.q_in.as<float>(), (uint32_t)nb, dim, dim, st.rows8.as<uint8_t>() + (size_t)s0 * row_bytes8,
+            vsb::launch_convert_rows_i8s(d_src, (uint32_t)nb, dim, dim, st.rows8.as<uint8_t>() + (size_t)s0 * row_bytes8,
                                          row_bytes8, st.sq8.as<float>() + s0, st.nrm8.as<float>() + s0, mstream);
             CU(cudaGetLastError());
         }
@@ -472,6 +479,11 @@ void destroy_single(vsb_index* ix) {
     cudaDeviceSynchronize();
     ix->t_resolve();
     ix->reap_inflight(true);
+    for (auto& sl : ix->slots) {
+        if (sl.cs) cudaStreamDestroy(sl.cs);
+        if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    }
     if (ix->stream) cudaStreamDestroy(ix->stream);
     if (ix->mstream) cudaStreamDestroy(ix->mstream);
     delete ix;
@@ -526,6 +538,15 @@ vsb_status vsb_add(vsb_index* ix, const uint64_t* keys, const float* rows, uint6
     if (ix->sharded) return vsbi::sharded_add(ix, keys, rows, n, nullptr, nullptr);
     std::lock_guard<std::mutex> g(ix->mut_mu);
     return ix->add(keys, rows, n, nullptr, nullptr);
+}
+
+vsb_status vsb_add_dev(vsb_index* ix, const uint64_t* keys, const float* d_rows, uint64_t n) {
+    if (!ix) return fail(VSB_EINVAL, "null index");
+    if (ix->sharded) return fail(VSB_EINVAL, "vsb_add_dev takes rows that already live on the index's device: add to a shard handle");
+    std::lock_guard<std::mutex> g(ix->mut_mu);
+    CU(cudaSetDevice(ix->device));
+    CU(cudaDeviceSynchronize());  // the rows were produced on a stream of the caller's
+    return ix->add(keys, d_rows, n, nullptr, nullptr, true);
 }
 
 vsb_status vsb_add_each(vsb_index* ix, const uint64_t* keys, const float* rows, uint64_t n, int32_t* row_status,
@@ -606,6 +627,7 @@ vsb_status vsb_set_search_params(vsb_index* ix, const vsb_search_params* p) {
         if (p->n_seeds) ix->n_seeds = std::min<uint32_t>(p->n_seeds, 32);
         if (p->min_graph_size) ix->min_graph_size = p->min_graph_size;
         if (p->search_width) ix->search_width = std::min<uint32_t>(p->search_width, 4);
+        if (p->traversal) ix->native_traversal = p->traversal == 2;
         if (p->filter_exact_below_pct) ix->filter_min_pct = p->filter_exact_below_pct == 0xFFFFFFFFu ? 0 : std::min<uint32_t>(p->filter_exact_below_pct, 101);
     }
     if (p->stream_threshold || p->expansion_add) {

@@ -21,6 +21,7 @@
 //   Seeds : contiguous copy of the entry-point sample ("upper layer")
 #pragma once
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <deque>
@@ -187,9 +188,20 @@ struct vsb_index {
         vsbi::View view;
     };
     std::deque<InFlight> inflight;  // views of searches whose kernels may still be running
+    // host-pointer searches of >= 1024 queries: two staging slots with their own copy stream (search_host)
+    struct HostSlot {
+        vsbi::DevBuf buf;
+        cudaStream_t cs = nullptr;
+        cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+        bool busy = false;
+    };
+    std::mutex slot_mu;
+    std::condition_variable slot_cv;
+    HostSlot slots[2];
     // runtime parameters (set under search_mu)
     uint32_t itopk = 64, max_iters = 0, n_seeds = 32, min_graph_size = 4096, search_width = 1;
     uint32_t filter_min_pct = 2;  // filtered ANN: below this share of admissible rows the exact bitmap scan is used
+    bool native_traversal = false;  // runtime override of VSB_FLAG_*_TRAVERSAL: K4 walks the stored rows themselves
     bool instrumented = false;
     uint64_t last_evals = 0, last_parents = 0, last_queries = 0;
     uint64_t cert_ok = 0, cert_fallback = 0, cert_scanned = 0;
@@ -237,7 +249,8 @@ struct vsb_index {
 
     vsb_status new_store(uint64_t cap, std::shared_ptr<vsbi::Store>& out);
     vsb_status reserve(uint64_t cap);
-    vsb_status add(const uint64_t* k, const float* r, uint64_t n, int32_t* row_status, uint64_t* n_added);
+    vsb_status add(const uint64_t* k, const float* r, uint64_t n, int32_t* row_status, uint64_t* n_added,
+                   bool rows_on_device = false);
     vsb_status remove(const uint64_t* k, uint64_t n, uint64_t* removed);
     vsb_status compact(bool keep_graph);
     vsb_status build();
@@ -256,6 +269,7 @@ struct vsb_index {
     struct GraphRun {
         uint32_t itopk = 64, max_iters = 0, n_seeds = 32, search_width = 1;
         bool count = false;  // instrumented launch (E / P counters)
+        bool native = false; // ignore the traversal copies
         const uint32_t* allow = nullptr;  // filtered ANN: bitmap over (key & 2^48-1)
         uint64_t allow_bits = 0;
     };

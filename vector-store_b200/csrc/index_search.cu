@@ -186,13 +186,15 @@ vsb_status vsb_index::graph_block(const View& v, Scratch& sc, const GraphRun& ru
     const vsbi::Seeds& sd = *v.sd;
     const vsb::RowsView x = rows_view(v);
     const uint32_t* deny_bm = v.any_tombstone ? st.deny.as<uint32_t>() : nullptr;
-    const bool rerank = trav16 && packed_out == nullptr;
+    // the traversal copies serve searches; `native` (a runtime override, searches only) walks the stored rows instead
+    const bool t16 = trav16 && !(run.native && packed_out == nullptr);
+    const bool rerank = t16 && packed_out == nullptr;
     // ---- bf16 shadow of the queries (f32 storage: tensor-core seed layer and/or bf16 traversal) ----
     bool seed_tc = tc_enabled && vsb::exact_tc_supported(storage, metric) && nb >= 16;
     vsb::RowsView q16v;
     if (q16_in != nullptr) {
         q16v = *q16_in;
-    } else if (storage == VSB_F32 && (seed_tc || trav16)) {
+    } else if (storage == VSB_F32 && (seed_tc || t16)) {
         CU(sc.q16_rows.ensure((size_t)nb * row_bytes16));
         CU(sc.q16_sq.ensure((size_t)nb * 4));
         CU(sc.q16_nrm.ensure((size_t)nb * 4));
@@ -258,11 +260,11 @@ vsb_status vsb_index::graph_block(const View& v, Scratch& sc, const GraphRun& ru
     CU(cudaGetLastError());
     // ---- K4 beam search (on the bf16 traversal copy when VSB_FLAG_BF16_TRAVERSAL is set) ----
     vsb::SearchParams gp;
-    gp.storage = trav16 ? VSB_BF16 : storage;
+    gp.storage = t16 ? VSB_BF16 : storage;
     gp.metric = metric;
-    gp.q = trav16 ? q16v : qv;
+    gp.q = t16 ? q16v : qv;
     gp.x = x;
-    if (trav16) {
+    if (t16) {
         gp.x.rows = st.rows16.as<uint8_t>();
         gp.x.sq = st.sq16.as<float>();
         gp.x.nrm = st.nrm16.as<float>();
@@ -436,6 +438,7 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
             run.n_seeds = n_seeds;
             run.search_width = search_width;
             run.count = instrumented;
+            run.native = native_traversal;
             if (filtered_graph) {
                 run.allow = d_allow;
                 run.allow_bits = allow_bits;
@@ -477,6 +480,8 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
     return VSB_OK;
 }
 
+static uint64_t popcount_words(const uint32_t* w, size_t n_words, uint64_t bits);
+// (defined below search_host's slot path, which needs it)
 static uint64_t popcount_words(const uint32_t* w, size_t n_words, uint64_t bits) {
     uint64_t c = 0;
     const size_t full = (size_t)(bits / 32);
@@ -491,13 +496,71 @@ vsb_status vsb_index::search_host(const float* queries, uint64_t nq, uint32_t k,
     if (nq == 0) return VSB_OK;
     if (k == 0) return fail(VSB_EINVAL, "k must be > 0");
     if (queries == nullptr || keys_out == nullptr || dists_out == nullptr) return fail(VSB_EINVAL, "null buffer");
+    const size_t in_bytes = (size_t)nq * dim * 4;
+    const size_t keys_bytes = (size_t)nq * k * 8, dists_bytes = (size_t)nq * k * 4, counts_bytes = (size_t)nq * 4;
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    if (nq >= 1024) {
+        // Large batches are PIPELINED across concurrent callers (the reference serves ann requests from a worker
+        // pool, worker.rs:44-118): each call takes one of two staging slots, uploads its queries on the slot's copy
+        // stream, runs its kernels on the search stream under search_mu, and downloads its results on the copy
+        // stream again — so one caller's H2D / D2H overlaps another caller's kernels.
+        CU(cudaSetDevice(device));
+        int si = -1;
+        {
+            std::unique_lock<std::mutex> lk(slot_mu);
+            slot_cv.wait(lk, [&] { return !slots[0].busy || !slots[1].busy; });
+            si = slots[0].busy ? 1 : 0;
+            slots[si].busy = true;
+        }
+        HostSlot& sl = slots[si];
+        struct Release {
+            vsb_index* ix;
+            int si;
+            ~Release() {
+                std::lock_guard<std::mutex> lk(ix->slot_mu);
+                ix->slots[si].busy = false;
+                ix->slot_cv.notify_one();
+            }
+        } release{this, si};
+        if (sl.cs == nullptr) {
+            CU(cudaStreamCreateWithFlags(&sl.cs, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+        }
+        CU(sl.buf.ensure(al(in_bytes) + al(keys_bytes) + al(dists_bytes) + al(counts_bytes)));
+        uint8_t* base = sl.buf.as<uint8_t>();
+        float* dq = reinterpret_cast<float*>(base);
+        uint64_t* dk = reinterpret_cast<uint64_t*>(base + al(in_bytes));
+        float* dd = reinterpret_cast<float*>(base + al(in_bytes) + al(keys_bytes));
+        uint32_t* dc = reinterpret_cast<uint32_t*>(base + al(in_bytes) + al(keys_bytes) + al(dists_bytes));
+        CU(cudaMemcpyAsync(dq, queries, in_bytes, cudaMemcpyHostToDevice, sl.cs));
+        CU(cudaEventRecord(sl.ev_in, sl.cs));
+        {
+            std::lock_guard<std::mutex> g(search_mu);
+            const uint32_t* d_allow = nullptr;
+            uint64_t allow_pop = 0;
+            if (allow_bitmap != nullptr) {
+                const size_t words = (size_t)((allow_bits + 31) / 32);
+                CU(ss.allow.ensure(std::max<size_t>(words * 4, 16)));
+                CU(cudaMemcpyAsync(ss.allow.p, allow_bitmap, words * 4, cudaMemcpyHostToDevice, stream));
+                d_allow = ss.allow.as<uint32_t>();
+                allow_pop = popcount_words(allow_bitmap, words, allow_bits);
+            }
+            CU(cudaStreamWaitEvent(stream, sl.ev_in, 0));
+            ST(search_dev(dq, nq, k, dk, dd, dc, stream, exact, d_allow, allow_bits, allow_pop));
+            CU(cudaEventRecord(sl.ev_done, stream));
+        }
+        CU(cudaStreamWaitEvent(sl.cs, sl.ev_done, 0));
+        CU(cudaMemcpyAsync(keys_out, dk, keys_bytes, cudaMemcpyDeviceToHost, sl.cs));
+        CU(cudaMemcpyAsync(dists_out, dd, dists_bytes, cudaMemcpyDeviceToHost, sl.cs));
+        if (counts_out) CU(cudaMemcpyAsync(counts_out, dc, counts_bytes, cudaMemcpyDeviceToHost, sl.cs));
+        CU(cudaStreamSynchronize(sl.cs));
+        return VSB_OK;
+    }
     std::lock_guard<std::mutex> g(search_mu);
     CU(cudaSetDevice(device));
     ST(begin_search(stream));
     vsbi::DevBuf& d_in = ss.q_in;
-    const size_t in_bytes = (size_t)nq * dim * 4;
-    const size_t keys_bytes = (size_t)nq * k * 8, dists_bytes = (size_t)nq * k * 4, counts_bytes = (size_t)nq * 4;
-    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
     CU(d_in.ensure(al(in_bytes) + al(keys_bytes) + al(dists_bytes) + al(counts_bytes)));
     uint8_t* base = d_in.as<uint8_t>();
     float* dq = reinterpret_cast<float*>(base);

@@ -21,15 +21,20 @@ using vsbi::fail;
 
 namespace {
 
-constexpr uint32_t kFlagBytes = 1024;  // flags[world] (u64) + push counter + error word, one block at the buffer head
+// one block at the buffer head: result flags[8] (u64) @0, aux flags[8] (u64) @64, result push counter @128, error word
+// @132, aux push counter @136
+constexpr uint32_t kFlagBytes = 1024;
+constexpr uint32_t kAuxFlagOff = 64, kCounterOff = 128, kErrorOff = 132, kAuxCounterOff = 136;
 
 struct Layout {
     uint64_t cap;     // max_q * max_k entries per rank part
     uint32_t world;
+    uint64_t aux;     // bytes per rank of the auxiliary all-gather region (query slices), multiple of 16
     size_t part_keys() const { return (size_t)cap * 8; }
     size_t part_dists() const { return (size_t)cap * 4; }
     size_t parity_bytes() const { return (size_t)world * (part_keys() + part_dists()); }
-    size_t total() const { return kFlagBytes + 2 * parity_bytes(); }
+    size_t aux_off(uint32_t parity, uint32_t part) const { return kFlagBytes + 2 * parity_bytes() + ((size_t)parity * world + part) * aux; }
+    size_t total() const { return kFlagBytes + 2 * parity_bytes() + 2 * (size_t)world * aux; }
     size_t keys_off(uint32_t parity, uint32_t part) const { return kFlagBytes + parity * parity_bytes() + (size_t)part * part_keys(); }
     size_t dists_off(uint32_t parity, uint32_t part) const {
         return kFlagBytes + parity * parity_bytes() + (size_t)world * part_keys() + (size_t)part * part_dists();
@@ -71,6 +76,29 @@ __global__ void __launch_bounds__(256) xchg_push_kernel(PeerTable peers, uint32_
     }
 }
 
+// all-gather of an opaque byte block per rank (the e2e path's query slices): same push / flag protocol
+__global__ void __launch_bounds__(256) xchg_push_bytes_kernel(PeerTable peers, uint32_t world, uint32_t rank, size_t dst_off,
+                                                              const uint4* __restrict__ src, size_t n16,
+                                                              unsigned long long step, uint32_t* counter) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = src[i];
+        for (uint32_t p = 0; p < world; ++p) reinterpret_cast<uint4*>(peers.base[p] + dst_off)[i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t done = atomicAdd(counter, 1u);
+        if (done == gridDim.x - 1) {
+            *counter = 0;
+            __threadfence_system();
+            for (uint32_t p = 0; p < world; ++p) {
+                unsigned long long* flag = reinterpret_cast<unsigned long long*>(peers.base[p] + kAuxFlagOff) + rank;
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(step) : "memory");
+            }
+        }
+    }
+}
+
 // one CTA, one thread per rank: wait until every rank's flag has reached `step`
 __global__ void xchg_wait_kernel(const unsigned long long* flags, uint32_t world, unsigned long long step,
                                  long long timeout_cycles, uint32_t* error) {
@@ -98,19 +126,20 @@ struct vsb_xchg {
     uint64_t max_q = 0;
     uint32_t max_k = 0;
     uint8_t* local = nullptr;
-    uint32_t* counter = nullptr;  // device word inside the local flag block
+    uint32_t* counter = nullptr;  // device words inside the local flag block
+    uint32_t* aux_counter = nullptr;
     uint32_t* error = nullptr;
     uint32_t* h_error = nullptr;  // pinned mirror, polled without a sync
     std::vector<uint8_t*> peer;
     std::vector<bool> opened;
-    unsigned long long step = 0;
+    unsigned long long step = 0, aux_step = 0;
     long long timeout_cycles = 4000000000ll;  // ~2 s at 2 GHz
 };
 
 extern "C" {
 
 vsb_status vsb_xchg_create(int32_t device, uint32_t world, uint32_t rank, uint64_t max_queries, uint32_t max_k,
-                           vsb_xchg** out) {
+                           uint64_t aux_bytes_per_rank, vsb_xchg** out) {
     if (!out) return fail(VSB_EINVAL, "null out");
     *out = nullptr;
     if (world < 1 || world > 8 || rank >= world) return fail(VSB_EINVAL, "world must be 1..8 and rank < world");
@@ -125,14 +154,16 @@ vsb_status vsb_xchg_create(int32_t device, uint32_t world, uint32_t rank, uint64
     x->max_k = max_k;
     x->lay.cap = (max_queries * max_k + 1) & ~1ull;
     x->lay.world = world;
+    x->lay.aux = (aux_bytes_per_rank + 15) & ~15ull;
     cudaError_t e = cudaMalloc(&x->local, x->lay.total());  // plain cudaMalloc: CUDA IPC cannot export pool/VMM memory
     if (e != cudaSuccess) {
         delete x;
         return fail(VSB_EOOM, "cudaMalloc(%zu): %s", x->lay.total(), cudaGetErrorString(e));
     }
     cudaMemset(x->local, 0, kFlagBytes);
-    x->counter = reinterpret_cast<uint32_t*>(x->local + 8 * 8 + 64);
-    x->error = x->counter + 1;
+    x->counter = reinterpret_cast<uint32_t*>(x->local + kCounterOff);
+    x->error = reinterpret_cast<uint32_t*>(x->local + kErrorOff);
+    x->aux_counter = reinterpret_cast<uint32_t*>(x->local + kAuxCounterOff);
     x->peer.assign(world, nullptr);
     x->opened.assign(world, false);
     x->peer[rank] = x->local;
@@ -208,6 +239,32 @@ vsb_status vsb_xchg_allgather_merge(vsb_xchg* x, const uint64_t* d_keys, const f
     vsb::g_kernel_launches += 2;
     CU(cudaGetLastError());
     (void)err;
+    return VSB_OK;
+}
+
+vsb_status vsb_xchg_allgather_bytes(vsb_xchg* x, const void* d_src, uint64_t bytes_per_rank, void** d_gathered, void* stream_) {
+    if (!x || !d_src || !d_gathered) return fail(VSB_EINVAL, "null argument");
+    if (bytes_per_rank == 0 || bytes_per_rank % 16 || bytes_per_rank > x->lay.aux)
+        return fail(VSB_EINVAL, "bytes_per_rank must be a multiple of 16 and <= the aux capacity %llu", (unsigned long long)x->lay.aux);
+    for (uint32_t r = 0; r < x->lay.world; ++r)
+        if (!x->peer[r]) return fail(VSB_ENCCL, "rank %u's buffer is not mapped: call vsb_xchg_open first", r);
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    CU(cudaSetDevice(x->device));
+    x->aux_step += 1;
+    const uint32_t parity = (uint32_t)(x->aux_step & 1);
+    PeerTable t{};
+    for (uint32_t r = 0; r < x->lay.world; ++r) t.base[r] = x->peer[r];
+    const size_t n16 = (size_t)bytes_per_rank / 16;
+    const unsigned grid = (unsigned)std::min<size_t>((n16 + 255) / 256, 148 * 4);
+    // the gathered blocks are lay.aux bytes apart (capacity stride): callers that need them contiguous create the
+    // exchange with aux_bytes_per_rank == bytes_per_rank (bench.py does)
+    xchg_push_bytes_kernel<<<grid, 256, 0, s>>>(t, x->lay.world, x->rank, x->lay.aux_off(parity, x->rank),
+                                                static_cast<const uint4*>(d_src), n16, x->aux_step, x->aux_counter);
+    xchg_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const unsigned long long*>(x->local + kAuxFlagOff), x->lay.world,
+                                      x->aux_step, x->timeout_cycles, x->error);
+    vsb::g_kernel_launches += 2;
+    CU(cudaGetLastError());
+    *d_gathered = x->local + x->lay.aux_off(parity, 0);
     return VSB_OK;
 }
 

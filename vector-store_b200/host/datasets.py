@@ -22,6 +22,92 @@ def embedding_like(n: int, dim: int = 768, seed: int = 1234, n_clusters: int = 2
     return np.ascontiguousarray(x, dtype=np.float32)
 
 
+# ---- counter-based mixture generator: NumPy twin of tools/synth/synth.cu (bit for bit) ----
+_K_A, _K_B, _K_CLUSTER = np.uint64(0x9E3779B97F4A7C15), np.uint64(0xD1B54A32D192ED03), np.uint64(0xC1057E7)
+_INV_STD = np.float32(float.fromhex("0x1.bb67aep-16"))  # 1 / sqrt(4 * (65536^2 - 1) / 12)
+
+
+def _mix64(z: np.ndarray) -> np.ndarray:
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def _h3(seed, a, b) -> np.ndarray:
+    return _mix64(np.uint64(seed) + a * _K_A + b * _K_B)
+
+
+def _gauss(h: np.ndarray) -> np.ndarray:
+    m = np.uint64(0xFFFF)
+    s = ((h & m) + ((h >> np.uint64(16)) & m) + ((h >> np.uint64(32)) & m) + (h >> np.uint64(48))).astype(np.int64) - 131070
+    return s.astype(np.float32) * _INV_STD
+
+
+def embedding_mix(n: int, dim: int = 768, row0: int = 0, seed: int = 1234, n_clusters: int = 256, sigma: float = 0.3,
+                  centers_seed: int = 99) -> np.ndarray:
+    """Rows [row0, row0 + n) of the counter-based Gaussian-mixture corpus, L2-normalised — exactly what
+    tools/synth/synth.cu writes into HBM for the same arguments (element (r, j) depends only on (seed, r, j)):
+    integer hashing for the randomness, individually rounded fp32 operations in the kernel's order for the rest."""
+    out = np.empty((n, dim), dtype=np.float32)
+    with np.errstate(over="ignore"):
+        j1 = np.arange(1, dim + 1, dtype=np.uint64)[None, :]
+        centers = _gauss(_h3(centers_seed, np.arange(n_clusters, dtype=np.uint64)[:, None], j1))
+        lanes = np.arange(32)
+        sig = np.float32(sigma)
+        CH = 8192
+
+        def fill(c0: int) -> None:
+            r = np.arange(row0 + c0, row0 + min(c0 + CH, n), dtype=np.uint64)
+            which = (_h3(np.uint64(seed) ^ _K_CLUSTER, r, np.uint64(0)) % np.uint64(n_clusters)).astype(np.int64)
+            x = centers[which] + sig * _gauss(_h3(seed, r[:, None], j1))
+            acc = np.zeros((len(r), 32), dtype=np.float32)
+            for t in range(0, dim, 32):
+                blk = x[:, t:t + 32]
+                acc[:, :blk.shape[1]] = acc[:, :blk.shape[1]] + blk * blk
+            for s in (16, 8, 4, 2, 1):
+                acc = acc + acc[:, lanes ^ s]
+            inv = np.float32(1.0) / np.sqrt(acc[:, 0])
+            out[c0:c0 + len(r)] = x * inv[:, None]
+
+        starts = list(range(0, n, CH))
+        if len(starts) > 1:  # NumPy releases the GIL inside its loops: chunks run on all host cores
+            import os
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as pool:
+                list(pool.map(fill, starts))
+        else:
+            for c0 in starts:
+                fill(c0)
+    return out
+
+
+_synth = None
+
+
+def synth_lib():
+    """tools/synth/libvsbsynth.so (built by __graft_entry__.build()); bench / test tooling, not the product library."""
+    global _synth
+    if _synth is None:
+        import ctypes as C
+        import os
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tools", "synth",
+                            "libvsbsynth.so")
+        lib = C.CDLL(path)
+        lib.vsbsynth_embedding_mix.restype = C.c_int
+        lib.vsbsynth_embedding_mix.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_float,
+                                               C.c_uint64, C.c_uint64, C.c_void_p]
+        _synth = lib
+    return _synth
+
+
+def embedding_mix_dev(d_out: int, n: int, dim: int, row0: int = 0, seed: int = 1234, n_clusters: int = 256,
+                      sigma: float = 0.3, centers_seed: int = 99, stream: int = 0) -> None:
+    """Same rows, written to the device buffer `d_out` (raw pointer, n x dim f32) by the CUDA generator."""
+    rc = synth_lib().vsbsynth_embedding_mix(d_out, row0, n, dim, n_clusters, sigma, seed, centers_seed, stream or None)
+    if rc != 0:
+        raise RuntimeError(f"vsbsynth_embedding_mix failed ({rc})")
+
+
 # ---- N4: .fbin / .ibin files (crates/benchmark/src/data/fbin.rs:23-148: u32 count, u32 dimension, rows) ----
 def read_bin_header(path: str) -> tuple[int, int]:
     with open(path, "rb") as f:

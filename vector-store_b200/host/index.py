@@ -111,6 +111,13 @@ class GpuIndex:
             raise native.VsbError(native.VSB_EINVAL, "keys/rows length mismatch")
         check(self._lib.vsb_add(self._h, _ptr(keys), _ptr(rows), rows.shape[0]))
 
+    def add_dev(self, keys, d_rows: int, n: int) -> None:
+        """rows already in HBM on the index's device (raw device pointer to n x dimensions f32)"""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        if keys.shape[0] != n:
+            raise native.VsbError(native.VSB_EINVAL, "keys/rows length mismatch")
+        check(self._lib.vsb_add_dev(self._h, _ptr(keys), d_rows, n))
+
     def add_each(self, keys, rows):
         """Row-by-row semantics of the reference's one-message-per-vector ingest (usearch.rs:1020-1033): a duplicate
         or reserved key fails only its own row.  -> (n_added, per-row status array)."""
@@ -149,9 +156,9 @@ class GpuIndex:
 
     def set_search_params(self, expansion_search: int = 0, max_iterations: int = 0, n_seeds: int = 0,
                           min_graph_size: int = 0, search_width: int = 0, stream_threshold: int = 0,
-                          filter_exact_below_pct: int = 0, expansion_add: int = 0) -> None:
+                          filter_exact_below_pct: int = 0, expansion_add: int = 0, traversal: int = 0) -> None:
         p = VsbSearchParams(expansion_search, max_iterations, n_seeds, min_graph_size, search_width, stream_threshold,
-                            filter_exact_below_pct, expansion_add)
+                            filter_exact_below_pct, expansion_add, traversal, 0)
         check(self._lib.vsb_set_search_params(self._h, C.byref(p)))
 
     def set_instrumented(self, on: bool) -> None:
@@ -309,10 +316,11 @@ class Exchange:
     `allgather_bytes(local: bytes) -> list[bytes]` is the host plumbing that swaps the 64-byte IPC handles
     (torch.distributed.all_gather_object in bench.py)."""
 
-    def __init__(self, device: int, world: int, rank: int, max_queries: int, max_k: int, allgather_bytes):
+    def __init__(self, device: int, world: int, rank: int, max_queries: int, max_k: int, allgather_bytes,
+                 aux_bytes_per_rank: int = 0):
         self._lib = lib()
         x = C.c_void_p()
-        check(self._lib.vsb_xchg_create(device, world, rank, max_queries, max_k, C.byref(x)))
+        check(self._lib.vsb_xchg_create(device, world, rank, max_queries, max_k, aux_bytes_per_rank, C.byref(x)))
         self._x = x
         mine = C.create_string_buffer(native.XCHG_HANDLE_BYTES)
         check(self._lib.vsb_xchg_local_handle(self._x, mine))
@@ -324,6 +332,12 @@ class Exchange:
                         d_out_counts: int, stream: int) -> None:
         check(self._lib.vsb_xchg_allgather_merge(self._x, d_keys, d_dists, q, k, d_out_keys, d_out_dists,
                                                  d_out_counts or None, stream or None))
+
+    def allgather_rows(self, d_src: int, bytes_per_rank: int, stream: int) -> int:
+        """-> device pointer to the world blocks in rank order (aux_bytes_per_rank apart)"""
+        out = C.c_void_p()
+        check(self._lib.vsb_xchg_allgather_bytes(self._x, d_src, bytes_per_rank, C.byref(out), stream or None))
+        return int(out.value)
 
     def check(self, stream: int) -> None:
         check(self._lib.vsb_xchg_check(self._x, stream or None))

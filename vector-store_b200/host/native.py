@@ -28,7 +28,8 @@ class VsbOptions(C.Structure):
 class VsbSearchParams(C.Structure):
     _fields_ = [("expansion_search", C.c_uint32), ("max_iterations", C.c_uint32), ("n_seeds", C.c_uint32),
                 ("min_graph_size", C.c_uint32), ("search_width", C.c_uint32), ("stream_threshold", C.c_uint32),
-                ("filter_exact_below_pct", C.c_uint32), ("expansion_add", C.c_uint32)]
+                ("filter_exact_below_pct", C.c_uint32), ("expansion_add", C.c_uint32), ("traversal", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class VsbStats(C.Structure):
@@ -58,6 +59,7 @@ SYMBOLS = [
     ("vsb_capacity", C.c_uint64, [_P]),
     ("vsb_size", C.c_uint64, [_P]),
     ("vsb_add", C.c_int, [_P, _P, _P, C.c_uint64]),
+    ("vsb_add_dev", C.c_int, [_P, _P, _P, C.c_uint64]),
     ("vsb_add_each", C.c_int, [_P, _P, _P, C.c_uint64, _P, C.POINTER(C.c_uint64)]),
     ("vsb_remove", C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     ("vsb_contains", C.c_int, [_P, C.c_uint64]),
@@ -81,7 +83,8 @@ SYMBOLS = [
     ("vsb_batcher_stats", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("vsb_batcher_add", C.c_int, [_P, C.c_uint64, _P]),
     ("vsb_batcher_flush", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
-    ("vsb_xchg_create", C.c_int, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.POINTER(_P)]),
+    ("vsb_xchg_create", C.c_int, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(_P)]),
+    ("vsb_xchg_allgather_bytes", C.c_int, [_P, _P, C.c_uint64, C.POINTER(_P), _P]),
     ("vsb_xchg_destroy", None, [_P]),
     ("vsb_xchg_local_handle", C.c_int, [_P, _P]),
     ("vsb_xchg_open", C.c_int, [_P, _P]),
