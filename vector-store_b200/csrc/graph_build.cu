@@ -423,6 +423,47 @@ __global__ void first_unreached_kernel(const uint8_t* __restrict__ state, const 
     atomicMin(out, i);
 }
 
+// The first `cap` unreached live nodes in slot order (deterministic): ONE CTA, thread t owns a contiguous 16-byte
+// aligned range of the state array; count, block-scan, then write.  out[0] = how many were found (<= cap),
+// out[1..] = their slots.
+__global__ void __launch_bounds__(1024) collect_unreached_kernel(const uint8_t* __restrict__ state,
+                                                                 const uint32_t* __restrict__ deny, uint32_t n, uint32_t cap,
+                                                                 uint32_t* __restrict__ out) {
+    __shared__ uint32_t s_cnt[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t chunk = (((n + 1023) / 1024) + 15) / 16 * 16;
+    const uint32_t lo = min(n, t * chunk), hi = min(n, lo + chunk);
+    auto unreached = [&](uint32_t i) { return state[i] == 0 && !(deny != nullptr && bit_test(deny, i)); };
+    uint32_t c = 0;
+    for (uint32_t i = lo; i < hi; i += 16) {
+        const uint4 v = *reinterpret_cast<const uint4*>(state + i);  // the buffer is padded to 16 bytes past n
+        auto all_nonzero = [](uint32_t w) { return ((w | (w >> 1)) & 0x01010101u) == 0x01010101u; };  // states are 0, 1, 2
+        if (all_nonzero(v.x) && all_nonzero(v.y) && all_nonzero(v.z) && all_nonzero(v.w)) continue;  // the common case
+        for (uint32_t j = i; j < min(hi, i + 16); ++j) c += unreached(j) ? 1u : 0u;
+    }
+    s_cnt[t] = c;
+    __syncthreads();
+    // exclusive scan (Hillis-Steele over 1024 entries)
+    for (uint32_t off = 1; off < 1024; off <<= 1) {
+        const uint32_t v = t >= off ? s_cnt[t - off] : 0u;
+        __syncthreads();
+        s_cnt[t] += v;
+        __syncthreads();
+    }
+    const uint32_t total = s_cnt[1023];
+    uint32_t pos = s_cnt[t] - c;
+    if (t == 0) out[0] = total < cap ? total : cap;
+    if (c == 0 || pos >= cap) return;
+    for (uint32_t i = lo; i < hi && pos < cap; ++i)
+        if (unreached(i)) out[1 + pos++] = i;
+}
+
+void launch_collect_unreached(const uint8_t* state, const uint32_t* deny, uint32_t n, uint32_t cap, uint32_t* out,
+                              cudaStream_t stream) {
+    collect_unreached_kernel<<<1, 1024, 0, stream>>>(state, deny, n, cap, out);
+    g_kernel_launches += 1;
+}
+
 void launch_reach_mark(uint8_t* state, const uint32_t* seeds, uint32_t n_seeds, cudaStream_t stream) {
     if (n_seeds == 0) return;
     reach_mark_kernel<<<(n_seeds + 255) / 256, 256, 0, stream>>>(state, seeds, n_seeds);

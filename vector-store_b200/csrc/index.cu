@@ -34,6 +34,27 @@ vsb_status fail(vsb_status st, const char* fmt, ...) {
     return st;
 }
 
+// one allocator stream per device (see DevBuf); the device's default pool is told to keep what it is given back
+cudaStream_t pool_stream(int device) {
+    static std::mutex mu;
+    static cudaStream_t streams[64] = {};
+    std::lock_guard<std::mutex> g(mu);
+    if (device < 0 || device >= 64) return nullptr;
+    if (streams[device] == nullptr) {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != device) cudaSetDevice(device);
+        cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        if (cur != device && cur >= 0) cudaSetDevice(cur);
+    }
+    return streams[device];
+}
+
 uint32_t storage_row_bytes(int storage, uint32_t dim) {
     uint64_t bits = 0;
     switch (storage) {

@@ -128,15 +128,16 @@ vsb_status vsb_index::build() {
     sh_nrm.release();
     ST(graph_from_knn(knn.as<uint64_t>(), n, kin, nullptr));
     knn.release();
-    ST(sample_seeds(n));
+    // the reachability pass (extra seeds for lost components) runs on the FINAL graph only
+    ST(sample_seeds(n, n >= n_slots));
     if (n < n_slots) {
         // large index: link the remaining rows with the streaming insert (K7), then rebuild every row's
         // list from an ANN search over that navigable graph and prune it exactly like the all-pairs lists
         ST(stream_insert());
-        ST(sample_seeds(n_slots));  // entry points drawn from every row, not only the all-pairs prefix
+        ST(sample_seeds(n_slots, refine_passes == 0));  // entry points drawn from every row, not only the all-pairs prefix
         for (uint32_t pass = 0; pass < refine_passes; ++pass) {
             ST(refine_graph());
-            ST(sample_seeds(n_slots));  // reachability of the FINAL graph from the entry points
+            ST(sample_seeds(n_slots, pass + 1 == refine_passes));
         }
     }
     return VSB_OK;
@@ -225,7 +226,7 @@ vsb_status vsb_index::refine_graph() {
 
 // Entry-point sample ("upper layer"): a stride permutation of the live slots below n_rows
 // (deterministic, seed-shifted), gathered into a contiguous block (+ bf16 shadow for f32 storage).
-vsb_status vsb_index::sample_seeds(uint32_t n) {
+vsb_status vsb_index::sample_seeds(uint32_t n, bool ensure_reach) {
     nvtxRangePushA("build.seeds");
     EvTimer t(mstream);
     const vsb::RowsView x = rows_view(w);
@@ -256,13 +257,16 @@ vsb_status vsb_index::sample_seeds(uint32_t n) {
     // every live graph node must be reachable from the seed set: expand the frontier from the sample to a fixed
     // point, then promote the first unreached live node to an extra seed and continue, once per lost component
     uint32_t extra_seeds = 0;
-    if (w.n_graphed >= n && n > 0 && S > 0 && reach_fix) {
+    if (w.n_graphed >= n && n > 0 && S > 0 && reach_fix && ensure_reach) {
         DevBuf reach_state;
-        CU(reach_state.alloc((size_t)n + 16));
+        const size_t flag_off = ((size_t)n + 16 + 15) / 16 * 16;  // the state array is readable 16 bytes past n
+        constexpr uint32_t kPromote = 64;                          // unreached nodes promoted per round
+        CU(reach_state.alloc(flag_off + 16 + (size_t)(1 + kPromote) * 4));
         uint8_t* state = reach_state.as<uint8_t>();
-        uint32_t* flag = reinterpret_cast<uint32_t*>(state + (((size_t)n + 7) / 8) * 8);  // [0] changed, [1] first unreached
+        uint32_t* flag = reinterpret_cast<uint32_t*>(state + flag_off);  // [0] changed
+        uint32_t* found = flag + 4;                                      // [0] count, [1..] slots
         CU(sd->slots.alloc((size_t)(S + reach_budget) * 4));
-        CU(cudaMemsetAsync(state, 0, n, mstream));
+        CU(cudaMemsetAsync(state, 0, flag_off, mstream));
         CU(cudaMemcpyAsync(sd->slots.p, h_seeds.data(), (size_t)S * 4, cudaMemcpyHostToDevice, mstream));
         vsb::launch_reach_mark(state, sd->slots.as<uint32_t>(), S, mstream);
         const uint32_t* deny_bm = w.any_tombstone ? st.deny.as<uint32_t>() : nullptr;
@@ -279,16 +283,19 @@ vsb_status vsb_index::sample_seeds(uint32_t n) {
             return VSB_OK;
         };
         ST(expand());
+        // unreached live nodes become extra seeds, up to kPromote of them (in slot order) per round: a lost component
+        // usually is a single node nobody links to, so promoting a batch and expanding once beats one round per node
+        std::vector<uint32_t> h_found(1 + kPromote);
         while (extra_seeds < reach_budget) {
-            CU(cudaMemsetAsync(flag + 1, 0xFF, 4, mstream));
-            vsb::launch_first_unreached(state, deny_bm, n, flag + 1, mstream);
-            uint32_t first = 0xFFFFFFFFu;
-            CU(cudaMemcpyAsync(&first, flag + 1, 4, cudaMemcpyDeviceToHost, mstream));
+            const uint32_t room = std::min<uint32_t>(kPromote, reach_budget - extra_seeds);
+            vsb::launch_collect_unreached(state, deny_bm, n, room, found, mstream);
+            CU(cudaMemcpyAsync(h_found.data(), found, (size_t)(1 + room) * 4, cudaMemcpyDeviceToHost, mstream));
             CU(cudaStreamSynchronize(mstream));
-            if (first == 0xFFFFFFFFu) break;
-            h_seeds.push_back(first);
-            ++extra_seeds;
-            CU(cudaMemsetAsync(state + first, 1, 1, mstream));
+            const uint32_t cnt = std::min(h_found[0], room);
+            if (cnt == 0) break;
+            for (uint32_t i = 0; i < cnt; ++i) h_seeds.push_back(h_found[1 + i]);
+            vsb::launch_reach_mark(state, found + 1, cnt, mstream);
+            extra_seeds += cnt;
             ST(expand());
         }
         CU(cudaGetLastError());

@@ -52,13 +52,25 @@ vsb_status fail(vsb_status st, const char* fmt, ...);
         if (s_ != VSB_OK) return s_; \
     } while (0)
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync on a dedicated allocator stream that is
+// drained before the pointer is handed out, so the block is valid on every stream) and goes back with cudaFreeAsync:
+// cudaMalloc / cudaFree serialise on the context and cudaFree waits for the whole device, which would stall every
+// running search whenever a mutator drops a temporary.  The pool keeps freed blocks (release threshold = max), so a
+// steady mutation stream allocates without ever reaching the driver.  Callers release a buffer only after the work
+// that used it has been synchronised (every mutator phase ends with an event wait); growing a scratch buffer that
+// un-synchronised kernels may still read drains the device first.  `plain` buffers (cudaMalloc) are for memory that
+// other devices or processes map: the router's gather buffers and the IPC exchange.
+cudaStream_t pool_stream(int device);  // index.cu
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    int dev = -1;
+    bool plain = false;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) {
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), dev(o.dev), plain(o.plain) {
         o.p = nullptr;
         o.bytes = 0;
     }
@@ -67,6 +79,8 @@ struct DevBuf {
             release();
             p = o.p;
             bytes = o.bytes;
+            dev = o.dev;
+            plain = o.plain;
             o.p = nullptr;
             o.bytes = 0;
         }
@@ -74,15 +88,31 @@ struct DevBuf {
     }
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            int cur = -1;
+            cudaGetDevice(&cur);
+            if (cur != dev) cudaSetDevice(dev);
+            if (plain) cudaFree(p);
+            else cudaFreeAsync(p, pool_stream(dev));
+            if (cur != dev && cur >= 0) cudaSetDevice(cur);
+        }
         p = nullptr;
         bytes = 0;
     }
-    // exact-size allocation (contents undefined)
-    cudaError_t alloc(size_t want) {
+    // exact-size allocation on the current device (contents undefined)
+    cudaError_t alloc(size_t want, bool plain_memory = false) {
         release();
         const size_t sz = want ? want : 16;
-        cudaError_t e = cudaMalloc(&p, sz);
+        cudaGetDevice(&dev);
+        plain = plain_memory;
+        cudaError_t e;
+        if (plain) {
+            e = cudaMalloc(&p, sz);
+        } else {
+            cudaStream_t ps = pool_stream(dev);
+            e = cudaMallocAsync(&p, sz, ps);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ps);
+        }
         if (e != cudaSuccess) {
             p = nullptr;
             return e;
@@ -91,9 +121,10 @@ struct DevBuf {
         return cudaSuccess;
     }
     // grow-only scratch (contents not preserved)
-    cudaError_t ensure(size_t want) {
+    cudaError_t ensure(size_t want, bool plain_memory = false) {
         if (want <= bytes) return cudaSuccess;
-        return alloc(want + want / 4);
+        if (p) cudaDeviceSynchronize();  // kernels of an un-synchronised search may still read the old block
+        return alloc(want + want / 4, plain_memory);
     }
     template <class T>
     T* as() const { return static_cast<T*>(p); }
@@ -257,7 +288,7 @@ struct vsb_index {
     vsb_status graph_from_knn(const uint64_t* knn, uint32_t n, uint32_t kin, const uint32_t* deny_bm);
     vsb_status refine_graph();
     vsb_status stream_insert();
-    vsb_status sample_seeds(uint32_t n_rows);
+    vsb_status sample_seeds(uint32_t n_rows, bool ensure_reach = true);
 
     // search building blocks: run on stream `s` with scratch `sc` against view `v`
     vsb_status exact_block(const vsbi::View& v, vsbi::Scratch& sc, const vsb::RowsView& q, const vsb::RowsView& x,

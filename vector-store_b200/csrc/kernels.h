@@ -95,6 +95,10 @@ void launch_merge_graph(const uint32_t* fwd, const uint32_t* rev, const uint32_t
 void launch_reach_mark(uint8_t* state, const uint32_t* seeds, uint32_t n_seeds, cudaStream_t stream);
 void launch_reach_step(const uint32_t* graph, uint32_t n, uint32_t stride, uint32_t degree, uint8_t* state,
                        uint32_t* changed, cudaStream_t stream);
+// out[0] = number found (<= cap), out[1..] = the first `cap` unreached live slots in slot order; state must be
+// readable 16 bytes past n
+void launch_collect_unreached(const uint8_t* state, const uint32_t* deny, uint32_t n, uint32_t cap, uint32_t* out,
+                              cudaStream_t stream);
 void launch_first_unreached(const uint8_t* state, const uint32_t* deny, uint32_t n, uint32_t* out, cudaStream_t stream);
 
 // compaction: renumber the rows and the edges of a graph through old2new (kInvalidSlot = removed)

@@ -399,8 +399,8 @@ static vsb_status fan_out(vsb_index* ix, const float* d_q, cudaEvent_t ready, ui
     const int dev0 = S.devices[0];
     if ((uint64_t)G * k > 2048) return fail(VSB_EINVAL, "shards*k must be <= 2048 for the merge");
     CU(cudaSetDevice(dev0));
-    CU(S.g_keys.ensure((size_t)G * nq * k * 8));
-    CU(S.g_dists.ensure((size_t)G * nq * k * 4));
+    CU(S.g_keys.ensure((size_t)G * nq * k * 8, true));
+    CU(S.g_dists.ensure((size_t)G * nq * k * 4, true));
     uint64_t* gk = S.g_keys.as<uint64_t>();
     float* gd = S.g_dists.as<float>();
     const size_t q_bytes = (size_t)nq * ix->dim * 4;
@@ -459,7 +459,7 @@ vsb_status sharded_search_host(vsb_index* ix, const float* queries, uint64_t nq,
     const size_t q_bytes = (size_t)nq * ix->dim * 4;
     const size_t kb = (size_t)nq * k * 8, db = (size_t)nq * k * 4, cb = (size_t)nq * 4;
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
-    CU(S.q0.ensure(q_bytes));
+    CU(S.q0.ensure(q_bytes, true));
     CU(S.out_buf.ensure(al(kb) + al(db) + al(cb)));
     uint64_t* ok = S.out_buf.as<uint64_t>();
     float* od = reinterpret_cast<float*>(S.out_buf.as<uint8_t>() + al(kb));
