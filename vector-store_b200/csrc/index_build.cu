@@ -192,7 +192,7 @@ vsb_status vsb_index::refine_graph() {
     run.itopk = ef;
     run.max_iters = 0;
     run.n_seeds = 32;
-    run.search_width = 1;
+    run.search_width = build_search_width;  // 2 parents per iteration: ~10 % more evaluations, but twice the rows in flight per warp
     {
         EvTimer t(mstream);
         const uint32_t QB = 16384;
@@ -355,7 +355,7 @@ vsb_status vsb_index::stream_insert() {
     run.itopk = ef;
     run.max_iters = 0;
     run.n_seeds = 32;
-    run.search_width = 1;
+    run.search_width = build_search_width;
     DevBuf cand;
     const uint32_t QB = 8192;
     CU(cand.alloc((size_t)QB * C * 8));

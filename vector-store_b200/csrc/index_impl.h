@@ -198,6 +198,7 @@ struct vsb_index {
     bool reach_fix = true;
     uint32_t reach_budget = 1024;
     uint32_t allpairs_max = 262144, allpairs_prefix = 131072, refine_passes = 1;
+    uint32_t build_search_width = 2;  // parents per K4 iteration in the streaming insert / refinement searches (VSB_BUILD_SW)
     vsbi::Sharded* sharded = nullptr;  // n_devices > 1: every entry point forwards to the router (owned; sharded.cu)
 
     // ---- published state ----
