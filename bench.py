@@ -353,8 +353,8 @@ def main():
         torch.cuda.synchronize()
         q_dev.append(qd)
         q_host.append(qd.cpu().pin_memory())
-    out_k = torch.empty((B, k), dtype=torch.int64, device=dev)
-    out_d = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_k0 = out_k = torch.empty((B, k), dtype=torch.int64, device=dev)
+    out_d0 = out_d = torch.empty((B, k), dtype=torch.float32, device=dev)
     keys_l = torch.empty((B, k), dtype=torch.int64, device=dev)
     dists_l = torch.empty((B, k), dtype=torch.float32, device=dev)
     assert world == 1 or B % world == 0, "query batch must divide evenly over the ranks"
@@ -374,12 +374,11 @@ def main():
         rec_all = torch.empty(world * rec_bytes, dtype=torch.uint8, device=dev)
         keys_l = rec_local[:B * k * 8].view(torch.int64).view(B, k)
         dists_l = rec_local[B * k * 8:].view(torch.float32).view(B, k)
-    q_slice = torch.empty((slice_rows, dim), dtype=torch.float32, device=dev)
-    q_e2e = torch.empty((B, dim), dtype=torch.float32, device=dev)
     xt = []  # (event before, event after) around the exchange of timed batches
 
-    def search_batch_dev(q_ptr, exact=False, timed=False):
-        """device-resident batch: local shard search [+ exchange + K8 merge]; result in out_k/out_d"""
+    def search_batch_dev(q_ptr, exact=False, timed=False, out=None):
+        """device-resident batch: local shard search [+ exchange + K8 merge]; result in out_k/out_d (or `out`)"""
+        out_k, out_d = out if out is not None else (out_k0, out_d0)
         if world == 1:
             idx.search_dev(q_ptr, B, k, out_k.data_ptr(), out_d.data_ptr(), 0, stream, exact)
             return
@@ -573,19 +572,42 @@ def main():
             [x.join() for x in ts]
             return
         # every shard needs every query: each rank uploads 1/N of the batch from its pinned buffer over its own
-        # PCIe link and the slices are exchanged over NVLink (job-wide H2D = one batch, not N batches)
+        # PCIe link and the slices are exchanged over NVLink (job-wide H2D = one batch, not N batches).  The batches
+        # of a step are pipelined over three streams (upload + gather | search + exchange | download), two buffers
+        # each, exactly what the two host threads do to the single-GPU library call.
         s0, s1 = shard.shard_range(B, rank, world)
+        main = torch.cuda.current_stream()
         for j in range(R):
-            q_slice.copy_(q_host[j % NB][s0:s1], non_blocking=True)
-            if xchg is not None:
-                q_ptr = xchg.allgather_rows(q_slice.data_ptr(), slice_rows * dim * 4, stream)
-            else:
-                dist.all_gather_into_tensor(q_e2e, q_slice)
-                q_ptr = q_e2e.data_ptr()
-            search_batch_dev(q_ptr)
-            h_keys[0].copy_(out_k, non_blocking=True)
-            h_dists[0].copy_(out_d, non_blocking=True)
-            torch.cuda.synchronize()
+            p = j % 2
+            with torch.cuda.stream(s_up):
+                s_up.wait_event(ev_s[p])        # search j-2 has consumed q_priv[p]
+                q_slices[p].copy_(q_host[j % NB][s0:s1], non_blocking=True)
+                if xchg is not None:
+                    # gathered into a private block: the exchange's window is overwritten by peers two gathers later
+                    xchg.allgather_rows(q_slices[p].data_ptr(), slice_rows * dim * 4, s_up.cuda_stream, q_priv[p].data_ptr())
+                else:
+                    dist.all_gather_into_tensor(q_priv[p], q_slices[p])
+                ev_q[p].record(s_up)
+            main.wait_event(ev_q[p])
+            main.wait_event(ev_d[p])            # download j-2 has drained outs[p]
+            search_batch_dev(q_priv[p].data_ptr(), out=outs[p])
+            ev_s[p].record(main)
+            with torch.cuda.stream(s_down):
+                s_down.wait_event(ev_s[p])
+                h_keys[p].copy_(outs[p][0], non_blocking=True)
+                h_dists[p].copy_(outs[p][1], non_blocking=True)
+                ev_d[p].record(s_down)
+        torch.cuda.synchronize()
+
+    if world > 1:
+        s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+        q_slices = [torch.empty((slice_rows, dim), dtype=torch.float32, device=dev) for _ in range(2)]
+        q_priv = [torch.empty((B, dim), dtype=torch.float32, device=dev) for _ in range(2)]
+        outs = [(torch.empty((B, k), dtype=torch.int64, device=dev), torch.empty((B, k), dtype=torch.float32, device=dev))
+                for _ in range(2)]
+        ev_q = [torch.cuda.Event() for _ in range(2)]
+        ev_s = [torch.cuda.Event() for _ in range(2)]
+        ev_d = [torch.cuda.Event() for _ in range(2)]
 
     for i in range(a.warmup):
         e2e_step()

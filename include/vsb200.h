@@ -287,10 +287,11 @@ vsb_status vsb_xchg_allgather_merge(vsb_xchg* x, const uint64_t* d_keys, const f
                                     uint32_t* d_out_counts, void* stream);
 /* All-gather of one opaque block per rank over the same peer stores (bench.py's e2e leg: every rank uploads 1/N of
  * the query batch over its own PCIe link and the slices are exchanged over NVLink).  bytes_per_rank: multiple of 16,
- * <= aux_bytes_per_rank of vsb_xchg_create.  *d_gathered = device pointer to the world blocks in rank order,
- * aux_bytes_per_rank apart, valid (stream-ordered) until the second-next call. */
+ * <= aux_bytes_per_rank of vsb_xchg_create.  *d_gathered (nullable) = device pointer to the world blocks in rank
+ * order, aux_bytes_per_rank apart, valid (stream-ordered) until a peer's second-next call; d_copy_out (nullable) =
+ * caller's device buffer that receives the blocks back to back (use it when gathers are pipelined). */
 vsb_status vsb_xchg_allgather_bytes(vsb_xchg* x, const void* d_src, uint64_t bytes_per_rank, void** d_gathered,
-                                    void* stream);
+                                    void* d_copy_out, void* stream);
 /* synchronises `stream` and reports VSB_ENCCL if the watchdog of a merge gave up on a rank (~2 s) */
 vsb_status vsb_xchg_check(vsb_xchg* x, void* stream);
 

@@ -234,9 +234,10 @@ vsb_status vsb_index::sample_seeds(uint32_t n, bool ensure_reach) {
     uint64_t live_below = 0;
     for (uint32_t wd = 0; wd < (n + 31) / 32; ++wd) live_below += __builtin_popcount(~h_deny[wd]);
     if (n % 32) live_below -= 32 - (n % 32);
-    uint32_t S = 256;
+    // S = 4 * sqrt(live rows), in whole 256-row tensor-core tiles, at most 8192: the seed GEMM costs Q * S * D flop per
+    // batch whatever the shard size, so a shard of n/G rows gets a sample (and a seed-layer time) ~1/sqrt(G) as large
     const double target = 4.0 * std::sqrt((double)live_below);
-    while (S < target && S < 8192) S <<= 1;
+    uint32_t S = std::min<uint32_t>(8192, std::max<uint32_t>(256, round_up((uint32_t)std::ceil(target), 256)));
     if (S > live_below / 4) S = (uint32_t)std::max<uint64_t>(32, live_below / 4);
     std::vector<uint32_t> h_seeds;
     h_seeds.reserve(S);

@@ -242,8 +242,9 @@ vsb_status vsb_xchg_allgather_merge(vsb_xchg* x, const uint64_t* d_keys, const f
     return VSB_OK;
 }
 
-vsb_status vsb_xchg_allgather_bytes(vsb_xchg* x, const void* d_src, uint64_t bytes_per_rank, void** d_gathered, void* stream_) {
-    if (!x || !d_src || !d_gathered) return fail(VSB_EINVAL, "null argument");
+vsb_status vsb_xchg_allgather_bytes(vsb_xchg* x, const void* d_src, uint64_t bytes_per_rank, void** d_gathered,
+                                    void* d_copy_out, void* stream_) {
+    if (!x || !d_src || (!d_gathered && !d_copy_out)) return fail(VSB_EINVAL, "null argument");
     if (bytes_per_rank == 0 || bytes_per_rank % 16 || bytes_per_rank > x->lay.aux)
         return fail(VSB_EINVAL, "bytes_per_rank must be a multiple of 16 and <= the aux capacity %llu", (unsigned long long)x->lay.aux);
     for (uint32_t r = 0; r < x->lay.world; ++r)
@@ -264,7 +265,10 @@ vsb_status vsb_xchg_allgather_bytes(vsb_xchg* x, const void* d_src, uint64_t byt
                                       x->aux_step, x->timeout_cycles, x->error);
     vsb::g_kernel_launches += 2;
     CU(cudaGetLastError());
-    *d_gathered = x->local + x->lay.aux_off(parity, 0);
+    if (d_gathered) *d_gathered = x->local + x->lay.aux_off(parity, 0);
+    if (d_copy_out)  // out of the window (peers overwrite it two gathers later) into the caller's block, rank by rank
+        CU(cudaMemcpy2DAsync(d_copy_out, bytes_per_rank, x->local + x->lay.aux_off(parity, 0), x->lay.aux, bytes_per_rank,
+                             x->lay.world, cudaMemcpyDeviceToDevice, s));
     return VSB_OK;
 }
 

@@ -333,10 +333,12 @@ class Exchange:
         check(self._lib.vsb_xchg_allgather_merge(self._x, d_keys, d_dists, q, k, d_out_keys, d_out_dists,
                                                  d_out_counts or None, stream or None))
 
-    def allgather_rows(self, d_src: int, bytes_per_rank: int, stream: int) -> int:
-        """-> device pointer to the world blocks in rank order (aux_bytes_per_rank apart)"""
+    def allgather_rows(self, d_src: int, bytes_per_rank: int, stream: int, d_copy_out: int = 0) -> int:
+        """-> device pointer to the world blocks in rank order (aux_bytes_per_rank apart); d_copy_out: the blocks are
+        also copied back to back into that device buffer (pipelined gathers must not read the window later)"""
         out = C.c_void_p()
-        check(self._lib.vsb_xchg_allgather_bytes(self._x, d_src, bytes_per_rank, C.byref(out), stream or None))
+        check(self._lib.vsb_xchg_allgather_bytes(self._x, d_src, bytes_per_rank, C.byref(out), d_copy_out or None,
+                                                 stream or None))
         return int(out.value)
 
     def check(self, stream: int) -> None:

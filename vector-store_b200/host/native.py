@@ -84,7 +84,7 @@ SYMBOLS = [
     ("vsb_batcher_add", C.c_int, [_P, C.c_uint64, _P]),
     ("vsb_batcher_flush", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("vsb_xchg_create", C.c_int, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(_P)]),
-    ("vsb_xchg_allgather_bytes", C.c_int, [_P, _P, C.c_uint64, C.POINTER(_P), _P]),
+    ("vsb_xchg_allgather_bytes", C.c_int, [_P, _P, C.c_uint64, C.POINTER(_P), _P, _P]),
     ("vsb_xchg_destroy", None, [_P]),
     ("vsb_xchg_local_handle", C.c_int, [_P, _P]),
     ("vsb_xchg_open", C.c_int, [_P, _P]),
