@@ -663,7 +663,7 @@ def test_c2_full_size_properties():
     st = idx.stats()
     assert st["n_graphed"] == n and st["hbm_bytes"] > n * (3072 + 1536)
     q = embedding_like(2000, dim, seed=4321)
-    idx.set_search_params(expansion_search=160, search_width=2)
+    idx.set_search_params(expansion_search=192, search_width=2)
     tk, td, tc = idx.search_batch(q, k, exact=True)
     gk, gd, gc = idx.search_batch(q, k)
     gk2, gd2, _ = idx.search_batch(q, k)
@@ -672,8 +672,8 @@ def test_c2_full_size_properties():
     assert np.all(np.diff(gd, axis=1) >= 0) and np.all(np.diff(td, axis=1) >= 0)
     assert np.all((gd >= 0) & (gd <= 2))                                # distance.rs:66-69
     r = O.recall_at_k(gk, tk)
-    print(f"C2 1M x 768 recall@10 at ef=160: {r:.4f}")
-    assert r >= 0.94
+    print(f"C2 1M x 768 recall@10 at ef=192: {r:.4f}")
+    assert r >= 0.94  # streamed (K7) graph, no optional refinement pass (VSB_REFINE_PASSES=0 default)
     # every hit's distance is the canonical fp32 distance of that stored row (checked on the oracle for 3 queries)
     for i in range(3):
         rows = np.stack([embedding_like(100_000, dim, seed=1234 + int(key) // 100_000)[int(key) % 100_000]

@@ -104,7 +104,7 @@ def test_c3_slice_exact_topk_vs_oracle_and_ann_recall():
     print(f"C3 slice 2M x 768 bf16: exact bit-equal on {nq} queries; ANN recall@10 = {recall:.4f} at ef={ef}")
     assert recall >= 0.95 and np.all(ac == k)
     bs = idx.build_stats()
-    assert bs["rows"] == n and bs["stream_rows"] > 0 and bs["refine_evals"] > 0 and bs["allpairs_flops"] > 0
+    assert bs["rows"] == n and bs["stream_rows"] > 0 and bs["stream_evals"] > 0 and bs["allpairs_flops"] > 0
     idx.close()
 
 

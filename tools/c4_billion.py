@@ -1,0 +1,215 @@
+#!/usr/bin/env python
+"""Config C4 (BASELINE.json configs[3]): 1 B x 128 bf16 dot-product, degree-64 graph, sharded over the
+GPUs of one box — 125 M rows (~64 GB of vectors + graph) per B200.
+
+  torchrun --nnodes=1 --nproc-per-node G tools/c4_billion.py [--rows-per-gpu 125000000]
+
+Every rank draws ITS row range of the counter-based corpus in HBM (tools/synth, never on the host), ingests it with
+vsb_add_dev, builds its shard (all-pairs prefix on tcgen05 + K7 streaming insert, out of core w.r.t. the all-pairs
+matrix), and the ranks answer every query batch together: local ANN search -> peer-memory exchange of the per-shard
+top-k over NVLink (vsb_xchg) -> K8 merge.  Ground truth = the same exchange over the shards' exact (tensor-core)
+search of the 10 000-query set.  The per-GPU layout is the full C4 layout whatever G is; G = 8 is the 1 B config,
+smaller G is the same shard size with fewer of them (weak scaling: total rows = G x rows-per-gpu).
+The reference would regrow its index 1 000 times in exclusive 1 M-slot steps here (usearch.rs:442-443, 655-665).
+Rank 0 prints one JSON line."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows-per-gpu", type=int, default=125_000_000)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--degree", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=10_000)
+    ap.add_argument("--batches", type=int, default=20, help="timed query batches")
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--target-recall", type=float, default=0.95)
+    ap.add_argument("--chunk", type=int, default=4_000_000)
+    a = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+    from importlib import import_module
+
+    import vector_store_b200 as v
+    ds = import_module("vector_store_b200.host.datasets")
+    index_mod = import_module("vector_store_b200.host.index")
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n_local, dim, k, B = a.rows_per_gpu, a.dim, a.k, a.batch
+    n_total = n_local * world
+    lo = rank * n_local
+    clusters = max(16, int(round(256 * n_total / 1e6)))
+    stream = torch.cuda.current_stream().cuda_stream
+
+    idx = v.GpuIndex(dim, v.Metric.IP, v.Scalar.BF16, connectivity=a.degree // 2, device=local_rank)
+    idx.reserve(n_local)
+    gbuf = torch.empty((min(a.chunk, n_local), dim), dtype=torch.float32, device=dev)
+    barrier()
+    t_gen = t_add = 0.0
+    for c0 in range(lo, lo + n_local, a.chunk):
+        nb = min(a.chunk, lo + n_local - c0)
+        t0 = time.perf_counter()
+        ds.embedding_mix_dev(gbuf.data_ptr(), nb, dim, row0=c0, seed=1234, n_clusters=clusters, stream=stream)
+        torch.cuda.synchronize()
+        t_gen += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        idx.add_dev(np.arange(c0, c0 + nb, dtype=np.uint64), gbuf.data_ptr(), nb)
+        t_add += time.perf_counter() - t0
+    del gbuf
+    torch.cuda.empty_cache()
+    barrier()
+    t0 = time.perf_counter()
+    idx.build()
+    barrier()
+    t_build = time.perf_counter() - t0
+    bs = idx.build_stats()
+    st = idx.stats()
+
+    # ---- queries (same generator, different stream) and the exchange ----
+    NB = 2
+    q_dev = []
+    for b in range(NB):
+        qd = torch.empty((B, dim), dtype=torch.float32, device=dev)
+        ds.embedding_mix_dev(qd.data_ptr(), B, dim, row0=0, seed=4321 + b, n_clusters=clusters, stream=stream)
+        q_dev.append(qd)
+    torch.cuda.synchronize()
+    out_k = torch.empty((B, k), dtype=torch.int64, device=dev)
+    out_d = torch.empty((B, k), dtype=torch.float32, device=dev)
+    keys_l = torch.empty((B, k), dtype=torch.int64, device=dev)
+    dists_l = torch.empty((B, k), dtype=torch.float32, device=dev)
+    xchg = None
+    if world > 1:
+        def ag(blob):
+            out = [None] * world
+            dist.all_gather_object(out, blob)
+            return out
+        xchg = index_mod.Exchange(local_rank, world, rank, B, k, ag)
+
+    def search(q_ptr, exact=False):
+        if world == 1:
+            idx.search_dev(q_ptr, B, k, out_k.data_ptr(), out_d.data_ptr(), 0, stream, exact)
+            return
+        idx.search_dev(q_ptr, B, k, keys_l.data_ptr(), dists_l.data_ptr(), 0, stream, exact)
+        xchg.allgather_merge(keys_l.data_ptr(), dists_l.data_ptr(), B, k, out_k.data_ptr(), out_d.data_ptr(), 0, stream)
+
+    # exact ground truth on the whole query set (sharded K1-TC + exchange + K8)
+    t0 = time.perf_counter()
+    gt = []
+    for b in range(NB):
+        search(q_dev[b].data_ptr(), exact=True)
+        torch.cuda.synchronize()
+        gt.append(out_k.cpu().numpy().copy())
+    barrier()
+    t_gt = time.perf_counter() - t0
+
+    def recall_of(b):
+        got = out_k.cpu().numpy()
+        hits = sum(len(np.intersect1d(got[i], gt[b][i])) for i in range(B))
+        return hits / (B * k)
+
+    sweep, ef_used = [], None
+    for ef in (32, 64, 96, 128, 160, 192, 256, 320, 384, 512):
+        idx.set_search_params(expansion_search=ef, search_width=2, max_iterations=10 ** 6)
+        search(q_dev[0].data_ptr())
+        torch.cuda.synchronize()
+        r = recall_of(0)
+        sweep.append({"ef": ef, "recall_at_10": round(r, 4)})
+        ef_used = ef
+        if r >= a.target_recall + 0.003:
+            break
+    # timed: batches resident in HBM, device clock, max over ranks
+    for i in range(3):
+        search(q_dev[i % NB].data_ptr())
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.batches):
+        search(q_dev[i % NB].data_ptr())
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    search(q_dev[1].data_ptr())
+    torch.cuda.synchronize()
+    recall_b1 = recall_of(1)
+    idx.set_instrumented(True)
+    idx.search_dev(q_dev[1].data_ptr(), B, k, keys_l.data_ptr(), dists_l.data_ptr(), 0, stream, False)
+    torch.cuda.synchronize()
+    s2 = idx.stats()
+    idx.set_instrumented(False)
+    E = s2["distance_evals"] / max(s2["queries"], 1)
+    P = s2["parent_expansions"] / max(s2["queries"], 1)
+    s_before = idx.stats()
+    idx.set_kernel_timing(True)
+    for i in range(4):
+        idx.search_dev(q_dev[i % NB].data_ptr(), B, k, keys_l.data_ptr(), dists_l.data_ptr(), 0, stream, False)
+    torch.cuda.synchronize()
+    s3 = idx.stats()
+    idx.set_kernel_timing(False)
+    k4_ms = (s3["graph_search_ns"] - s_before["graph_search_ns"]) / 1e6 / max(1, s3["graph_search_launches"] - s_before["graph_search_launches"])
+    free_b, total_b = torch.cuda.mem_get_info()
+    t_add_m, t_build_m, t_gen_m = max_over_ranks(t_add), max_over_ranks(t_build), max_over_ranks(t_gen)
+    if rank == 0:
+        bytes_per_query = E * (st["row_bytes"]) + P * st["graph_degree"] * 4
+        out = {
+            "config": f"C4 (BASELINE configs[3]): {n_total} x {dim} bf16 dot-product (unit-norm rows, {clusters} mixture "
+                      f"components), degree {st['graph_degree']}, {world} GPU(s) x {n_local} rows, k={k}, query batch {B}",
+            "n_gpus": world, "rows_total": n_total, "rows_per_gpu": n_local,
+            "hbm_gb_per_gpu_index": round(st["hbm_bytes"] / 1e9, 2),
+            "hbm_gb_per_gpu_device_used": round((total_b - free_b) / 1e9, 2),
+            "generate_s": round(t_gen_m, 2), "add_s": round(t_add_m, 2), "build_s": round(t_build_m, 2),
+            "build_vectors_per_s": n_total / t_build_m,
+            "build_vectors_per_s_incl_ingest": n_total / (t_add_m + t_build_m),
+            "build_phase_s_rank0": {kk: round(bs[kk] / 1e9, 3) for kk in bs if kk.endswith("_ns")},
+            "stream_evals_per_row": bs["stream_evals"] / max(bs["stream_rows"], 1),
+            "ground_truth_s": round(t_gt, 2),
+            "expansion_search": ef_used, "ef_sweep": sweep,
+            "recall_at_10": round(recall_b1, 4),
+            "qps": a.batches * B / (ms / 1e3), "ms_per_batch": ms / a.batches,
+            "distance_evals_per_query_per_shard": E, "parent_expansions_per_query_per_shard": P,
+            "k4_algorithmic_bytes_per_query_per_shard": bytes_per_query,
+            "k4_ms_per_batch_rank0": k4_ms,
+            "k4_hbm_gbs_rank0": B * bytes_per_query / (k4_ms * 1e-3) / 1e9 if k4_ms else None,
+            "extra_seeds": st.get("extra_seeds"),
+        }
+        print(json.dumps(out), flush=True)
+    if xchg is not None:
+        xchg.close()
+    idx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -154,11 +154,14 @@ def main():
     qt.start()
     mt.start()
     # recall checkpoints at 1/3, 2/3 and the end (main thread; exact GT of the live set at that moment)
+    ck_windows = []
     for frac in (1 / 3, 2 / 3):
         time.sleep(max(0.0, t_begin + frac * a.seconds - time.perf_counter()))
         st = idx.stats()
+        ck0 = round(time.perf_counter() - t_begin, 3)
         checkpoints.append({"t_s": round(time.perf_counter() - t_begin, 1), "recall_at_10": round(recall_now(), 4),
                             "n_slots": st["n_slots"], "n_graphed": st["n_graphed"], "size": idx.size()})
+        ck_windows.append([ck0, round(time.perf_counter() - t_begin, 3)])
     mt.join()
     t_mut = time.perf_counter() - t_begin
     stop.set()
@@ -173,6 +176,16 @@ def main():
     lt = np.array(lat1_t)
     la = np.array(lat1)
     inside = np.concatenate([la[(lt > s) & (lt < e)] for s, e in slow]) if len(la) else np.array([])
+    # timeline of the slow batch-1 queries: when they ended, how long they took, and the mutator call (if any) they ended in
+    slow_q = []
+    for i in np.argsort(-la)[:40]:
+        if la[i] < 0.003:
+            break
+        inside_call = next(((s, e) for s, e in mut_calls if s < lt[i] < e + la[i]), None)
+        slow_q.append({"end_s": round(float(lt[i] - t_begin), 4), "ms": round(float(la[i] * 1e3), 2),
+                       "mut_call_ms": round((inside_call[1] - inside_call[0]) * 1e3, 1) if inside_call else None,
+                       "offset_in_call_ms": round((lt[i] - la[i] - inside_call[0]) * 1e3, 1) if inside_call else None})
+    slow_q.sort(key=lambda d: d["end_s"])
     out = {
         "config": f"C5: {n0}x{dim} f32 cosine (bf16 traversal), {a.rate} mutations/s (70/20/10 insert/delete/update) for "
                   f"{a.seconds:.0f} s in batches of {a.mut_batch}, concurrent batch-1 queries + a 1000-query batch every {a.big_every} s",
@@ -189,7 +202,8 @@ def main():
                                                     "p99": float(np.percentile(inside, 99) * 1e3)} if len(inside) else None),
         "batch1000_ms": {"n": len(lat_big), "p50": float(np.percentile(lat_big, 50) * 1e3) if lat_big else None,
                          "p99": float(np.percentile(lat_big, 99) * 1e3) if lat_big else None},
-        "checkpoints": checkpoints,
+        "checkpoints": checkpoints, "checkpoint_windows_s": ck_windows, "slow_batch1_queries": slow_q,
+        "slow_mutator_calls": [{"start_s": round(s - t_begin, 3), "ms": round((e - s) * 1e3, 1)} for s, e in sorted(slow)],
         "refine_rows": bs["refine_rows"], "stream_rows": bs["stream_rows"], "compact_ms": bs["compact_ns"] / 1e6,
         "errors": errors,
     }

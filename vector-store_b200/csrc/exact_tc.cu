@@ -8,18 +8,25 @@
 // (vs_index/usearch.rs:191-222).  Output format is identical to exact.cu's K1 (per-split sorted
 // candidate lists), so K3 (exact_rerank_kernel) finishes both the same way.
 //
-// CTA = 192 threads, one CTA per SM (TMEM 512 columns, ~213 KB smem):
+// CTA = 320 threads, one CTA per SM (TMEM 512 columns, ~217 KB smem):
 //   warp 0      TMA producer: A = 128 queries x 128 B of K, B = 256 corpus rows x 128 B of K,
 //               3-stage mbarrier ring (full/empty)
 //   warp 1      tcgen05.mma issuer (one elected lane): D[128 x 256] fp32 in TMEM, double buffered
 //               (2 x 256 columns) so the epilogue of tile t overlaps the MMAs of tile t+1
-//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time; thread = one query row;
-//               distance from the dot product and per-column norms; compare with the row's
-//               current k'-th best (register); survivors go to a per-row smem buffer that is
-//               sorted with the shuffle bitonic network and folded into the row's list.
+//   warps 2-9   epilogue, two warps per TMEM lane quarter, each owning 128 of the tile's 256 columns
+//               (a "column half" = its own candidate list per query, merged by K3 like a split):
+//               tcgen05.ld 32 lanes x 32 columns at a time; thread = one query row; distance from
+//               the dot product and per-column norms; a 32-bit hit mask against the row's current
+//               k'-th best (register); the columns in which ANY row of the warp hit are revisited
+//               in a warp-uniform loop (one tcgen05.ld.x1 each) and the survivors go to a 32-entry
+//               per-row smem buffer that is sorted with the shuffle bitonic network and folded into
+//               the row's list when full (tc_flush_rows, kept out of line: the tile loop stays
+//               small enough for the instruction cache).
 // kind::f16 (bf16 / f16 storage, exact products) or kind::tf32 (f32 storage, candidate grade).
 #include <cuda.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "kernels.h"
@@ -34,14 +41,17 @@ constexpr int TC_N = 256;
 constexpr int TC_KBYTES = 128;
 constexpr int TC_STAGES = 3;       // 1-CTA variant: 3 x 48 KB
 constexpr int TC2_STAGES = 4;      // 2-CTA variant: 4 x 32 KB (each CTA stages its own A and half of B)
-constexpr int TC_BUFCAP = 64;
-constexpr int TC_THREADS = 192;
+constexpr int TC_BUFCAP = 32;        // candidates buffered per (query row, column half) before a flush
+constexpr int TC_HALVES = 2;         // epilogue warps per TMEM lane quarter = candidate lists per (query, row split)
+constexpr int TC_HALF_N = TC_N / TC_HALVES;
+constexpr int TC_EPI_WARPS = 4 * TC_HALVES;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr uint32_t TC_A_BYTES = TC_M * TC_KBYTES;   // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_N * TC_KBYTES;   // 32 KB
 constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr uint32_t TC_OFF_BUF = TC_STAGES * TC_STAGE_BYTES;
-constexpr uint32_t TC_OFF_COLP = TC_OFF_BUF + TC_M * TC_BUFCAP * 8;
-constexpr uint32_t TC_OFF_BAR = TC_OFF_COLP + 4 * 2 * TC_N * 4;  // per epilogue warp, per accumulator stage
+constexpr uint32_t TC_OFF_COLP = TC_OFF_BUF + TC_HALVES * TC_M * TC_BUFCAP * 8;
+constexpr uint32_t TC_OFF_BAR = TC_OFF_COLP + TC_EPI_WARPS * 2 * TC_HALF_N * 4;  // per epilogue warp, per accumulator stage
 constexpr uint32_t TC_SMEM_BYTES = TC_OFF_BAR + 128 + 1024;  // + alignment slack
 // both variants use the same offsets for buf / colp / barriers: 4 x 32 KB < 3 x 48 KB
 static_assert(TC2_STAGES * (TC_A_BYTES + TC_B_BYTES / 2) <= TC_OFF_BUF, "2-CTA stages must fit the stage area");
@@ -60,7 +70,7 @@ struct TcArgs {
     const uint64_t* keys;
     const uint32_t* allow;
     uint64_t allow_bits;
-    uint32_t kp, n_splits, rows_per_split;
+    uint32_t kp, n_splits, rows_per_split;  // n_splits = lists per query = TC_HALVES * gridDim.y
     uint64_t* part;
     int tile_min;  // 1: emit only each tile's best row per query (seed layer), no list maintenance
 };
@@ -179,6 +189,46 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(v) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return v;
+}
+
+// Candidate-stage distance of one (query, corpus row) pair from the tile's dot product.  col = per-column parameter
+// (|x|^2, 1/|x|, 1), qpar = per-query parameter (|q|^2, -1/|q|, unused).  One definition for the hit test and for the
+// value that is stored, so both see the same bits.
+template <int METRIC>
+__device__ __forceinline__ float tc_dist(float dot, float col, float qpar) {
+    if constexpr (METRIC == VSB_METRIC_L2SQ) return __fadd_rn(__fmaf_rn(dot, -2.0f, col), qpar);
+    else if constexpr (METRIC == VSB_METRIC_COS) return __fmaf_rn(__fmul_rn(dot, col), qpar, 1.0f);
+    else return __fmaf_rn(dot, -1.0f, col);
+}
+
+// Folds the buffered candidates of the rows in `need_mask` (bit r = row r of this warp) into their lists: the whole
+// warp sorts one row's buffer (shuffle bitonic network) and carry-merges it into the row's sorted list in global
+// memory.  Returns the calling lane's threshold: the new k'-th best of its row if that row was flushed and its list
+// is full, `thr` otherwise.  Out of line on purpose (called from the tile loop's rare path).
+__device__ __noinline__ float tc_flush_rows(uint32_t need_mask, uint64_t* warp_lists, size_t list_stride, uint32_t kp,
+                                            const uint64_t* keys, const uint64_t* warp_buf, int cnt, float thr, int lane) {
+    const LessByKey less{keys};
+    __syncwarp();  // make every lane's buffered candidates visible to the warp
+    while (need_mask) {
+        const int r = __ffs(need_mask) - 1;
+        need_mask &= need_mask - 1;
+        const int c = __shfl_sync(kFullMask, cnt, r);
+        uint64_t* list = warp_lists + (size_t)r * list_stride;
+        uint64_t v = lane < c ? warp_buf[(size_t)r * TC_BUFCAP + lane] : kInvalidPacked;
+        v = warp_sort32(v, lane, less);
+        warp_list_merge(list, (int)kp, v, lane, less);
+        const uint64_t worst = list[kp - 1];
+        if (lane == r && worst != kInvalidPacked) thr = ord_to_f32(packed_hi(worst));
+    }
+    __syncwarp();
+    return thr;
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -232,7 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], CTA2 ? 8 : 4);  // the leader also waits for the peer CTA's epilogue warps
+            mbar_init(&tmem_empty[i], CTA2 ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);  // the leader also waits for the peer CTA's epilogue warps
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -315,24 +365,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
         }
     } else {
-        // ===== epilogue: one thread per query row =====
-        const int quarter = warp & 3;                // TMEM lane quarter this warp may read
+        // ===== epilogue: one thread per (query row, column half) =====
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may read (hardware: warp id % 4)
+        const int half = (warp - 2) >> 2;            // which 128 columns of every tile this warp owns
         const int row = quarter * 32 + lane;         // row inside the CTA tile
         const uint32_t q = q0 + row;
         const bool q_valid = q < a.nq;
-        const LessByKey less{a.keys};
-        uint64_t* my_buf = buf + (size_t)row * TC_BUFCAP;
-        float qsq = 0.f, inv_qn = 0.f;
+        const uint32_t list_id = split * TC_HALVES + half;   // a.n_splits = TC_HALVES * (row splits)
+        uint64_t* my_buf = buf + ((size_t)half * TC_M + row) * TC_BUFCAP;
+        float qpar = 0.f;   // L2sq: |q|^2; cosine: -1/|q|
         if (q_valid) {
-            qsq = a.q_sq[q];
-            const float qn = a.q_nrm[q];
-            inv_qn = qn > 0.f ? 1.0f / qn : 0.f;
+            if constexpr (METRIC == VSB_METRIC_L2SQ) qpar = a.q_sq[q];
+            if constexpr (METRIC == VSB_METRIC_COS) {
+                const float qn = a.q_nrm[q];
+                qpar = qn > 0.f ? -(1.0f / qn) : 0.f;
+            }
         }
-        // this warp's 32 lists live in global memory (L2 resident); initialise them
-        for (int r = 0; r < 32; ++r) {
-            const uint32_t qq = q0 + quarter * 32 + r;
-            if (qq >= a.nq) break;
-            uint64_t* list = a.part + ((size_t)qq * a.n_splits + split) * a.kp;
+        // this warp's 32 lists live in global memory (L2 resident); row r's list is r * list_stride further on
+        const size_t list_stride = (size_t)a.n_splits * a.kp;
+        uint64_t* warp_lists = a.part + ((size_t)(q0 + quarter * 32) * a.n_splits + list_id) * a.kp;
+        const uint64_t* warp_buf = buf + ((size_t)half * TC_M + quarter * 32) * TC_BUFCAP;
+        for (int r = 0; r < 32; ++r) {   // (tile-min mode: the entries of tiles this split does not have stay invalid)
+            if (q0 + quarter * 32 + r >= a.nq) break;
+            uint64_t* list = warp_lists + (size_t)r * list_stride;
             for (uint32_t i = lane; i < a.kp; i += 32) list[i] = kInvalidPacked;
         }
         __syncwarp();
@@ -343,77 +398,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const uint64_t* keys = a.keys;
         const uint64_t allow_bits = a.allow_bits;
 
-        auto flush = [&](uint32_t need_mask) {
-            __syncwarp();  // make every lane's buffered candidates visible to the warp
-            while (need_mask) {
-                const int r = __ffs(need_mask) - 1;
-                need_mask &= need_mask - 1;
-                const int c = __shfl_sync(kFullMask, cnt, r);
-                const uint32_t qq = q0 + quarter * 32 + r;
-                uint64_t* list = a.part + ((size_t)qq * a.n_splits + split) * a.kp;
-                const uint64_t* rb = buf + (size_t)(quarter * 32 + r) * TC_BUFCAP;
-                for (int base = 0; base < c; base += 32) {
-                    uint64_t v = (base + lane < c) ? rb[base + lane] : kInvalidPacked;
-                    v = warp_sort32(v, lane, less);
-                    warp_list_merge(list, (int)a.kp, v, lane, less);
-                }
-                const uint64_t worst = list[a.kp - 1];
-                if (lane == r) {
-                    cnt = 0;
-                    if (worst != kInvalidPacked) thr = ord_to_f32(packed_hi(worst));
-                }
-                __syncwarp();
-            }
-        };
-
         for (uint32_t t = 0; t < n_tiles; ++t) {
             const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
-            const uint32_t n0 = r_lo + t * TC_N;
+            const uint32_t n0 = r_lo + t * TC_N + half * TC_HALF_N;   // first corpus row of this warp's columns
             float best_d = __int_as_float(0x7F800000);
             uint32_t best_c = kInvalidSlot;
             // per-column parameter of this tile (NaN marks columns outside the split); every epilogue warp keeps
-            // its own copy so the four warps never wait for each other
-            float* cp = colp + ((warp - 2) * 2 + acc) * TC_N;
-            for (int c = lane; c < TC_N; c += 32) {
+            // its own copy so the warps never wait for each other
+            float* cp = colp + ((warp - 2) * 2 + acc) * TC_HALF_N;
+            for (int c = lane; c < TC_HALF_N; c += 32) {
                 const uint32_t n = n0 + c;
-                float p = __int_as_float(0x7FC00000);
+                float pv = __int_as_float(0x7FC00000);
                 if (n < r_hi) {
-                    if constexpr (METRIC == VSB_METRIC_L2SQ) p = a.x_sq[n];
+                    if constexpr (METRIC == VSB_METRIC_L2SQ) pv = a.x_sq[n];
                     else if constexpr (METRIC == VSB_METRIC_COS) {
                         const float xn = a.x_nrm[n];
-                        p = xn > 0.f ? 1.0f / xn : 0.f;
-                    } else p = 1.0f;
+                        pv = xn > 0.f ? 1.0f / xn : 0.f;
+                    } else pv = 1.0f;
                 }
-                cp[c] = p;
+                cp[c] = pv;
             }
             __syncwarp();
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_N + half * TC_HALF_N;
 #pragma unroll 1
-            for (int ch = 0; ch < TC_N / 32; ++ch) {
+            for (int ch = 0; ch < TC_HALF_N / 32; ++ch) {
                 uint32_t v[32];
                 tmem_ld32(taddr + ch * 32, v);
-                // fast path: distance of 32 columns and their minimum (FFMA + FMNMX per column); only when the
-                // minimum beats the row's threshold — rare once the list has warmed up — is anything else done
                 const float4* cp4 = reinterpret_cast<const float4*>(cp + ch * 32);
-                float d[32];
-                float dmin = __int_as_float(0x7F800000);
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 p4 = cp4[j4];
-                    const float pj[4] = {p4.x, p4.y, p4.z, p4.w};
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = j4 * 4 + jj;
-                        const float dot = __uint_as_float(v[j]);
-                        if constexpr (METRIC == VSB_METRIC_L2SQ) d[j] = fmaf(dot, -2.0f, pj[jj]) + qsq;
-                        else if constexpr (METRIC == VSB_METRIC_COS) d[j] = fmaf(dot * pj[jj], -inv_qn, 1.0f);
-                        else d[j] = fmaf(dot, -1.0f, pj[jj]);
-                        dmin = fminf(dmin, d[j]);  // NaN (masked column) never wins
-                    }
-                }
                 if constexpr (TILE_MIN) {
+                    float d[32];
+                    float dmin = __int_as_float(0x7F800000);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 p4 = cp4[j4];
+                        const float pj[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = j4 * 4 + jj;
+                            d[j] = tc_dist<METRIC>(__uint_as_float(v[j]), pj[jj], qpar);
+                            dmin = fminf(dmin, d[j]);  // NaN (masked column) never wins
+                        }
+                    }
                     if (dmin < best_d) {
 #pragma unroll
                         for (int j = 31; j >= 0; --j)
@@ -421,35 +448,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         best_d = dmin;
                     }
                 } else {
-                    if (dmin <= thr) {
+                    // bit j = column j of this chunk beats (or ties) the row's k'-th best; NaN never does
+                    uint32_t hit = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (d[j] <= thr) {
-                                const uint32_t n = n0 + ch * 32 + j;
-                                bool ok = true;
-                                if (deny != nullptr && bit_test(deny, n)) ok = false;
-                                if (ok && allow != nullptr) {
-                                    const uint64_t rid = keys[n] & kRowMask48;
-                                    ok = rid < allow_bits && bit_test(allow, (uint32_t)rid);
-                                }
-                                if (ok) {
-                                    float dd = d[j];
-                                    if constexpr (METRIC == VSB_METRIC_L2SQ) dd = fmaxf(dd, 0.0f);
-                                    if constexpr (METRIC == VSB_METRIC_COS) dd = fminf(fmaxf(dd, 0.0f), 2.0f);
-                                    my_buf[cnt++] = pack_ds(dd, n);
-                                }
-                            }
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 p4 = cp4[j4];
+                        const float pj[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = j4 * 4 + jj;
+                            if (tc_dist<METRIC>(__uint_as_float(v[j]), pj[jj], qpar) <= thr) hit |= 1u << j;
                         }
                     }
-                    const uint32_t need = __ballot_sync(kFullMask, cnt > TC_BUFCAP - 32);
-                    if (need) flush(need);
+                    // The columns in which ANY row of the warp hit, one at a time (warp-uniform loop): the dot product
+                    // comes back from TMEM with a one-column load (registers cannot be indexed by a run-time j), the
+                    // same tc_dist gives the same bits, and only the rows that hit append.  With warmed-up lists
+                    // the loop body runs for well under one column per chunk (exact search) to a few (the build's
+                    // all-pairs lists, k' = 96 over 131 072 rows).
+                    uint32_t any_hit = __reduce_or_sync(kFullMask, hit);
+                    while (any_hit != 0) {
+                        const int j = __ffs(any_hit) - 1;
+                        any_hit &= any_hit - 1;
+                        const float dot = __uint_as_float(tmem_ld1(taddr + ch * 32 + j));
+                        if ((hit >> j) & 1u) {
+                            const uint32_t n = n0 + ch * 32 + j;
+                            bool ok = true;
+                            if (deny != nullptr && bit_test(deny, n)) ok = false;
+                            if (ok && allow != nullptr) {
+                                const uint64_t rid = keys[n] & kRowMask48;
+                                ok = rid < allow_bits && bit_test(allow, (uint32_t)rid);
+                            }
+                            if (ok) {
+                                float dd = tc_dist<METRIC>(dot, cp[ch * 32 + j], qpar);
+                                if constexpr (METRIC == VSB_METRIC_L2SQ) dd = fmaxf(dd, 0.0f);
+                                if constexpr (METRIC == VSB_METRIC_COS) dd = fminf(fmaxf(dd, 0.0f), 2.0f);
+                                my_buf[cnt++] = pack_ds(dd, n);
+                            }
+                        }
+                        const uint32_t full_rows = __ballot_sync(kFullMask, cnt == TC_BUFCAP);
+                        if (full_rows != 0) {
+                            thr = tc_flush_rows(full_rows, warp_lists, list_stride, a.kp, keys, warp_buf, cnt, thr, lane);
+                            if ((full_rows >> lane) & 1u) cnt = 0;
+                        }
+                    }
                 }
             }
             if constexpr (TILE_MIN) {
                 if (q_valid && best_c != kInvalidSlot && t < a.kp) {
                     if constexpr (METRIC == VSB_METRIC_L2SQ) best_d = fmaxf(best_d, 0.0f);
                     if constexpr (METRIC == VSB_METRIC_COS) best_d = fminf(fmaxf(best_d, 0.0f), 2.0f);
-                    a.part[((size_t)q * a.n_splits + split) * a.kp + t] = pack_ds(best_d, n0 + best_c);
+                    a.part[((size_t)q * a.n_splits + list_id) * a.kp + t] = pack_ds(best_d, n0 + best_c);
                 }
             }
             // accumulator drained: hand the TMEM buffer back to the MMA warp
@@ -460,8 +508,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 else mbar_arrive(&tmem_empty[acc]);
             }
         }
-        const uint32_t rest = __ballot_sync(kFullMask, cnt > 0);
-        if (rest) flush(rest);
+        if constexpr (!TILE_MIN) {
+            const uint32_t rest = __ballot_sync(kFullMask, cnt > 0);
+            if (rest) tc_flush_rows(rest, warp_lists, list_stride, a.kp, keys, warp_buf, cnt, thr, lane);
+        }
     }
 
     tc_fence_before();
@@ -560,37 +610,46 @@ bool exact_tc_supported(int storage, int metric) {
     return storage == VSB_ST_F32 || storage == VSB_ST_BF16 || storage == VSB_ST_F16;
 }
 
-// tile-min mode keeps one entry per tile: a split may not hold more than kp tiles
+// Both functions return the number of candidate LISTS per query (what ExactParams::n_splits means to K3 and to the
+// part buffer): TC_HALVES lists — one per epilogue column half — for each row split of the corpus.
+// tile-min mode keeps one entry per (tile, column half): a row split may not hold more than kp tiles
 uint32_t exact_tc_min_splits_tile_min(uint32_t n_rows, uint32_t kp) {
     const uint32_t tiles = (n_rows + TC_N - 1) / TC_N;
-    return (tiles + kp - 1) / kp;
+    return TC_HALVES * ((tiles + kp - 1) / kp);
 }
 
-uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count) {
-    // One CTA per SM: the sweep takes ceil(q_tiles * s / SMs) waves of 1/s of the corpus each.  Pick the split
-    // count that minimises waves / s (wave quantisation: 79 query tiles x 2 splits = 158 CTAs would run as
-    // two waves on 148 SMs), with a per-split penalty: every split warms its own lists up, and the operand
-    // stream is L2-bandwidth bound (~6.3 TB/s measured), so more resident CTAs do not add throughput.
+uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count, uint32_t kp) {
+    // One CTA per SM: the sweep takes ceil(q_tiles * s / SMs) waves of 1/s of the corpus each.  Pick the row-split
+    // count s that minimises waves / s, i.e. fills the last wave (79 query tiles x 1 split would leave 69 of 148 SMs
+    // idle; x 13 splits = 1027 CTAs = 6.94 waves) — weighed against the list work it adds: every list warms up on
+    // its own (~ kp * (1 + ln(rows_per_list / kp)) insertions, each worth ~10 scanned rows of epilogue time) and K3
+    // merges them all.  Short lists over many rows (exact search) split freely; the build's all-pairs lists
+    // (k' = 96 over 131 072 rows) stay at one split.  kp = 0: tile-min mode, no lists.  CTAs of one wave walk the
+    // same row split in step, so the corpus stream stays L2-resident however many splits there are.
     const uint32_t q_tiles = (nq + TC_M - 1) / TC_M;
-    uint32_t max_by_rows = (n_rows + 2 * TC_N - 1) / (2 * TC_N);  // >= 2 tiles per split
+    const uint32_t min_tiles = kp == 0 ? 2 : 8;
+    uint32_t max_by_rows = n_rows / (min_tiles * TC_N);
     if (max_by_rows < 1) max_by_rows = 1;
-    const uint32_t s_max = max_by_rows < 160 ? max_by_rows : 160;
-    static const double penalty = [] {
+    const uint32_t s_max = max_by_rows < 64 ? max_by_rows : 64;
+    static const double insert_cost = [] {
         const char* e = getenv("VSB_TC_SPLIT_PENALTY");
-        return e ? atof(e) : 1.0;
+        return e ? atof(e) : 10.0;
     }();
     uint32_t best = 1;
     double best_cost = 1e30;
     for (uint32_t s = 1; s <= s_max; ++s) {
         const uint32_t ctas = q_tiles * s;
         const uint32_t waves = (ctas + (uint32_t)sm_count - 1) / (uint32_t)sm_count;
-        const double cost = (double)waves / s * (1.0 + penalty * s);
+        const double lists = (double)TC_HALVES * s;
+        const double per_list = (double)n_rows / lists;
+        const double inserts = kp == 0 ? 1.0 : (double)kp * (1.0 + std::log(std::max(1.0, per_list / kp)));
+        const double cost = (double)waves / s * (1.0 + insert_cost * lists * inserts / (double)n_rows);
         if (cost < best_cost - 1e-12) {
             best_cost = cost;
             best = s;
         }
     }
-    return best;
+    return TC_HALVES * best;
 }
 
 // Same contract as launch_exact_candidates (exact.cu); returns false if the TMA descriptors could
@@ -611,14 +670,16 @@ bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream, bool 
     a.x_sq = p.x.sq; a.x_nrm = p.x.nrm; a.x_lo = p.x_lo; a.x_hi = p.x_hi; a.row_bytes = p.x.row_bytes;
     a.deny = p.deny; a.keys = p.keys; a.allow = p.allow; a.allow_bits = p.allow_bits;
     a.kp = p.kp; a.n_splits = p.n_splits;
+    if (p.n_splits % TC_HALVES != 0) return false;  // callers size the lists with exact_tc_pick_splits
+    const uint32_t row_splits = p.n_splits / TC_HALVES;
     const uint32_t rows = p.x_hi - p.x_lo;
-    const uint32_t rps = (rows + p.n_splits - 1) / p.n_splits;
+    const uint32_t rps = (rows + row_splits - 1) / row_splits;
     a.rows_per_split = ((rps + TC_N - 1) / TC_N) * TC_N;
     a.part = p.part;
     a.tile_min = tile_min ? 1 : 0;
     uint32_t q_tiles = (p.q.n + TC_M - 1) / TC_M;
     if (cta2) q_tiles = (q_tiles + 1) & ~1u;  // CTA pairs: an odd tail tile gets an all-padding partner
-    dim3 grid(q_tiles, p.n_splits);
+    dim3 grid(q_tiles, row_splits);
     switch (kind) {
         case KIND_BF16: launch_tc_kind<KIND_BF16>(p.metric, mq, mx, a, grid, stream, cta2); break;
         case KIND_F16: launch_tc_kind<KIND_F16>(p.metric, mq, mx, a, grid, stream, cta2); break;

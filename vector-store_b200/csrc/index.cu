@@ -55,6 +55,15 @@ cudaStream_t pool_stream(int device) {
     return streams[device];
 }
 
+static int64_t now_ns() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+MutGuard::MutGuard(vsb_index* ix) : lock(ix->mut_mu) {
+    const bool searching = ix->mstream_green != nullptr && now_ns() - ix->last_search_ns.load(std::memory_order_relaxed) < 2000000000ll;
+    ix->mstream = searching ? ix->mstream_green : ix->mstream_full;
+}
+
 uint32_t storage_row_bytes(int storage, uint32_t dim) {
     uint64_t bits = 0;
     switch (storage) {
@@ -476,6 +485,7 @@ vsb_status create_single(const vsb_options* o, vsb_index** out) {
     if (const char* v = getenv("VSB_ALLPAIRS_MAX")) ix->allpairs_max = (uint32_t)strtoul(v, nullptr, 10);
     if (const char* v = getenv("VSB_ALLPAIRS_PREFIX")) ix->allpairs_prefix = (uint32_t)strtoul(v, nullptr, 10);
     if (const char* v = getenv("VSB_REFINE_PASSES")) ix->refine_passes = (uint32_t)strtoul(v, nullptr, 10);
+    if (const char* v = getenv("VSB_CHURN_REFINE")) ix->churn_refine = !(v[0] == '0');
     if (const char* v = getenv("VSB_BUILD_SW")) ix->build_search_width = std::min<uint32_t>(4, std::max<uint32_t>(1, (uint32_t)strtoul(v, nullptr, 10)));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
@@ -484,10 +494,19 @@ vsb_status create_single(const vsb_options* o, vsb_index** out) {
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     e = cudaStreamCreateWithPriority(&ix->stream, cudaStreamNonBlocking, prio_hi);
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ix->mstream, cudaStreamNonBlocking, prio_lo);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ix->mstream_full, cudaStreamNonBlocking, prio_lo);
     if (e != cudaSuccess) {
         destroy_single(ix);
         return fail(VSB_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    ix->mstream = ix->mstream_full;
+    unsigned reserve = 12;  // SMs the mutators never touch while searches are active (VSB_SEARCH_SM_RESERVE, 0 = off)
+    if (const char* v = getenv("VSB_SEARCH_SM_RESERVE")) reserve = (unsigned)strtoul(v, nullptr, 10);
+    if (reserve > 0) {
+        unsigned sms = 0;
+        if (make_green_stream(dev, reserve, prio_lo, &ix->mstream_green, &ix->green_ctx, &sms)) ix->green_sms = sms;
+        if (getenv("VSB_VERBOSE")) fprintf(stderr, "vsb200: mutator green context on device %d: %s (%u SMs, %u reserved for searches)\n", dev, ix->mstream_green ? "on" : "unavailable", sms, reserve);
+        CU(cudaSetDevice(dev));
     }
     ix->w.st = std::make_shared<Store>();
     ix->publish();
@@ -507,7 +526,9 @@ void destroy_single(vsb_index* ix) {
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
     }
     if (ix->stream) cudaStreamDestroy(ix->stream);
-    if (ix->mstream) cudaStreamDestroy(ix->mstream);
+    if (ix->mstream_full) cudaStreamDestroy(ix->mstream_full);
+    if (ix->mstream_green) cudaStreamDestroy(ix->mstream_green);
+    if (ix->green_ctx) destroy_green(ix->green_ctx);
     delete ix;
 }
 
@@ -540,7 +561,7 @@ void vsb_destroy(vsb_index* ix) {
 vsb_status vsb_reserve(vsb_index* ix, uint64_t capacity) {
     if (!ix) return fail(VSB_EINVAL, "null index");
     if (ix->sharded) return vsbi::sharded_reserve(ix, capacity);
-    std::lock_guard<std::mutex> g(ix->mut_mu);
+    vsbi::MutGuard g(ix);
     return ix->reserve(capacity);
 }
 
@@ -558,14 +579,14 @@ uint64_t vsb_size(const vsb_index* ix) {
 vsb_status vsb_add(vsb_index* ix, const uint64_t* keys, const float* rows, uint64_t n) {
     if (!ix) return fail(VSB_EINVAL, "null index");
     if (ix->sharded) return vsbi::sharded_add(ix, keys, rows, n, nullptr, nullptr);
-    std::lock_guard<std::mutex> g(ix->mut_mu);
+    vsbi::MutGuard g(ix);
     return ix->add(keys, rows, n, nullptr, nullptr);
 }
 
 vsb_status vsb_add_dev(vsb_index* ix, const uint64_t* keys, const float* d_rows, uint64_t n) {
     if (!ix) return fail(VSB_EINVAL, "null index");
     if (ix->sharded) return fail(VSB_EINVAL, "vsb_add_dev takes rows that already live on the index's device: add to a shard handle");
-    std::lock_guard<std::mutex> g(ix->mut_mu);
+    vsbi::MutGuard g(ix);
     CU(cudaSetDevice(ix->device));
     CU(cudaDeviceSynchronize());  // the rows were produced on a stream of the caller's
     return ix->add(keys, d_rows, n, nullptr, nullptr, true);
@@ -580,7 +601,7 @@ vsb_status vsb_add_each(vsb_index* ix, const uint64_t* keys, const float* rows, 
         row_status = local.data();
     }
     if (ix->sharded) return vsbi::sharded_add(ix, keys, rows, n, row_status, n_added);
-    std::lock_guard<std::mutex> g(ix->mut_mu);
+    vsbi::MutGuard g(ix);
     return ix->add(keys, rows, n, row_status, n_added);
 }
 
@@ -590,7 +611,7 @@ vsb_status vsb_remove(vsb_index* ix, const uint64_t* keys, uint64_t n, uint64_t*
     if (n == 0) return VSB_OK;
     if (!keys) return fail(VSB_EINVAL, "null keys");
     if (ix->sharded) return vsbi::sharded_remove(ix, keys, n, n_removed);
-    std::lock_guard<std::mutex> g(ix->mut_mu);
+    vsbi::MutGuard g(ix);
     return ix->remove(keys, n, n_removed);
 }
 
@@ -605,7 +626,7 @@ int vsb_contains(const vsb_index* cix, uint64_t key) {
 vsb_status vsb_build(vsb_index* ix) {
     if (!ix) return fail(VSB_EINVAL, "null index");
     if (ix->sharded) return vsbi::sharded_build(ix);
-    std::lock_guard<std::mutex> g(ix->mut_mu);
+    vsbi::MutGuard g(ix);
     nvtxRangePushA("vsb_build");
     const auto t0 = std::chrono::steady_clock::now();
     const vsb_status st = ix->build();
@@ -619,7 +640,7 @@ vsb_status vsb_build(vsb_index* ix) {
 vsb_status vsb_insert_pending(vsb_index* ix) {
     if (!ix) return fail(VSB_EINVAL, "null index");
     if (ix->sharded) return vsbi::sharded_insert_pending(ix);
-    std::lock_guard<std::mutex> g(ix->mut_mu);
+    vsbi::MutGuard g(ix);
     const vsb_status st = ix->stream_insert();
     if (st == VSB_OK) ix->publish();
     return st;

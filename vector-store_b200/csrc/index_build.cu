@@ -99,7 +99,8 @@ vsb_status vsb_index::build() {
     {
         nvtxRangePushA("build.allpairs");
         EvTimer t(mstream);
-        const uint32_t QB = 16384;
+        // query blocks of one 128-row tensor-core tile per SM: a block is exactly one wave of K1-TC CTAs
+        const uint32_t QB = std::max<uint32_t>(16384, (uint32_t)sm_count * 128);
         for (uint32_t b0 = 0; b0 < n; b0 += QB) {
             vsb::RowsView q;
             q.n = std::min(QB, n - b0);
@@ -277,8 +278,10 @@ vsb_status vsb_index::sample_seeds(uint32_t n, bool ensure_reach) {
                 for (int i = 0; i < 4; ++i)
                     vsb::launch_reach_step(w.gr->g.as<uint32_t>(), n, graph_stride, degree, state, flag, mstream);
                 uint32_t changed = 0;
-                CU(cudaMemcpyAsync(&changed, flag, 4, cudaMemcpyDeviceToHost, mstream));
-                CU(cudaStreamSynchronize(mstream));
+                vsbi::HostReadback rb(ms.pin, mstream);
+                CU(rb.reserve(4));
+                CU(rb.copy(&changed, flag, 4));
+                CU(rb.finish());
                 if (!changed) break;
             }
             return VSB_OK;
@@ -290,8 +293,12 @@ vsb_status vsb_index::sample_seeds(uint32_t n, bool ensure_reach) {
         while (extra_seeds < reach_budget) {
             const uint32_t room = std::min<uint32_t>(kPromote, reach_budget - extra_seeds);
             vsb::launch_collect_unreached(state, deny_bm, n, room, found, mstream);
-            CU(cudaMemcpyAsync(h_found.data(), found, (size_t)(1 + room) * 4, cudaMemcpyDeviceToHost, mstream));
-            CU(cudaStreamSynchronize(mstream));
+            {
+                vsbi::HostReadback rb(ms.pin, mstream);
+                CU(rb.reserve((size_t)(1 + room) * 4));
+                CU(rb.copy(h_found.data(), found, (size_t)(1 + room) * 4));
+                CU(rb.finish());
+            }
             const uint32_t cnt = std::min(h_found[0], room);
             if (cnt == 0) break;
             for (uint32_t i = 0; i < cnt; ++i) h_seeds.push_back(h_found[1 + i]);
@@ -392,7 +399,7 @@ vsb_status vsb_index::stream_insert() {
     // 10 % of the graph has churned, one refinement pass (K4 kNN lists of every row -> K6) restores the
     // quality of a fresh build and drops the tombstoned rows from every list.  Searches are not held up:
     // the pass builds a new graph beside the published one.
-    if (!in_build && refine_passes > 0 && churn_since_refine * 10 >= w.n_graphed && w.n_graphed >= min_graph_size) {
+    if (!in_build && churn_refine && churn_since_refine * 10 >= w.n_graphed && w.n_graphed >= min_graph_size) {
         publish();  // the streamed rows are navigable from here on
         ST(refine_graph());
         ST(sample_seeds(w.n_graphed));

@@ -20,10 +20,12 @@
 //   Graph : [cap][stride] u32 fixed-degree neighbour rows; rows >= n_graphed are the brute-force tail
 //   Seeds : contiguous copy of the entry-point sample ("upper layer")
 #pragma once
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <deque>
 #include <memory>
 #include <mutex>
@@ -132,6 +134,78 @@ struct DevBuf {
 
 inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 
+// Device -> host copies never go straight into PAGEABLE memory: for such a destination cudaMemcpyAsync waits INSIDE the
+// call — holding the context lock — until the stream has reached the copy, and every other thread's CUDA call queues up
+// behind it.  Measured in config C5: while a refinement pass read back its 16-byte work counters after each K4 launch,
+// every concurrent batch-1 search took one whole launch (21 ms) instead of 0.3 ms.  Pageable destinations are staged
+// through a pinned buffer (the async copy returns at once, the wait is a cudaStreamSynchronize, which blocks nobody
+// else); destinations the caller pinned (cudaHostAlloc / cudaHostRegister, e.g. bench.py's e2e buffers) are written
+// directly.
+struct PinBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    PinBuf() = default;
+    PinBuf(const PinBuf&) = delete;
+    PinBuf& operator=(const PinBuf&) = delete;
+    ~PinBuf() {
+        if (p) cudaFreeHost(p);
+    }
+    cudaError_t ensure(size_t want) {
+        if (want <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        const size_t sz = std::max<size_t>(want + want / 4, 4096);
+        const cudaError_t e = cudaHostAlloc(&p, sz, cudaHostAllocDefault);
+        if (e == cudaSuccess) bytes = sz;
+        else p = nullptr;
+        return e;
+    }
+};
+
+inline bool host_is_pinned(const void* ptr) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+// A batch of device -> host copies on one stream followed by one synchronisation.  reserve() the total first.
+class HostReadback {
+    PinBuf& pin;
+    cudaStream_t s;
+    struct Item {
+        void* dst;
+        size_t off, bytes;
+    };
+    Item items[4];
+    int n_items = 0;
+    size_t used = 0;
+
+   public:
+    HostReadback(PinBuf& pin_, cudaStream_t s_) : pin(pin_), s(s_) {}
+    cudaError_t reserve(size_t total) { return pin.ensure(total + 4 * 256); }
+    cudaError_t copy(void* dst, const void* src_dev, size_t bytes) {
+        if (bytes == 0) return cudaSuccess;
+        if (host_is_pinned(dst)) return cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, s);
+        if (n_items == 4 || used + bytes > pin.bytes) return cudaErrorInvalidValue;
+        items[n_items++] = Item{dst, used, bytes};
+        const cudaError_t e = cudaMemcpyAsync(static_cast<uint8_t*>(pin.p) + used, src_dev, bytes, cudaMemcpyDeviceToHost, s);
+        used += (bytes + 255) / 256 * 256;
+        return e;
+    }
+    cudaError_t finish() {
+        const cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return e;
+        for (int i = 0; i < n_items; ++i) std::memcpy(items[i].dst, static_cast<uint8_t*>(pin.p) + items[i].off, items[i].bytes);
+        n_items = 0;
+        used = 0;
+        return cudaSuccess;
+    }
+};
+
 // capacity-sized per-row arrays; reserve / compaction build a NEW store and publish it
 struct Store {
     uint64_t capacity = 0;
@@ -169,6 +243,7 @@ struct Scratch {
     DevBuf q_in, q_rows, q_sq, q_nrm, q16_rows, q16_sq, q16_nrm, q8_rows, q8_sq, q8_nrm;
     DevBuf part, seed_part, tmp_keys, tmp_dists, rr_packed, counters, allow;
     DevBuf cert_state, fb_map, fb_rows, fb_sq, fb_nrm;  // certified exact search
+    PinBuf pin;                                          // pinned staging of this caller class's read-backs
     size_t bytes() const {
         const DevBuf* all[] = {&q_in, &q_rows, &q_sq, &q_nrm, &q16_rows, &q16_sq, &q16_nrm, &q8_rows, &q8_sq, &q8_nrm, &part,
                                &seed_part, &tmp_keys, &tmp_dists, &rr_packed, &counters, &allow, &cert_state, &fb_map,
@@ -197,7 +272,11 @@ struct vsb_index {
     uint32_t cert_kp = 128, cert_kp16 = 32;
     bool reach_fix = true;
     uint32_t reach_budget = 1024;
-    uint32_t allpairs_max = 262144, allpairs_prefix = 131072, refine_passes = 1;
+    uint32_t allpairs_max = 262144, allpairs_prefix = 131072;
+    // refinement passes at the end of vsb_build (VSB_REFINE_PASSES).  0 by default: with detour-pruned K7 links a pass buys
+    // ~2 % QPS at equal recall and costs 1.7x the rest of the build (10 M x 768: 5.7 s -> 16.6 s, profiles/r2_*)
+    uint32_t refine_passes = 0;
+    bool churn_refine = true;  // one refinement pass after 10 % of the graph has churned (VSB_CHURN_REFINE=0 turns it off)
     uint32_t build_search_width = 2;  // parents per K4 iteration in the streaming insert / refinement searches (VSB_BUILD_SW)
     vsbi::Sharded* sharded = nullptr;  // n_devices > 1: every entry point forwards to the router (owned; sharded.cu)
 
@@ -223,6 +302,7 @@ struct vsb_index {
     // host-pointer searches of >= 1024 queries: two staging slots with their own copy stream (search_host)
     struct HostSlot {
         vsbi::DevBuf buf;
+        vsbi::PinBuf pin;
         cudaStream_t cs = nullptr;
         cudaEvent_t ev_in = nullptr, ev_done = nullptr;
         bool busy = false;
@@ -255,7 +335,11 @@ struct vsb_index {
 
     // ---- mutator side (mut_mu) ----
     std::mutex mut_mu;
-    cudaStream_t mstream = nullptr;  // mutator stream (low priority)
+    cudaStream_t mstream = nullptr;  // the stream the running mutator uses: mstream_green while searches are active
+    cudaStream_t mstream_full = nullptr, mstream_green = nullptr;  // low priority on all SMs / green context (green.cu)
+    void* green_ctx = nullptr;
+    uint32_t green_sms = 0;
+    std::atomic<int64_t> last_search_ns{0};  // steady-clock time of the latest search (mutators pick their stream by it)
     vsbi::Scratch ms;
     vsbi::View w;                    // the mutators' working view; `publish()` makes it current
     uint64_t live = 0;
@@ -317,6 +401,16 @@ struct vsb_index {
 };
 
 namespace vsbi {
+// green.cu
+bool make_green_stream(int device, unsigned reserve_sms, int priority, cudaStream_t* stream_out, void** ctx_out,
+                       unsigned* sms_out);
+void destroy_green(void* ctx);
+// Mutator entry: takes mut_mu and picks the stream — the green-context stream (a few SMs stay free for searches) if a
+// search ran within the last two seconds, the whole device otherwise (a bulk build with nobody searching).
+struct MutGuard {
+    std::lock_guard<std::mutex> lock;
+    explicit MutGuard(vsb_index* ix);
+};
 uint32_t storage_row_bytes(int storage, uint32_t dim);
 // index.cu: creates an un-sharded handle on opt.device (shared by vsb_create, the router and vsb_load)
 vsb_status create_single(const vsb_options* o, vsb_index** out);

@@ -2,6 +2,7 @@
 // blocks (seed layer + K4 [+ K3 re-rank]), and the two entry points (device pointers / host pointers).
 // Replaces usearch::Index::search / filtered_search behind vs_index/usearch.rs:203-248.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 
 #include <nvtx3/nvToolsExt.h>
@@ -45,7 +46,7 @@ vsb_status vsb_index::exact_block(const View& v, Scratch& sc, const vsb::RowsVie
     bool tc = tc_shape && (approx_ok || storage != VSB_F32 || certify);
     const uint32_t kp_simt = p.kp;
     if (certify && tc) p.kp = std::min<uint32_t>(256, std::max<uint32_t>(p.kp, round_up(storage == VSB_F32 ? cert_kp : cert_kp16, 32)));
-    p.n_splits = tc ? vsb::exact_tc_pick_splits(q.n, x_hi - x_lo, sm_count)
+    p.n_splits = tc ? vsb::exact_tc_pick_splits(q.n, x_hi - x_lo, sm_count, p.kp)
                     : vsb::exact_pick_splits(q.n, x_hi - x_lo, sm_count);
     CU(sc.part.ensure(vsb::exact_part_elems(q.n, p.n_splits, p.kp) * 8));
     p.part = sc.part.as<uint64_t>();
@@ -99,8 +100,12 @@ vsb_status vsb_index::exact_block(const View& v, Scratch& sc, const vsb::RowsVie
     std::vector<uint32_t> map, flags;
     auto collect = [&](uint32_t n_stage, const std::vector<uint32_t>* prev) -> vsb_status {
         flags.resize(n_stage);
-        CU(cudaMemcpyAsync(flags.data(), d_flags, (size_t)n_stage * 4, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+        {
+            vsbi::HostReadback rb(sc.pin, s);
+            CU(rb.reserve((size_t)n_stage * 4));
+            CU(rb.copy(flags.data(), d_flags, (size_t)n_stage * 4));
+            CU(rb.finish());
+        }
         std::vector<uint32_t> next;
         for (uint32_t i = 0; i < n_stage; ++i)
             if (flags[i]) next.push_back(prev ? (*prev)[i] : i);
@@ -117,8 +122,10 @@ vsb_status vsb_index::exact_block(const View& v, Scratch& sc, const vsb::RowsVie
         return VSB_OK;
     };
     auto read_count = [&](uint32_t* out) -> vsb_status {
-        CU(cudaMemcpyAsync(out, d_count, 4, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+        vsbi::HostReadback rb(sc.pin, s);
+        CU(rb.reserve(4));
+        CU(rb.copy(out, d_count, 4));
+        CU(rb.finish());
         return VSB_OK;
     };
 
@@ -225,7 +232,7 @@ vsb_status vsb_index::graph_block(const View& v, Scratch& sc, const GraphRun& ru
     if (seed_tc) {
         // tensor cores: one winner per 256-row tile per query (no list maintenance);
         // f32 storage multiplies the bf16 shadows of the queries and of the seed block
-        sp.n_splits = std::max(vsb::exact_tc_pick_splits(nb, sd.n, sm_count), vsb::exact_tc_min_splits_tile_min(sd.n, 32));
+        sp.n_splits = std::max(vsb::exact_tc_pick_splits(nb, sd.n, sm_count, 0), vsb::exact_tc_min_splits_tile_min(sd.n, 32));
         if (storage == VSB_F32) {
             sp.storage = VSB_BF16;
             sp.q = q16v;
@@ -356,8 +363,12 @@ vsb_status vsb_index::graph_block(const View& v, Scratch& sc, const GraphRun& ru
     }
     if (count) {
         unsigned long long h[2];
-        CU(cudaMemcpyAsync(h, sc.counters.p, 16, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+        {
+            vsbi::HostReadback rb(sc.pin, s);  // pinned staging: see index_impl.h (a pageable read-back stalls every search)
+            CU(rb.reserve(16));
+            CU(rb.copy(h, sc.counters.p, 16));
+            CU(rb.finish());
+        }
         if (evals_out) *evals_out += h[0];
         if (parents_out) *parents_out += h[1];
         if (run.count) {
@@ -377,6 +388,8 @@ vsb_status vsb_index::search_dev(const float* d_q, uint64_t nq, uint32_t k, uint
     if (k == 0) return fail(VSB_EINVAL, "k must be > 0");
     if (d_q == nullptr || d_keys == nullptr || d_dists == nullptr) return fail(VSB_EINVAL, "null buffer");
     CU(cudaSetDevice(device));
+    last_search_ns.store(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(),
+                         std::memory_order_relaxed);
     const View v = snapshot();
     ST(begin_search(s));
     Scratch& sc = ss;
@@ -551,10 +564,13 @@ vsb_status vsb_index::search_host(const float* queries, uint64_t nq, uint32_t k,
             CU(cudaEventRecord(sl.ev_done, stream));
         }
         CU(cudaStreamWaitEvent(sl.cs, sl.ev_done, 0));
-        CU(cudaMemcpyAsync(keys_out, dk, keys_bytes, cudaMemcpyDeviceToHost, sl.cs));
-        CU(cudaMemcpyAsync(dists_out, dd, dists_bytes, cudaMemcpyDeviceToHost, sl.cs));
-        if (counts_out) CU(cudaMemcpyAsync(counts_out, dc, counts_bytes, cudaMemcpyDeviceToHost, sl.cs));
-        CU(cudaStreamSynchronize(sl.cs));
+        vsbi::HostReadback rb(sl.pin, sl.cs);
+        if (!vsbi::host_is_pinned(keys_out) || !vsbi::host_is_pinned(dists_out) || (counts_out && !vsbi::host_is_pinned(counts_out)))
+            CU(rb.reserve(al(keys_bytes) + al(dists_bytes) + al(counts_bytes)));
+        CU(rb.copy(keys_out, dk, keys_bytes));
+        CU(rb.copy(dists_out, dd, dists_bytes));
+        if (counts_out) CU(rb.copy(counts_out, dc, counts_bytes));
+        CU(rb.finish());
         return VSB_OK;
     }
     std::lock_guard<std::mutex> g(search_mu);
@@ -578,10 +594,12 @@ vsb_status vsb_index::search_host(const float* queries, uint64_t nq, uint32_t k,
         allow_pop = popcount_words(allow_bitmap, words, allow_bits);
     }
     ST(search_dev(dq, nq, k, dk, dd, dc, stream, exact, d_allow, allow_bits, allow_pop));
-    CU(cudaMemcpyAsync(keys_out, dk, keys_bytes, cudaMemcpyDeviceToHost, stream));
-    CU(cudaMemcpyAsync(dists_out, dd, dists_bytes, cudaMemcpyDeviceToHost, stream));
-    if (counts_out) CU(cudaMemcpyAsync(counts_out, dc, counts_bytes, cudaMemcpyDeviceToHost, stream));
-    CU(cudaStreamSynchronize(stream));
+    vsbi::HostReadback rb(ss.pin, stream);
+    CU(rb.reserve(al(keys_bytes) + al(dists_bytes) + al(counts_bytes)));
+    CU(rb.copy(keys_out, dk, keys_bytes));
+    CU(rb.copy(dists_out, dd, dists_bytes));
+    if (counts_out) CU(rb.copy(counts_out, dc, counts_bytes));
+    CU(rb.finish());
     reap_inflight(true);
     return VSB_OK;
 }

@@ -75,7 +75,7 @@ void launch_max_norm(const float* nrm, uint32_t lo, uint32_t hi, float* out, cud
 
 // K1 on tcgen05 tensor cores (exact_tc.cu): same contract as launch_exact_candidates.
 bool exact_tc_supported(int storage, int metric);
-uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count);
+uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count, uint32_t kp);
 bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream, bool tile_min = false);
 uint32_t exact_tc_min_splits_tile_min(uint32_t n_rows, uint32_t kp);
 

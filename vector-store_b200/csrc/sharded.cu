@@ -40,6 +40,7 @@ struct Sharded {
     cudaStream_t stream0 = nullptr;
     cudaEvent_t q_ready = nullptr;
     DevBuf g_keys, g_dists, out_buf, q0;
+    PinBuf pin;  // pinned staging of the merged results for pageable callers
     // per shard
     std::vector<DevBuf> qbuf, allow;
     std::vector<cudaEvent_t> done_ev;
@@ -220,7 +221,7 @@ vsb_status sharded_reserve(vsb_index* ix, uint64_t capacity) {
     if (capacity <= S.cap_requested) return VSB_OK;
     const uint64_t per = shard_capacity_for(capacity, S.G());
     ST(S.for_each([&](uint32_t i) {
-        std::lock_guard<std::mutex> l(S.shards[i]->mut_mu);
+        MutGuard l(S.shards[i]);
         return S.shards[i]->reserve(per);
     }));
     S.cap_requested = capacity;
@@ -278,7 +279,7 @@ vsb_status sharded_add(vsb_index* ix, const uint64_t* keys, const float* rows, u
             std::memcpy(&r2[j * dim], rows + mine[j] * dim, (size_t)dim * 4);
         }
         vsb_index* sh = S.shards[s];
-        std::lock_guard<std::mutex> l(sh->mut_mu);
+        MutGuard l(sh);
         const uint64_t cap = sh->w.st ? sh->w.st->capacity : 0;
         if (sh->live + mine.size() > cap) ST(sh->reserve((sh->live + mine.size()) + (sh->live + mine.size()) / 8 + 64));
         const vsb_status rc = sh->add(k2.data(), r2.data(), mine.size(), row_status ? st2.data() : nullptr, &added[s]);
@@ -300,7 +301,7 @@ vsb_status sharded_remove(vsb_index* ix, const uint64_t* keys, uint64_t n, uint6
     std::vector<uint64_t> removed(G, 0);
     ST(S.for_each([&](uint32_t s) -> vsb_status {
         if (ks[s].empty()) return VSB_OK;
-        std::lock_guard<std::mutex> l(S.shards[s]->mut_mu);
+        MutGuard l(S.shards[s]);
         return S.shards[s]->remove(ks[s].data(), ks[s].size(), &removed[s]);
     }));
     if (n_removed)
@@ -472,10 +473,12 @@ vsb_status sharded_search_host(vsb_index* ix, const float* queries, uint64_t nq,
         for (size_t i = 0; i < words; ++i) pop += (uint64_t)__builtin_popcount(allow_bitmap[i]);
     }
     ST(fan_out(ix, S.q0.as<float>(), S.q_ready, nq, k, ok, od, oc, S.stream0, exact, allow_bitmap, allow_bits, pop));
-    CU(cudaMemcpyAsync(keys, ok, kb, cudaMemcpyDeviceToHost, S.stream0));
-    CU(cudaMemcpyAsync(dists, od, db, cudaMemcpyDeviceToHost, S.stream0));
-    if (counts) CU(cudaMemcpyAsync(counts, oc, cb, cudaMemcpyDeviceToHost, S.stream0));
-    CU(cudaStreamSynchronize(S.stream0));
+    vsbi::HostReadback rb(S.pin, S.stream0);  // pageable destinations are staged (index_impl.h)
+    CU(rb.reserve(al(kb) + al(db) + al(cb)));
+    CU(rb.copy(keys, ok, kb));
+    CU(rb.copy(dists, od, db));
+    if (counts) CU(rb.copy(counts, oc, cb));
+    CU(rb.finish());
     return VSB_OK;
 }
 
