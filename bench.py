@@ -600,7 +600,9 @@ def main():
         torch.cuda.synchronize()
 
     if world > 1:
-        s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+        # high priority: the gather / copy kernels of batch j+1 must get a CTA slot while K4 of batch j fills every SM,
+        # or the upload lands on the critical path instead of under the search
+        s_up, s_down = torch.cuda.Stream(priority=-1), torch.cuda.Stream(priority=-1)
         q_slices = [torch.empty((slice_rows, dim), dtype=torch.float32, device=dev) for _ in range(2)]
         q_priv = [torch.empty((B, dim), dtype=torch.float32, device=dev) for _ in range(2)]
         outs = [(torch.empty((B, k), dtype=torch.int64, device=dev), torch.empty((B, k), dtype=torch.float32, device=dev))

@@ -104,3 +104,35 @@ def test_struct_layouts_match_the_ctypes_mirror(tmp_path):
     for decl in re.findall(r"uint64_t\s+([^;]+);", body):
         names += [n.strip() for n in decl.split(",")]
     assert names == [n for n, _ in native.VsbStats._fields_], (names, [n for n, _ in native.VsbStats._fields_])
+
+
+def _header_struct_fields(name):
+    text = open(os.path.join(ROOT, "include", "vsb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    body = next(chunk.split("}")[0] for chunk in text.split("typedef struct {")[1:]
+                if re.match(r"\s*" + name + r"\s*;", chunk.split("}", 1)[1]))
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.split(None, 1)[1]
+        fields += [re.sub(r"\[.*?\]", "", n).strip() for n in names.split(",")]
+    return fields
+
+
+def test_rust_ffi_declares_every_header_symbol():
+    """integration/vsb200-sys/src/lib.rs (uncompiled here: no cargo) stays in step with the header: every entry point
+    declared, every struct with the same field names in the same order."""
+    rs = open(os.path.join(ROOT, "integration", "vsb200-sys", "src", "lib.rs")).read()
+    declared_rs = sorted(set(re.findall(r"pub fn (vsb_[a-z0-9_]+)\s*\(", rs)))
+    assert declared_rs == _header_symbols()
+    for struct in ("vsb_options", "vsb_search_params", "vsb_stats", "vsb_build_stats"):
+        body = re.search(r"pub struct " + struct + r" \{(.*?)\n\}", rs, flags=re.S).group(1)
+        fields_rs = re.findall(r"pub ([a-z0-9_]+):", body)
+        assert fields_rs == _header_struct_fields(struct), struct
+    gpu = open(os.path.join(ROOT, "integration", "vs_index", "gpu.rs")).read()
+    for call in re.findall(r"sys::(vsb_[a-z0-9_]+)\(", gpu):
+        assert call in declared_rs, call
+    for elision in ("(..)", ", ..,", "-> ...", "..., "):
+        assert elision not in gpu, "gpu.rs must be complete source, no elisions"

@@ -213,17 +213,62 @@ __device__ __forceinline__ float tc_dist(float dot, float col, float qpar) {
 __device__ __noinline__ float tc_flush_rows(uint32_t need_mask, uint64_t* warp_lists, size_t list_stride, uint32_t kp,
                                             const uint64_t* keys, const uint64_t* warp_buf, int cnt, float thr, int lane) {
     const LessByKey less{keys};
+    constexpr int MAXB = 8;  // kp <= 256
+    const int nb = (int)(kp >> 5);
     __syncwarp();  // make every lane's buffered candidates visible to the warp
-    while (need_mask) {
-        const int r = __ffs(need_mask) - 1;
+    // The lists live in global memory (L2): all blocks of a row's list are fetched with independent loads BEFORE the
+    // buffer is sorted, and the next row's list is fetched while this row's is merged, so a flush pays the L2
+    // latency once instead of once per 32-entry block (the build's all-pairs lists are 128 long and flush ~60 times
+    // per row and launch).
+    uint64_t blk[MAXB], nxt[MAXB];
+    int r = __ffs(need_mask) - 1;
+    need_mask &= need_mask - 1;
+    {
+        const uint64_t* list = warp_lists + (size_t)r * list_stride;
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) blk[b] = b < nb ? list[b * 32 + lane] : kInvalidPacked;
+    }
+    while (true) {
+        const int r_next = need_mask ? __ffs(need_mask) - 1 : -1;
         need_mask &= need_mask - 1;
+        if (r_next >= 0) {
+            const uint64_t* list = warp_lists + (size_t)r_next * list_stride;
+#pragma unroll
+            for (int b = 0; b < MAXB; ++b) nxt[b] = b < nb ? list[b * 32 + lane] : kInvalidPacked;
+        }
         const int c = __shfl_sync(kFullMask, cnt, r);
         uint64_t* list = warp_lists + (size_t)r * list_stride;
-        uint64_t v = lane < c ? warp_buf[(size_t)r * TC_BUFCAP + lane] : kInvalidPacked;
-        v = warp_sort32(v, lane, less);
-        warp_list_merge(list, (int)kp, v, lane, less);
-        const uint64_t worst = list[kp - 1];
+        uint64_t carry = lane < c ? warp_buf[(size_t)r * TC_BUFCAP + lane] : kInvalidPacked;
+        carry = warp_sort32(carry, lane, less);
+        uint64_t worst = kInvalidPacked;
+        // one ROLLED loop over the blocks (the body — two bitonic merges — is the bulk of this function's code and
+        // must stay small for the instruction cache); the prefetched blocks rotate through blk[0]
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            uint64_t cur = blk[0];
+#pragma unroll
+            for (int i = 0; i + 1 < MAXB; ++i) blk[i] = blk[i + 1];
+            // nothing in the carry beats this block's maximum -> block unchanged, carry unchanged
+            const uint64_t blk_max = shfl_u64(cur, 31);
+            const uint64_t carry_min = shfl_u64(carry, 0);
+            if (less(carry_min, blk_max)) {
+                const uint64_t rc = shfl_u64(carry, 31 - lane);
+                const bool rc_less = less(rc, cur);
+                uint64_t lo = rc_less ? rc : cur;
+                uint64_t hi = rc_less ? cur : rc;
+                lo = warp_bitonic_merge32(lo, lane, less);
+                hi = warp_bitonic_merge32(hi, lane, less);
+                list[b * 32 + lane] = lo;
+                cur = lo;
+                carry = hi;
+            }
+            worst = shfl_u64(cur, 31);  // after the last block: the list's k'-th best
+        }
         if (lane == r && worst != kInvalidPacked) thr = ord_to_f32(packed_hi(worst));
+        if (r_next < 0) break;
+        r = r_next;
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) blk[b] = nxt[b];
     }
     __syncwarp();
     return thr;
@@ -605,6 +650,15 @@ void launch_tc_kind(int metric, const CUtensorMap& mq, const CUtensorMap& mx, co
 
 }  // namespace
 
+// cta_group::2 form of the list-maintaining kernel (VSB_TC_2CTA=0/1); the seed layer's tile-min kernel is always 1-CTA
+static bool tc_use_cta_pairs() {
+    static const bool on = [] {
+        const char* e = getenv("VSB_TC_2CTA");
+        return e != nullptr ? e[0] == '1' : true;  // default on: 1 046 vs 964 TFLOP/s on 10 000 x 1 M x 768 bf16
+    }();
+    return on;
+}
+
 bool exact_tc_supported(int storage, int metric) {
     if (metric == VSB_METRIC_HAMMING) return false;
     return storage == VSB_ST_F32 || storage == VSB_ST_BF16 || storage == VSB_ST_F16;
@@ -622,18 +676,20 @@ uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count, uint32
     // One CTA per SM: the sweep takes ceil(q_tiles * s / SMs) waves of 1/s of the corpus each.  Pick the row-split
     // count s that minimises waves / s, i.e. fills the last wave (79 query tiles x 1 split would leave 69 of 148 SMs
     // idle; x 13 splits = 1027 CTAs = 6.94 waves) — weighed against the list work it adds: every list warms up on
-    // its own (~ kp * (1 + ln(rows_per_list / kp)) insertions, each worth ~10 scanned rows of epilogue time) and K3
+    // its own (~ kp * (1 + ln(rows_per_list / kp)) insertions, each worth ~200 scanned elements of epilogue time —
+    // calibrated on 10 000 x 1 M x 768: 19.7 ms at weight 10, 15.6 ms at 100..300, 19.4 ms at 1000) and K3
     // merges them all.  Short lists over many rows (exact search) split freely; the build's all-pairs lists
     // (k' = 96 over 131 072 rows) stay at one split.  kp = 0: tile-min mode, no lists.  CTAs of one wave walk the
     // same row split in step, so the corpus stream stays L2-resident however many splits there are.
-    const uint32_t q_tiles = (nq + TC_M - 1) / TC_M;
+    uint32_t q_tiles = (nq + TC_M - 1) / TC_M;
+    if (kp != 0 && tc_use_cta_pairs()) q_tiles = (q_tiles + 1) & ~1u;  // CTA pairs: an odd tail tile gets a partner
     const uint32_t min_tiles = kp == 0 ? 2 : 8;
     uint32_t max_by_rows = n_rows / (min_tiles * TC_N);
     if (max_by_rows < 1) max_by_rows = 1;
     const uint32_t s_max = max_by_rows < 64 ? max_by_rows : 64;
     static const double insert_cost = [] {
         const char* e = getenv("VSB_TC_SPLIT_PENALTY");
-        return e ? atof(e) : 10.0;
+        return e ? atof(e) : 200.0;
     }();
     uint32_t best = 1;
     double best_cost = 1e30;
@@ -657,11 +713,7 @@ uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count, uint32
 bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream, bool tile_min) {
     if (p.q.n == 0 || p.x_hi <= p.x_lo) return true;
     const int kind = p.storage == VSB_ST_F32 ? KIND_TF32 : (p.storage == VSB_ST_BF16 ? KIND_BF16 : KIND_F16);
-    static const bool cta2_env = [] {
-        const char* e = getenv("VSB_TC_2CTA");
-        return e != nullptr && e[0] == '1';
-    }();
-    const bool cta2 = cta2_env && !tile_min;
+    const bool cta2 = tc_use_cta_pairs() && !tile_min;
     CUtensorMap mq, mx;
     if (!make_map(&mq, kind, p.q.rows, p.q.n, p.q.row_bytes, TC_M)) return false;
     if (!make_map(&mx, kind, p.x.rows, p.x_hi, p.x.row_bytes, cta2 ? TC_N / 2 : TC_N)) return false;
