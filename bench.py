@@ -666,7 +666,9 @@ def main():
         "dtype": a.storage, "data": "synthetic",
         "config": {"workload": workload_name(a), "step": f"{R} query batches of {B}",
                    "index": "M=16 (degree 32) ef_add=128; build = exact all-pairs kNN on a 131072-row prefix (tcgen05) + "
-                            "K7 streaming insert (detour-pruned links) + one K4/K6 refinement pass",
+                            "K7 streaming insert (detour-pruned links)" +
+                            (f" + {bs['refine_rows'] // max(bs['rows'], 1)} K4/K6 refinement pass(es)" if bs["refine_rows"] else
+                             "; no refinement pass (VSB_REFINE_PASSES=0)"),
                    "traversal": trav_txt, "expansion_search": ef_used, "search_width": sw_used,
                    "max_iterations": max_iters_used, "recall_at_10": round(recall_timed, 4),
                    "operating_points": [{kk: c[kk] for kk in ("ef", "max_iterations", "search_width", "ms_per_batch")} for c in cands],

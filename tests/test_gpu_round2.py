@@ -108,6 +108,40 @@ def test_c3_slice_exact_topk_vs_oracle_and_ann_recall():
     idx.close()
 
 
+def test_c4_slice_exact_topk_vs_oracle_and_ann_recall():
+    """BASELINE configs[3] (1B x 128 bf16 dot-product, degree-64 graph, 125M rows per GPU) on a 4M-row slice of one
+    shard: 32 queries' exact top-10 bit-equal to the oracle (bf16 storage, IP metric, tensor-core candidate stage),
+    the graph really has degree 64, and ANN recall >= 0.95.  tools/c4_billion.py runs the full per-GPU size."""
+    n, dim, k, nq = 4_000_000, 128, 10, 32
+    clusters = 1024
+    x = chunked_corpus(n, dim, clusters)
+    q = embedding_like(2000, dim, seed=4321, n_clusters=clusters)
+    keys = np.arange(n, dtype=np.uint64)
+    v = V()
+    idx = v.GpuIndex(dim, v.Metric.IP, v.Scalar.BF16, connectivity=32)
+    idx.reserve(n)
+    for c0 in range(0, n, 500_000):
+        idx.add_batch(keys[c0:c0 + 500_000], x[c0:c0 + 500_000])
+    gk, gd, gc = idx.search_batch(q[:nq], k, exact=True)
+    ok, od, oc, _ = O.exact_topk(x, q[:nq], k, O.IP, O.BF16, keys=keys)
+    assert_bit_equal(gk, gd, gc, ok, od, oc)
+    del x
+    idx.build()
+    st = idx.stats()
+    assert st["graph_degree"] == 64 and st["n_graphed"] == n and st["row_bytes"] == 256
+    tk, _, _ = idx.search_batch(q, k, exact=True)
+    recall = 0.0
+    for ef in (64, 96, 128, 192, 256):
+        idx.set_search_params(expansion_search=ef, search_width=2)
+        ak, _, ac = idx.search_batch(q, k)
+        recall = O.recall_at_k(ak, tk)
+        if recall >= 0.95:
+            break
+    print(f"C4 slice 4M x 128 bf16 IP degree 64: exact bit-equal on {nq} queries; ANN recall@10 = {recall:.4f} at ef={ef}")
+    assert recall >= 0.95 and np.all(ac == k)
+    idx.close()
+
+
 # ---- mutation semantics --------------------------------------------------------------------------------------------
 def test_churn_without_build_reuses_slots():
     """an update stream (remove + add, live size flat) must never run out of slots.  Capacity is

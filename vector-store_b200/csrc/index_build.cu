@@ -237,8 +237,12 @@ vsb_status vsb_index::sample_seeds(uint32_t n, bool ensure_reach) {
     if (n % 32) live_below -= 32 - (n % 32);
     // S = 4 * sqrt(live rows), in whole 256-row tensor-core tiles, at most 8192: the seed GEMM costs Q * S * D flop per
     // batch whatever the shard size, so a shard of n/G rows gets a sample (and a seed-layer time) ~1/sqrt(G) as large
+    // The cap keeps the seed GEMM at the cost of 8192 rows of 768 dimensions: short rows get proportionally more
+    // entry points (C4's 125 M x 128 shards: 4 * sqrt(n) = 44 800 seeds — with 8192 most of its 64 000 clusters had no
+    // entry point and recall@10 stalled at 0.946 for ef = 512).
     const double target = 4.0 * std::sqrt((double)live_below);
-    uint32_t S = std::min<uint32_t>(8192, std::max<uint32_t>(256, round_up((uint32_t)std::ceil(target), 256)));
+    const uint32_t seed_cap = std::min<uint32_t>(65536, 8192u * std::max<uint32_t>(1, 768u / std::max<uint32_t>(dim, 1)));
+    uint32_t S = std::min<uint32_t>(seed_cap, std::max<uint32_t>(256, round_up((uint32_t)std::ceil(target), 256)));
     if (S > live_below / 4) S = (uint32_t)std::max<uint64_t>(32, live_below / 4);
     std::vector<uint32_t> h_seeds;
     h_seeds.reserve(S);
@@ -331,6 +335,7 @@ vsb_status vsb_index::sample_seeds(uint32_t n, bool ensure_reach) {
     }
     CU(cudaStreamSynchronize(mstream));
     sd->n = S;
+    sd->sampled_rows = n;
     w.sd = sd;
     bstats.seeds_ns += t.stop();
     nvtxRangePop();
@@ -369,6 +374,9 @@ vsb_status vsb_index::stream_insert() {
     CU(cand.alloc((size_t)QB * C * 8));
     EvTimer t(mstream);
     while (w.n_graphed < w.n_slots) {
+        // the entry points follow the graph: a sample drawn when the graph was half its size (at the start of a bulk
+        // build: from the all-pairs prefix only) leaves the newer regions without a nearby seed
+        if (w.sd && w.n_graphed >= 2 * std::max<uint32_t>(w.sd->sampled_rows, 1024)) ST(sample_seeds(w.n_graphed, false));
         const uint32_t t0 = w.n_graphed;
         const uint32_t nb = std::min(QB, w.n_slots - t0);
         vsb::RowsView qv;

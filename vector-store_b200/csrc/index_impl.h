@@ -25,6 +25,7 @@
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <memory>
@@ -63,6 +64,17 @@ vsb_status fail(vsb_status st, const char* fmt, ...);
 // un-synchronised kernels may still read drains the device first.  `plain` buffers (cudaMalloc) are for memory that
 // other devices or processes map: the router's gather buffers and the IPC exchange.
 cudaStream_t pool_stream(int device);  // index.cu
+
+// Experiment knob (VSB_PLAIN_ALLOC_MB): buffers of at least this many MB come from cudaMalloc instead of the pool
+// (page size / TLB reach of a 15 GB row store).  0 = never (default).
+inline size_t big_alloc_threshold() {
+    static const size_t t = [] {
+        const char* e = getenv("VSB_PLAIN_ALLOC_MB");
+        const size_t mb = e ? (size_t)strtoull(e, nullptr, 10) : 0;
+        return mb ? mb << 20 : ~(size_t)0;
+    }();
+    return t;
+}
 
 struct DevBuf {
     void* p = nullptr;
@@ -106,7 +118,7 @@ struct DevBuf {
         release();
         const size_t sz = want ? want : 16;
         cudaGetDevice(&dev);
-        plain = plain_memory;
+        plain = plain_memory || sz >= big_alloc_threshold();
         cudaError_t e;
         if (plain) {
             e = cudaMalloc(&p, sz);
@@ -227,6 +239,7 @@ struct Seeds {
     DevBuf rows, sq, nrm, slots;
     DevBuf rows16, sq16, nrm16;  // bf16 shadow of the seed block (f32 storage only)
     uint32_t n = 0, extra = 0;
+    uint32_t sampled_rows = 0;  // rows the sample was drawn from (the streaming insert re-samples when the graph has doubled)
     size_t bytes() const { return rows.bytes + sq.bytes + nrm.bytes + slots.bytes + rows16.bytes + sq16.bytes + nrm16.bytes; }
 };
 
