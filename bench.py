@@ -67,6 +67,7 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--cpu-queries", type=int, default=2_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--refine", action="store_true", help="VSB_FLAG_BUILD_REFINE: vsb_build ends with one refinement pass")
     a = ap.parse_args()
     cfg = CONFIGS[a.config]
     if a.n is None:
@@ -314,7 +315,8 @@ def main():
         del tmp, hx
 
     # ---- corpus shard: generated in HBM chunk by chunk and ingested from there ----
-    idx = v.GpuIndex(dim, v.Metric.Cos, scalar, device=local_rank, bf16_traversal=trav16, i8_traversal=trav8)
+    idx = v.GpuIndex(dim, v.Metric.Cos, scalar, device=local_rank, bf16_traversal=trav16, i8_traversal=trav8,
+                     build_refine=a.refine)
     idx.reserve(n_local)
     CH = 500_000
     gbuf = torch.empty((min(CH, n_local), dim), dtype=torch.float32, device=dev)

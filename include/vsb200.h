@@ -86,6 +86,11 @@ typedef struct {
  * so returned distances are still the canonical fp32 ones.  Implies VSB_FLAG_BF16_TRAVERSAL (the bf16 copy
  * keeps serving the build and the seed tiles); +25 % HBM for the rows on top of it. */
 #define VSB_FLAG_I8_TRAVERSAL 2u
+/* vsb_build ends with one refinement pass: every row searches the finished graph for its own nearest rows (K4, beam =
+ * expansion_add) and the lists go through the pruning pipeline again.  The streamed (K7) graph needs a ~15 % wider
+ * beam for the same recall (1 M x 768: ef 224 instead of 192, 10 % fewer QPS; 10 M x 768 bf16: 2-4 %); the pass
+ * costs 1.7-1.9x the rest of the build.  Off by default; VSB_REFINE_PASSES overrides. */
+#define VSB_FLAG_BUILD_REFINE 4u
 
 /* Runtime tunables of the graph search (all 0 = keep current). */
 typedef struct {
@@ -265,6 +270,26 @@ vsb_status vsb_batcher_stats(vsb_batcher* batcher, uint64_t* n_queries, uint64_t
  * far is searchable. */
 vsb_status vsb_batcher_add(vsb_batcher* batcher, uint64_t key, const float* row);
 vsb_status vsb_batcher_flush(vsb_batcher* batcher, uint64_t* n_added, uint64_t* n_failed);
+
+/* ---- A13: the actor's partition state (vs_index/usearch.rs:626-895) as an object: a map PartitionId -> index with the
+ * reference's lazy creation, capacity growth (+1 000 000 slots for a global index, +1 000 for a local one, whenever
+ * fewer than free_threshold + n slots are free; usearch.rs:442-443, 655-665), per-IndexId live counters (Count),
+ * empty answers for unknown partitions and the FilteredAnn -> Ann downgrade (allow_bitmap == NULL).
+ * PartitionId = IndexId << 48 | partition number, bit 63 = global index (table/partition_id.rs:11-44).
+ * free_threshold 0 = 64 (the reference uses its channel depth, 3 x workers). */
+typedef struct vsb_set vsb_set;
+vsb_status vsb_set_create(const vsb_options* options, uint32_t free_threshold, vsb_set** out);
+void vsb_set_destroy(vsb_set* set);
+vsb_status vsb_set_add(vsb_set* set, uint64_t partition_id, const uint64_t* keys, const float* rows, uint64_t n,
+                       uint64_t* n_added);
+vsb_status vsb_set_remove(vsb_set* set, uint64_t partition_id, const uint64_t* keys, uint64_t n, uint64_t* n_removed);
+vsb_status vsb_set_remove_partition(vsb_set* set, uint64_t partition_id);
+vsb_status vsb_set_search(vsb_set* set, uint64_t partition_id, const float* queries, uint64_t q, uint32_t k,
+                          const uint32_t* allow_bitmap, uint64_t bitmap_bits, uint64_t* keys, float* distances,
+                          uint32_t* counts);
+uint64_t vsb_set_count(const vsb_set* set, uint16_t index_id);
+uint64_t vsb_set_partitions(const vsb_set* set);
+vsb_index* vsb_set_index(vsb_set* set, uint64_t partition_id);
 
 /* ---- multi-process sharding (one rank per GPU, e.g. under torchrun): exchange of the per-shard top-k over
  * NVLink peer memory instead of an NCCL all-gather.  Every rank creates an exchange on its device, the ranks

@@ -16,6 +16,10 @@ pub struct vsb_batcher {
     _private: [u8; 0],
 }
 #[repr(C)]
+pub struct vsb_set {
+    _private: [u8; 0],
+}
+#[repr(C)]
 pub struct vsb_xchg {
     _private: [u8; 0],
 }
@@ -46,6 +50,8 @@ pub const VSB_FLAG_NONE: u32 = 0;
 pub const VSB_FLAG_BF16_TRAVERSAL: u32 = 1;
 /// f32 storage + cosine: the graph walk reads a scaled-int8 copy, fp32 re-rank
 pub const VSB_FLAG_I8_TRAVERSAL: u32 = 2;
+/// vsb_build ends with one refinement pass (better graph, 1.7-1.9x the build time)
+pub const VSB_FLAG_BUILD_REFINE: u32 = 4;
 
 pub const VSB_XCHG_HANDLE_BYTES: usize = 64;
 
@@ -236,6 +242,39 @@ unsafe extern "C" {
     pub fn vsb_batcher_stats(batcher: *mut vsb_batcher, n_queries: *mut u64, n_batches: *mut u64) -> vsb_status;
     pub fn vsb_batcher_add(batcher: *mut vsb_batcher, key: u64, row: *const f32) -> vsb_status;
     pub fn vsb_batcher_flush(batcher: *mut vsb_batcher, n_added: *mut u64, n_failed: *mut u64) -> vsb_status;
+    pub fn vsb_set_create(options: *const vsb_options, free_threshold: u32, out: *mut *mut vsb_set) -> vsb_status;
+    pub fn vsb_set_destroy(set: *mut vsb_set);
+    pub fn vsb_set_add(
+        set: *mut vsb_set,
+        partition_id: u64,
+        keys: *const u64,
+        rows: *const f32,
+        n: u64,
+        n_added: *mut u64,
+    ) -> vsb_status;
+    pub fn vsb_set_remove(
+        set: *mut vsb_set,
+        partition_id: u64,
+        keys: *const u64,
+        n: u64,
+        n_removed: *mut u64,
+    ) -> vsb_status;
+    pub fn vsb_set_remove_partition(set: *mut vsb_set, partition_id: u64) -> vsb_status;
+    pub fn vsb_set_search(
+        set: *mut vsb_set,
+        partition_id: u64,
+        queries: *const f32,
+        q: u64,
+        k: u32,
+        allow_bitmap: *const u32,
+        bitmap_bits: u64,
+        keys: *mut u64,
+        distances: *mut f32,
+        counts: *mut u32,
+    ) -> vsb_status;
+    pub fn vsb_set_count(set: *const vsb_set, index_id: u16) -> u64;
+    pub fn vsb_set_partitions(set: *const vsb_set) -> u64;
+    pub fn vsb_set_index(set: *mut vsb_set, partition_id: u64) -> *mut vsb_index;
     pub fn vsb_xchg_create(
         device: i32,
         world: u32,

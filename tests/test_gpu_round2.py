@@ -67,11 +67,11 @@ def test_c2_full_size_exact_topk_vs_oracle():
     assert np.array_equal(bk[sel], ok) and np.array_equal(bd[sel].view(np.uint32), od.view(np.uint32))
     # ANN at the bench's operating point reaches the target against that oracle ground truth
     idx.build()
-    idx.set_search_params(expansion_search=160, search_width=2)
+    idx.set_search_params(expansion_search=224, search_width=2)
     ak, _, _ = idx.search_batch(q, k)
     r = O.recall_at_k(ak, ok)
-    print(f"C2 1M x 768 f32: exact top-10 bit-equal to the oracle on {nq} queries; ANN recall@10 (ef 160) = {r:.4f}")
-    assert r >= 0.93
+    print(f"C2 1M x 768 f32: exact top-10 bit-equal to the oracle on {nq} queries; ANN recall@10 (ef 224) = {r:.4f}")
+    assert r >= 0.93  # 64 queries only; bench.py measures the operating point on 2000 per batch
     idx.close()
 
 
@@ -140,6 +140,57 @@ def test_c4_slice_exact_topk_vs_oracle_and_ann_recall():
     print(f"C4 slice 4M x 128 bf16 IP degree 64: exact bit-equal on {nq} queries; ANN recall@10 = {recall:.4f} at ef={ef}")
     assert recall >= 0.95 and np.all(ac == k)
     idx.close()
+
+
+def test_index_set_mirrors_the_actor_partition_state():
+    """A13 in C++ (vsb_set_*, csrc/index_set.cu) against the reference actor's rules (usearch.rs:626-895): lazy partition
+    creation, +1000 / +1000000 capacity growth, Count per IndexId, empty answer for an unknown partition, remove of
+    unknown keys / partitions is not an error, RemovePartition drops the index, results equal to the oracle."""
+    v = V()
+    rng = np.random.default_rng(3)
+    dim, k = 64, 5
+    s = v.IndexSet(dim, v.Metric.L2sq, v.Scalar.F32, free_threshold=16)
+    local_a, local_b = (7 << 48) | 1, (7 << 48) | 2          # two partitions of local index 7
+    global_p = (0x8003 << 48)                                 # the global partition of index 0x8003
+    xa = rng.standard_normal((300, dim)).astype(np.float32)
+    xb = rng.standard_normal((40, dim)).astype(np.float32)
+    xg = rng.standard_normal((500, dim)).astype(np.float32)
+    q = rng.standard_normal((6, dim)).astype(np.float32)
+    # unknown partition: empty result, no error (usearch.rs:787-806)
+    _, _, c = s.search(local_a, q, k)
+    assert np.all(c == 0) and s.partitions() == 0 and s.count(7) == 0
+    ka = np.arange(300, dtype=np.uint64)
+    assert s.add(local_a, ka[:100], xa[:100]) == 100
+    assert s.capacity(local_a) == 1000                        # RESERVE_INCREMENT_LOCAL
+    assert s.add(local_a, ka[100:], xa[100:]) == 200
+    assert s.add(local_b, np.arange(40, dtype=np.uint64), xb) == 40
+    assert s.add(global_p, np.arange(500, dtype=np.uint64), xg) == 500
+    assert s.capacity(global_p) == 1_000_000                  # RESERVE_INCREMENT_GLOBAL
+    assert s.partitions() == 3 and s.count(7) == 340 and s.count(0x8003) == 500 and s.count(9) == 0
+    # a duplicate key fails alone (usearch multi=false, add errors are swallowed by the actor)
+    assert s.add(local_a, np.array([5, 1000], np.uint64), xa[:2]) == 1 and s.count(7) == 341
+    gk, gd, gc = s.search(local_a, q, k)
+    xa2 = np.concatenate([xa, xa[1:2]])
+    ok, od, oc, _ = O.exact_topk(xa2, q, k, O.L2SQ, O.F32, keys=np.concatenate([ka, np.array([1000], np.uint64)]))
+    assert_bit_equal(gk, gd, gc, ok, od, oc)                  # 301 rows < min_graph_size: exact path
+    # filtered: only even row ids admissible; None = the FilteredAnn -> Ann downgrade (same as plain search)
+    mask = np.zeros(1001, dtype=bool)
+    mask[::2] = True
+    fk, _, fc = s.search(local_a, q, k, allow_mask=mask)
+    assert np.all(fc == k) and np.all(fk % 2 == 0)
+    # removes: unknown keys / partitions are not errors
+    assert s.remove(local_a, np.array([0, 1, 999_999], np.uint64)) == 2 and s.count(7) == 339
+    assert s.remove((7 << 48) | 55, np.array([1], np.uint64)) == 0
+    gk2, _, _ = s.search(local_a, q, k)
+    assert not np.isin(gk2, [0, 1]).any()
+    s.remove_partition(local_b)
+    _, _, c = s.search(local_b, q, k)
+    assert np.all(c == 0) and s.partitions() == 2
+    # growth: 1000 more rows into the local partition cross the first increment
+    xm = rng.standard_normal((1000, dim)).astype(np.float32)
+    assert s.add(local_a, np.arange(2000, 3000, dtype=np.uint64), xm) == 1000
+    assert s.capacity(local_a) >= 1299 + 16
+    s.close()
 
 
 # ---- mutation semantics --------------------------------------------------------------------------------------------

@@ -196,6 +196,16 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
     return v;
 }
 
+__device__ __forceinline__ uint32_t tmem_ld1_nowait(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(v) : "r"(taddr));
+    return v;
+}
+// the loaded registers are operands of the wait, so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_wait_ld4(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a), "+r"(b), "+r"(c), "+r"(d)::"memory");
+}
+
 // Candidate-stage distance of one (query, corpus row) pair from the tile's dot product.  col = per-column parameter
 // (|x|^2, 1/|x|, 1), qpar = per-query parameter (|q|^2, -1/|q|, unused).  One definition for the hit test and for the
 // value that is stored, so both see the same bits.
@@ -512,28 +522,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     // all-pairs lists, k' = 96 over 131 072 rows).
                     uint32_t any_hit = __reduce_or_sync(kFullMask, hit);
                     while (any_hit != 0) {
-                        const int j = __ffs(any_hit) - 1;
-                        any_hit &= any_hit - 1;
-                        const float dot = __uint_as_float(tmem_ld1(taddr + ch * 32 + j));
-                        if ((hit >> j) & 1u) {
-                            const uint32_t n = n0 + ch * 32 + j;
-                            bool ok = true;
-                            if (deny != nullptr && bit_test(deny, n)) ok = false;
-                            if (ok && allow != nullptr) {
-                                const uint64_t rid = keys[n] & kRowMask48;
-                                ok = rid < allow_bits && bit_test(allow, (uint32_t)rid);
-                            }
-                            if (ok) {
-                                float dd = tc_dist<METRIC>(dot, cp[ch * 32 + j], qpar);
-                                if constexpr (METRIC == VSB_METRIC_L2SQ) dd = fmaxf(dd, 0.0f);
-                                if constexpr (METRIC == VSB_METRIC_COS) dd = fminf(fmaxf(dd, 0.0f), 2.0f);
-                                my_buf[cnt++] = pack_ds(dd, n);
-                            }
+                        // up to four hit columns per round trip to TMEM: four one-column loads, ONE wait
+                        int jj[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            jj[u] = any_hit != 0 ? __ffs(any_hit) - 1 : -1;
+                            any_hit &= any_hit - 1;  // 0 stays 0
                         }
-                        const uint32_t full_rows = __ballot_sync(kFullMask, cnt == TC_BUFCAP);
-                        if (full_rows != 0) {
-                            thr = tc_flush_rows(full_rows, warp_lists, list_stride, a.kp, keys, warp_buf, cnt, thr, lane);
-                            if ((full_rows >> lane) & 1u) cnt = 0;
+                        uint32_t dv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) dv[u] = tmem_ld1_nowait(taddr + ch * 32 + (jj[u] >= 0 ? jj[u] : jj[0]));
+                        tmem_wait_ld4(dv[0], dv[1], dv[2], dv[3]);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (jj[u] < 0) break;  // warp-uniform
+                            const int j = jj[u];
+                            if ((hit >> j) & 1u) {
+                                const uint32_t n = n0 + ch * 32 + j;
+                                bool ok = true;
+                                if (deny != nullptr && bit_test(deny, n)) ok = false;
+                                if (ok && allow != nullptr) {
+                                    const uint64_t rid = keys[n] & kRowMask48;
+                                    ok = rid < allow_bits && bit_test(allow, (uint32_t)rid);
+                                }
+                                if (ok) {
+                                    float dd = tc_dist<METRIC>(__uint_as_float(dv[u]), cp[ch * 32 + j], qpar);
+                                    if constexpr (METRIC == VSB_METRIC_L2SQ) dd = fmaxf(dd, 0.0f);
+                                    if constexpr (METRIC == VSB_METRIC_COS) dd = fminf(fmaxf(dd, 0.0f), 2.0f);
+                                    my_buf[cnt++] = pack_ds(dd, n);
+                                }
+                            }
+                            const uint32_t full_rows = __ballot_sync(kFullMask, cnt == TC_BUFCAP);
+                            if (full_rows != 0) {
+                                thr = tc_flush_rows(full_rows, warp_lists, list_stride, a.kp, keys, warp_buf, cnt, thr, lane);
+                                if ((full_rows >> lane) & 1u) cnt = 0;
+                            }
                         }
                     }
                 }

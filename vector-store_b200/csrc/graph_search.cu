@@ -42,6 +42,15 @@ void launch_seed_scan(int storage, int metric, const RowsView& q, const RowsView
     g_kernel_launches += 1;
 }
 
+// VSB_K4_MMA=0 keeps 16-bit rows on the SIMT evaluation (canonical distances straight from K4)
+bool graph_search_uses_mma(int storage, uint32_t n_queries, bool filtered) {
+    static const bool on = [] {
+        const char* e = getenv("VSB_K4_MMA");
+        return e == nullptr || e[0] != '0';
+    }();
+    return on && !filtered && n_queries > graph_search_small_batch() && (storage == VSB_ST_BF16 || storage == VSB_ST_F16);
+}
+
 void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
     if (p.q.n == 0) return;
     K4Args a;
@@ -72,6 +81,7 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
     a.allow = p.allow;
     a.allow_bits = p.allow_bits;
     a.rk = p.allow != nullptr ? ((p.k + 31) / 32) * 32 : 0;
+    a.mma = 0;
     const int cpl = pick_cpl((int)(p.x.row_bytes / 16));
     // filtered ANN always runs the warp-per-query kernel (the second list lives there)
     if (p.q.n <= graph_search_small_batch() && p.allow == nullptr) {
@@ -92,6 +102,7 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
         return;
     }
     dim3 grid((p.q.n + K4_WARPS - 1) / K4_WARPS);
+    a.mma = (p.mma && p.allow == nullptr && (p.storage == VSB_ST_BF16 || p.storage == VSB_ST_F16)) ? 1u : 0u;
     const size_t smem = (size_t)K4_WARPS * ((size_t)a.itopk * 8 + ((size_t)2 << bits) + (size_t)a.queue_cap * 8 + (size_t)a.rk * 8);
     switch (p.storage) {
         case VSB_ST_F32: launch_k4_f32(a, cpl, grid, smem, stream); break;

@@ -49,6 +49,7 @@ struct K4Args {
     const uint32_t* allow;  // filtered ANN: admissibility bitmap over (key & 2^48-1); only the FILTER instantiation reads it
     uint64_t allow_bits;
     uint32_t rk;            // length of the result list of the FILTER instantiation (k rounded up to 32)
+    uint32_t mma;           // 1: 16-bit rows are evaluated on the tensor cores (mma.sync), distances are candidate-grade
 };
 
 __device__ __forceinline__ bool hash_insert(uint32_t* tab, uint32_t mask, uint32_t bits, uint32_t slot) {
@@ -186,25 +187,86 @@ __device__ __forceinline__ float finish_raw(float raw, int metric, float qn, flo
     }
 }
 
+// ---- tensor-core evaluation of 16-bit rows (warp-per-query kernel) -------------------------------------------------
+// mma.sync.m16n8k16 (bf16 / f16 in, fp32 accumulate).  The unpack of bf16 rows to fp32 was the hottest line of the SIMT
+// evaluation (one shift or mask per element before every FFMA); the tensor core consumes the packed rows as they come
+// out of the 128-bit loads.  A first layout that gave each thread quad 64 contiguous bytes of 16 different rows
+// (natural for the fragments) was measured SLOWER than SIMT once the per-row pieces dropped to 192 bytes per pipeline
+// stage (10.1 vs 9.2 ms): HBM wants long contiguous bursts per row.  group_reduce_mma therefore keeps the SIMT
+// kernel's loads (one warp load = 512 contiguous bytes of one row) and adapts the fragments to them.  The accumulation
+// order is the tensor core's, not the canonical one: results are candidate-grade and the caller re-ranks what it
+// returns (K3).
+template <int ST>
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+    if constexpr (ST == VSB_ST_BF16) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    } else {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+}
+
+// tensor-core form of group_reduce for one group of U rows held in registers (same loads, same double buffering as the
+// SIMT form): rows are taken two at a time, lane l's 16-byte piece of row u fills the fragment slots of MMA row
+// g = l / 4 (piece of row u + 1: MMA row g + 8), lane l's piece of the query fills column g.  D[g][g] is then the
+// partial dot product of the pieces held by quad g (D[g + 8][g] for the second row); the off-diagonal entries pair
+// pieces of different offsets and are ignored.  The diagonal entry of quad g sits in thread t = g / 2, register g % 2.
+template <int ST, int CPL, int U>
+__device__ __forceinline__ void group_reduce_mma(const VecGroup<CPL, U>& grp, const uint4* qc, float* newd, uint32_t base,
+                                                 uint32_t stride, uint32_t n_new, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const bool diag = t == (g >> 1);
+    const bool odd = (g & 1) != 0;
+#pragma unroll
+    for (int u = 0; u < U; u += 2) {
+        constexpr bool kPair = U > 1;
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            const uint4 xa = grp.x[u][j];
+            const uint4 xb = kPair ? grp.x[kPair ? u + 1 : u][j] : xa;
+            mma_16816<ST>(c, xa.x, xb.x, xa.y, xb.y, qc[j].x, qc[j].y);
+            mma_16816<ST>(c, xa.z, xb.z, xa.w, xb.w, qc[j].z, qc[j].w);
+        }
+        float v0 = diag ? (odd ? c[1] : c[0]) : 0.0f;
+        float v1 = diag ? (odd ? c[3] : c[2]) : 0.0f;
+        v0 = butterfly_sum(v0);
+        if (kPair) v1 = butterfly_sum(v1);
+        if (lane == 0) {
+            const uint32_t i0 = base + u * stride, i1 = base + (u + 1) * stride;
+            if (i0 < n_new) newd[i0] = v0;
+            if (kPair && i1 < n_new) newd[i1] = v1;
+        }
+    }
+}
+
 // all queue entries of this warp: index(m) = first + m * stride, m < mine.  Double buffered: the loads of
 // group m+1 are in flight while group m is reduced.
-template <int ST, int CPL, int U>
+template <int ST, int CPL, int U, bool MMA = false>
 __device__ __forceinline__ void evaluate_entries(const uint8_t* __restrict__ x_rows, uint32_t row_bytes,
                                                  const uint32_t* newq, float* newd, uint32_t first, uint32_t stride,
                                                  uint32_t mine, uint32_t n_new, const float* qf, const uint4* qc,
                                                  bool is_l2, int lane, int n_chunks, bool full) {
     if (mine == 0) return;
     const uint32_t last = first + (mine - 1) * stride;
+    auto reduce = [&](const VecGroup<CPL, U>& grp, uint32_t base) {
+        if constexpr (MMA) group_reduce_mma<ST, CPL, U>(grp, qc, newd, base, stride, n_new, lane);
+        else group_reduce<ST, CPL, U>(grp, qf, qc, is_l2, newd, base, stride, n_new, lane);
+    };
     VecGroup<CPL, U> ga, gb;
     group_load<CPL, U>(ga, x_rows, row_bytes, newq, first, stride, last, lane, n_chunks, full);
     for (uint32_t m0 = 0; m0 < mine; m0 += 2 * U) {
         const bool has_b = m0 + U < mine;
         if (has_b) group_load<CPL, U>(gb, x_rows, row_bytes, newq, first + (m0 + U) * stride, stride, last, lane, n_chunks, full);
-        group_reduce<ST, CPL, U>(ga, qf, qc, is_l2, newd, first + m0 * stride, stride, n_new, lane);
+        reduce(ga, first + m0 * stride);
         if (has_b) {
             if (m0 + 2 * U < mine)
                 group_load<CPL, U>(ga, x_rows, row_bytes, newq, first + (m0 + 2 * U) * stride, stride, last, lane, n_chunks, full);
-            group_reduce<ST, CPL, U>(gb, qf, qc, is_l2, newd, first + (m0 + U) * stride, stride, n_new, lane);
+            reduce(gb, first + (m0 + U) * stride);
         }
     }
 }
@@ -219,12 +281,14 @@ constexpr int k4_min_blocks() { return (ST == VSB_ST_I8 && CPL <= 2) ? 4 : 3; }
 // FILTER = true (vsb_search_filtered): the traversal is unchanged, but every evaluated row whose key is admissible is
 // ALSO folded into a second list of rk entries, and that list is what the kernel emits.  The beam still walks through
 // inadmissible rows, exactly like usearch's predicate search (usearch.rs:224-248).
-template <int ST, int CPL, bool FILTER>
+// MMA = true (16-bit float storages): the rows of a group are multiplied on the tensor cores (group_reduce_mma) instead
+// of being unpacked and FMA'd lane by lane; the query stays packed in registers; the distances are candidate-grade.
+template <int ST, int CPL, bool FILTER, bool MMA = false>
 __global__ void __launch_bounds__(K4_WARPS * 32, k4_min_blocks<ST, CPL>()) graph_search_kernel(K4Args a) {
     constexpr int E = Storage<ST>::ELEMS;
     constexpr bool kFloat = Storage<ST>::kFloat;
     constexpr int U = CPL <= 3 ? 4 : (CPL <= 6 ? 2 : 1);  // vectors per load group
-    constexpr int QF = kFloat ? CPL * E : 1;
+    constexpr int QF = (kFloat && !MMA) ? CPL * E : 1;
 
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -254,17 +318,18 @@ __global__ void __launch_bounds__(K4_WARPS * 32, k4_min_blocks<ST, CPL>()) graph
     // ---- query into registers ----
     const uint4* qrow = reinterpret_cast<const uint4*>(a.q_rows + (size_t)q * a.q_row_bytes);
     float qf[QF];
-    uint4 qc[kFloat ? 1 : CPL];
+    uint4 qc[(kFloat && !MMA) ? 1 : CPL];  // integer storages and the tensor-core form keep the query packed
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
         const int c = j * 32 + lane;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (c < n_chunks) v = qrow[c];
-        if constexpr (kFloat)
+        if constexpr (kFloat && !MMA)
             Storage<ST>::unpack(v, &qf[j * E]);
         else
             qc[j] = v;
     }
+    if constexpr (MMA) qf[0] = 0.0f;
     const float qn = a.q_nrm[q];
     __syncwarp();
 
@@ -286,16 +351,32 @@ __global__ void __launch_bounds__(K4_WARPS * 32, k4_min_blocks<ST, CPL>()) graph
         __syncwarp();
         if (n_new == 0) return;
         n_evals += n_new;
-        evaluate_entries<ST, CPL, U>(a.x_rows, a.x_row_bytes, newq, newd, 0, 1, n_new, n_new, qf, qc, is_l2, lane,
-                                     n_chunks, full);
+        // MMA: the candidates' norms are a dependent gather that would otherwise start only after the rows have been
+        // multiplied, with nothing else of this warp in flight — fetch the first 64 before the rows
+        float xn_pre[2] = {0.0f, 0.0f};
+        if constexpr (MMA) {
+            if (is_cos || is_l2) {
+                if (lane < n_new) xn_pre[0] = __ldg(a.x_nrm + newq[lane]);
+                if (32 + lane < n_new) xn_pre[1] = __ldg(a.x_nrm + newq[32 + lane]);
+            }
+        }
+        evaluate_entries<ST, CPL, U, MMA>(a.x_rows, a.x_row_bytes, newq, newd, 0, 1, n_new, n_new, qf, qc, is_l2, lane,
+                                          n_chunks, full);
         __syncwarp();
         const uint64_t worst = list[a.itopk - 1];
         for (uint32_t base = 0; base < n_new; base += 32) {
             uint64_t res = kInvalidPacked;
             if (base + lane < n_new) {
                 const uint32_t slot = newq[base + lane];
-                const float xn = is_cos ? __ldg(a.x_nrm + slot) : 0.0f;
-                res = pack_ds(finish_raw<ST>(newd[base + lane], a.metric, qn, xn), slot);
+                float xn = 0.0f;
+                if (MMA && base < 64) xn = base == 0 ? xn_pre[0] : xn_pre[1];
+                else if (is_cos || (MMA && is_l2)) xn = __ldg(a.x_nrm + slot);
+                float raw = newd[base + lane];
+                if constexpr (MMA) {
+                    // the tensor-core sum is the dot product; squared L2 from the norms (candidate-grade like the rest)
+                    if (is_l2) raw = fmaxf(fmaf(-2.0f, raw, fmaf(qn, qn, xn * xn)), 0.0f);
+                }
+                res = pack_ds(finish_raw<ST>(raw, a.metric, qn, xn), slot);
             }
             if constexpr (FILTER) {
                 uint64_t adm = kInvalidPacked;
@@ -790,6 +871,13 @@ void launch_k4_inst(const K4Args& a, dim3 grid, size_t smem, cudaStream_t stream
         cudaFuncSetAttribute(graph_search_kernel<ST, CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         graph_search_kernel<ST, CPL, true><<<grid, K4_WARPS * 32, smem, stream>>>(a);
         return;
+    }
+    if constexpr (ST == VSB_ST_BF16 || ST == VSB_ST_F16) {
+        if (a.mma) {
+            cudaFuncSetAttribute(graph_search_kernel<ST, CPL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            graph_search_kernel<ST, CPL, false, true><<<grid, K4_WARPS * 32, smem, stream>>>(a);
+            return;
+        }
     }
     cudaFuncSetAttribute(graph_search_kernel<ST, CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     graph_search_kernel<ST, CPL, false><<<grid, K4_WARPS * 32, smem, stream>>>(a);

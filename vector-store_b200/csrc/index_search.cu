@@ -195,7 +195,13 @@ vsb_status vsb_index::graph_block(const View& v, Scratch& sc, const GraphRun& ru
     const uint32_t* deny_bm = v.any_tombstone ? st.deny.as<uint32_t>() : nullptr;
     // the traversal copies serve searches; `native` (a runtime override, searches only) walks the stored rows instead
     const bool t16 = trav16 && !(run.native && packed_out == nullptr);
-    const bool rerank = t16 && packed_out == nullptr;
+    // 16-bit float rows (stored, or the bf16 traversal copy) in a large batch are evaluated on the tensor cores: the
+    // distances K4 ranks by are then candidate-grade and the rows a SEARCH returns are re-ranked by K3 in the canonical
+    // order, exactly like the results of the bf16 / int8 traversal copies (the build only needs the ranking)
+    const int trav_storage = t16 ? (int)VSB_BF16 : storage;
+    const bool use8_early = trav8 && t16 && packed_out == nullptr;
+    const bool mma = !use8_early && vsb::graph_search_uses_mma(trav_storage, nb, run.allow != nullptr);
+    const bool rerank = (t16 || mma) && packed_out == nullptr;
     // ---- bf16 shadow of the queries (f32 storage: tensor-core seed layer and/or bf16 traversal) ----
     bool seed_tc = tc_enabled && vsb::exact_tc_supported(storage, metric) && nb >= 16;
     vsb::RowsView q16v;
@@ -316,6 +322,7 @@ vsb_status vsb_index::graph_block(const View& v, Scratch& sc, const GraphRun& ru
     gp.self_base = self_base;
     gp.allow = run.allow;
     gp.allow_bits = run.allow_bits;
+    gp.mma = mma;
     uint32_t kr = 0;
     if (packed_out != nullptr) {
         gp.out_packed = packed_out;

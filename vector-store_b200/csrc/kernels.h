@@ -135,7 +135,11 @@ struct SearchParams {
     // result list (a second list next to the traversal list)
     const uint32_t* allow = nullptr;
     uint64_t allow_bits = 0;
+    // 16-bit float rows, warp-per-query kernel only: evaluate the rows on the tensor cores (mma.sync, candidate-grade
+    // distances — the caller re-ranks the rows it returns).  graph_search_uses_mma() tells which launches honour it.
+    bool mma = false;
 };
+bool graph_search_uses_mma(int storage, uint32_t n_queries, bool filtered);
 void launch_graph_search(const SearchParams& p, cudaStream_t stream);
 bool graph_search_supported(uint32_t row_bytes);  // rows up to 6144 bytes
 uint32_t graph_search_small_batch();

@@ -38,10 +38,12 @@ def _ptr(a):
 class GpuIndex:
     def __init__(self, dimensions: int, metric: Metric = Metric.Cos, storage: Scalar = Scalar.F32,
                  connectivity: int = 0, expansion_add: int = 0, expansion_search: int = 0, device: int = -1,
-                 seed: int = 0, bf16_traversal: bool = False, i8_traversal: bool = False, devices=None):
+                 seed: int = 0, bf16_traversal: bool = False, i8_traversal: bool = False, devices=None,
+                 build_refine: bool = False):
         """devices: list of 2..8 CUDA ordinals -> ONE handle over one shard per device (vsb_options.n_devices)."""
         self._lib = lib()
-        flags = (1 if bf16_traversal else 0) | (2 if i8_traversal else 0)  # VSB_FLAG_BF16_TRAVERSAL | VSB_FLAG_I8_TRAVERSAL
+        # VSB_FLAG_BF16_TRAVERSAL | VSB_FLAG_I8_TRAVERSAL | VSB_FLAG_BUILD_REFINE
+        flags = (1 if bf16_traversal else 0) | (2 if i8_traversal else 0) | (4 if build_refine else 0)
         devs = list(devices) if devices else []
         opt = VsbOptions(dimensions, int(metric), int(storage), connectivity, expansion_add, expansion_search,
                          device, flags, seed, len(devs), (C.c_int32 * 8)(*(devs + [0] * (8 - len(devs)))))
@@ -309,6 +311,76 @@ def merge_topk_strided_dev(d_keys: int, d_dists: int, parts: int, key_part_strid
                            stream: int) -> None:
     check(lib().vsb_merge_topk_strided_dev(d_keys, d_dists, parts, key_part_stride, dist_part_stride, q, k, d_out_keys,
                                            d_out_dists, d_out_counts or None, device, stream or None))
+
+
+class IndexSet:
+    """A13: the actor's partition map as the library keeps it (vsb_set_*, csrc/index_set.cu): lazily created
+    per-partition indexes, the reference's capacity growth, per-IndexId counters, empty answers for unknown partitions.
+    partition_id = index_id << 48 | partition number; bit 63 set = global index (table/partition_id.rs:11-44)."""
+
+    def __init__(self, dimensions: int, metric: Metric = Metric.Cos, storage: Scalar = Scalar.F32, connectivity: int = 0,
+                 expansion_add: int = 0, expansion_search: int = 0, device: int = -1, bf16_traversal: bool = False,
+                 free_threshold: int = 0):
+        self._lib = lib()
+        opt = VsbOptions(dimensions, int(metric), int(storage), connectivity, expansion_add, expansion_search, device,
+                         1 if bf16_traversal else 0, 0, 0, (C.c_int32 * 8)(*([0] * 8)))
+        h = C.c_void_p()
+        check(self._lib.vsb_set_create(C.byref(opt), free_threshold, C.byref(h)))
+        self._h = h
+        self.dimensions = dimensions
+
+    def add(self, partition_id: int, keys, rows) -> int:
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        r = np.ascontiguousarray(rows, dtype=np.float32).reshape(len(k), self.dimensions)
+        added = C.c_uint64(0)
+        check(self._lib.vsb_set_add(self._h, partition_id, _ptr(k), _ptr(r), len(k), C.byref(added)))
+        return int(added.value)
+
+    def remove(self, partition_id: int, keys) -> int:
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        removed = C.c_uint64(0)
+        check(self._lib.vsb_set_remove(self._h, partition_id, _ptr(k), len(k), C.byref(removed)))
+        return int(removed.value)
+
+    def remove_partition(self, partition_id: int) -> None:
+        check(self._lib.vsb_set_remove_partition(self._h, partition_id))
+
+    def search(self, partition_id: int, queries, k: int, allow_mask=None):
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dimensions)
+        n = q.shape[0]
+        keys = np.empty((n, k), dtype=np.uint64)
+        dists = np.empty((n, k), dtype=np.float32)
+        counts = np.empty(n, dtype=np.uint32)
+        bm, bits = None, 0
+        if allow_mask is not None:
+            mask = np.asarray(allow_mask, dtype=bool)
+            bm = np.packbits(mask, bitorder="little")
+            bm = np.concatenate([bm, np.zeros((-len(bm)) % 4, np.uint8)]).view(np.uint32)
+            bits = len(mask)
+        check(self._lib.vsb_set_search(self._h, partition_id, _ptr(q), n, k, _ptr(bm), bits, _ptr(keys), _ptr(dists),
+                                       _ptr(counts)))
+        return keys, dists, counts
+
+    def count(self, index_id: int) -> int:
+        return int(self._lib.vsb_set_count(self._h, index_id))
+
+    def partitions(self) -> int:
+        return int(self._lib.vsb_set_partitions(self._h))
+
+    def capacity(self, partition_id: int) -> int:
+        h = self._lib.vsb_set_index(self._h, partition_id)
+        return int(self._lib.vsb_capacity(h)) if h else 0
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.vsb_set_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Exchange:

@@ -83,6 +83,15 @@ SYMBOLS = [
     ("vsb_batcher_stats", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("vsb_batcher_add", C.c_int, [_P, C.c_uint64, _P]),
     ("vsb_batcher_flush", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("vsb_set_create", C.c_int, [C.POINTER(VsbOptions), C.c_uint32, C.POINTER(_P)]),
+    ("vsb_set_destroy", None, [_P]),
+    ("vsb_set_add", C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    ("vsb_set_remove", C.c_int, [_P, C.c_uint64, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    ("vsb_set_remove_partition", C.c_int, [_P, C.c_uint64]),
+    ("vsb_set_search", C.c_int, [_P, C.c_uint64, _P, C.c_uint64, C.c_uint32, _P, C.c_uint64, _P, _P, _P]),
+    ("vsb_set_count", C.c_uint64, [_P, C.c_uint16]),
+    ("vsb_set_partitions", C.c_uint64, [_P]),
+    ("vsb_set_index", _P, [_P, C.c_uint64]),
     ("vsb_xchg_create", C.c_int, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(_P)]),
     ("vsb_xchg_allgather_bytes", C.c_int, [_P, _P, C.c_uint64, C.POINTER(_P), _P, _P]),
     ("vsb_xchg_destroy", None, [_P]),
