@@ -148,17 +148,32 @@ def main():
         ef_used = ef
         if r >= a.target_recall + 0.003:
             break
+    # parents per iteration: the fastest of 2 / 4 / 8 at this beam that still reaches the target
+    def timed(n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            search(q_dev[i % NB].data_ptr())
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    widths, sw_used, best_ms = [], 2, None
+    for sw in (2, 4, 8):
+        idx.set_search_params(expansion_search=ef_used, search_width=sw, max_iterations=10 ** 6)
+        search(q_dev[0].data_ptr())
+        torch.cuda.synchronize()
+        r = recall_of(0)
+        t = timed(4) / 4
+        widths.append({"search_width": sw, "recall_at_10": round(r, 4), "ms_per_batch": round(t, 3)})
+        if r >= a.target_recall + 0.003 and (best_ms is None or t < best_ms):
+            best_ms, sw_used = t, sw
+    idx.set_search_params(expansion_search=ef_used, search_width=sw_used, max_iterations=10 ** 6)
     # timed: batches resident in HBM, device clock, max over ranks
     for i in range(3):
         search(q_dev[i % NB].data_ptr())
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(a.batches):
-        search(q_dev[i % NB].data_ptr())
-    e1.record()
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms = timed(a.batches)
     search(q_dev[1].data_ptr())
     torch.cuda.synchronize()
     recall_b1 = recall_of(1)
@@ -193,7 +208,7 @@ def main():
             "build_phase_s_rank0": {kk: round(bs[kk] / 1e9, 3) for kk in bs if kk.endswith("_ns")},
             "stream_evals_per_row": bs["stream_evals"] / max(bs["stream_rows"], 1),
             "ground_truth_s": round(t_gt, 2),
-            "expansion_search": ef_used, "ef_sweep": sweep,
+            "expansion_search": ef_used, "ef_sweep": sweep, "search_width": sw_used, "search_width_sweep": widths,
             "recall_at_10": round(recall_b1, 4),
             "qps": a.batches * B / (ms / 1e3), "ms_per_batch": ms / a.batches,
             "distance_evals_per_query_per_shard": E, "parent_expansions_per_query_per_shard": P,

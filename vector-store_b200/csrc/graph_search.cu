@@ -61,7 +61,7 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
     a.seed_slots = p.seed_slots; a.deny = p.deny; a.keys = p.keys;
     a.itopk = ((p.itopk + 31) / 32) * 32;
     if (a.itopk < ((p.k + 31) / 32) * 32) a.itopk = ((p.k + 31) / 32) * 32;
-    a.search_width = p.search_width < 1 ? 1 : (p.search_width > 4 ? 4 : p.search_width);
+    a.search_width = p.search_width < 1 ? 1 : (p.search_width > (uint32_t)K4_MAX_WIDTH ? (uint32_t)K4_MAX_WIDTH : p.search_width);
     a.max_iters = p.max_iters ? p.max_iters : (2 * a.itopk) / a.search_width + 8;
     a.k = p.k;
     // Visited hash: 16 KB per warp (4096 slots) = 3 CTAs x 4 query warps per SM, the same residency the
@@ -82,6 +82,11 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
     a.allow_bits = p.allow_bits;
     a.rk = p.allow != nullptr ? ((p.k + 31) / 32) * 32 : 0;
     a.mma = 0;
+    static const uint32_t compact_env = [] {
+        const char* e = getenv("VSB_K4_COMPACT");
+        return e ? (uint32_t)atoi(e) : 1u;
+    }();
+    a.compact = compact_env;
     const int cpl = pick_cpl((int)(p.x.row_bytes / 16));
     // filtered ANN always runs the warp-per-query kernel (the second list lives there)
     if (p.q.n <= graph_search_small_batch() && p.allow == nullptr) {
@@ -103,7 +108,7 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
     }
     dim3 grid((p.q.n + K4_WARPS - 1) / K4_WARPS);
     a.mma = (p.mma && p.allow == nullptr && (p.storage == VSB_ST_BF16 || p.storage == VSB_ST_F16)) ? 1u : 0u;
-    const size_t smem = (size_t)K4_WARPS * ((size_t)a.itopk * 8 + ((size_t)2 << bits) + (size_t)a.queue_cap * 8 + (size_t)a.rk * 8);
+    const size_t smem = (size_t)K4_WARPS * ((size_t)a.itopk * 8 + ((size_t)2 << bits) + (size_t)a.queue_cap * 8 + (size_t)a.rk * 8 + 64 * 8);
     switch (p.storage) {
         case VSB_ST_F32: launch_k4_f32(a, cpl, grid, smem, stream); break;
         case VSB_ST_F16: launch_k4_f16(a, cpl, grid, smem, stream); break;

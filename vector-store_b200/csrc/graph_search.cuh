@@ -50,6 +50,7 @@ struct K4Args {
     uint64_t allow_bits;
     uint32_t rk;            // length of the result list of the FILTER instantiation (k rounded up to 32)
     uint32_t mma;           // 1: 16-bit rows are evaluated on the tensor cores (mma.sync), distances are candidate-grade
+    uint32_t compact;       // 1: survivors of an iteration are compacted before the sort + merge
 };
 
 __device__ __forceinline__ bool hash_insert(uint32_t* tab, uint32_t mask, uint32_t bits, uint32_t slot) {
@@ -271,7 +272,7 @@ __device__ __forceinline__ void evaluate_entries(const uint8_t* __restrict__ x_r
     }
 }
 
-constexpr int K4_MAX_WIDTH = 4;  // parents expanded per iteration (search_width)
+constexpr int K4_MAX_WIDTH = 8;  // parents expanded per iteration (search_width)
 
 // resident CTAs per SM the register budget is sized for: short int8 rows (the scaled-int8 traversal copy) need
 // few load registers, and the kernel is bound by the number of rows in flight per SM, not by bytes
@@ -297,12 +298,13 @@ __global__ void __launch_bounds__(K4_WARPS * 32, k4_min_blocks<ST, CPL>()) graph
 
     const uint32_t hsize = 1u << a.hash_bits, hmask = hsize - 1;
     const uint32_t qcap = a.queue_cap;
-    const size_t per_warp = (size_t)a.itopk * 8 + (size_t)hsize * 2 + (size_t)qcap * 8 + (FILTER ? (size_t)a.rk * 8 : 0);
+    const size_t per_warp = (size_t)a.itopk * 8 + (size_t)hsize * 2 + (size_t)qcap * 8 + (FILTER ? (size_t)a.rk * 8 : 0) + 64 * 8;
     uint64_t* list = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warp * per_warp);
     uint16_t* hash = reinterpret_cast<uint16_t*>(list + a.itopk);  // [hsize] 16-bit tags
     uint32_t* newq = reinterpret_cast<uint32_t*>(hash + hsize);   // [qcap] un-visited neighbour slots of this iteration
     float* newd = reinterpret_cast<float*>(newq + qcap);     // [qcap] their raw sums
     uint64_t* rlist = reinterpret_cast<uint64_t*>(newd + qcap);  // [rk] FILTER: best admissible rows seen so far
+    uint64_t* stage = rlist + (FILTER ? a.rk : 0);               // [64] candidates of this iteration that can enter the list
     if constexpr (FILTER) {
         for (uint32_t i = lane; i < a.rk; i += 32) rlist[i] = kInvalidPacked;
     }
@@ -363,7 +365,18 @@ __global__ void __launch_bounds__(K4_WARPS * 32, k4_min_blocks<ST, CPL>()) graph
         evaluate_entries<ST, CPL, U, MMA>(a.x_rows, a.x_row_bytes, newq, newd, 0, 1, n_new, n_new, qf, qc, is_l2, lane,
                                           n_chunks, full);
         __syncwarp();
-        const uint64_t worst = list[a.itopk - 1];
+        // Candidates that cannot enter the list (most of them once the beam has converged) are dropped first and the
+        // survivors of ALL batches of this iteration are compacted into `stage`, so the shuffle sort + list merge — the
+        // longest dependent chain of an iteration — runs once per 32 survivors, not once per 32 candidates.
+        uint64_t worst = list[a.itopk - 1];
+        uint32_t n_stage = 0;
+        auto fold_stage = [&](uint32_t n) {  // sort + merge stage[0, n), n <= 32
+            __syncwarp();
+            uint64_t v = lane < n ? stage[lane] : kInvalidPacked;
+            v = warp_sort32(v, lane, less);
+            warp_list_merge(list, (int)a.itopk, v, lane, less);
+            worst = list[a.itopk - 1];
+        };
         for (uint32_t base = 0; base < n_new; base += 32) {
             uint64_t res = kInvalidPacked;
             if (base + lane < n_new) {
@@ -389,10 +402,26 @@ __global__ void __launch_bounds__(K4_WARPS * 32, k4_min_blocks<ST, CPL>()) graph
                     warp_list_merge(rlist, (int)a.rk, adm, lane, less);
                 }
             }
-            if (__ballot_sync(kFullMask, res < worst) == 0) continue;  // nothing here can enter the list
-            res = warp_sort32(res, lane, less);
-            warp_list_merge(list, (int)a.itopk, res, lane, less);
+            const bool keep = res < worst;
+            const uint32_t km = __ballot_sync(kFullMask, keep);
+            if (km == 0) continue;  // nothing here can enter the list
+            if (!a.compact) {       // A/B switch (VSB_K4_COMPACT=0): sort + merge every batch that has a survivor
+                res = warp_sort32(res, lane, less);
+                warp_list_merge(list, (int)a.itopk, res, lane, less);
+                continue;
+            }
+            if (keep) stage[n_stage + __popc(km & ((1u << lane) - 1))] = res;  // < 64 entries
+            n_stage += __popc(km);
+            if (n_stage >= 32) {
+                fold_stage(32);
+                __syncwarp();
+                const uint64_t mv = lane + 32 < n_stage ? stage[32 + lane] : kInvalidPacked;
+                __syncwarp();
+                if (lane + 32 < n_stage) stage[lane] = mv;
+                n_stage -= 32;
+            }
         }
+        if (n_stage != 0) fold_stage(n_stage);
         n_new = 0;
     };
 
