@@ -518,8 +518,8 @@ def main():
         for ent in tr if isinstance(tr, list) else [tr]:
             if all(ent.get(k_) == v_ for k_, v_ in (("n", a.n), ("n_gpus", world), ("dim", dim), ("storage", a.storage),
                                                       ("traversal", a.traversal), ("batch", B), ("k", k),
-                                                      ("expansion_search", ef_used), ("search_width", sw_used),
-                                                      ("max_iterations", max_iters_used))):
+                                                      ("expansion_search", ef_used), ("search_width", sw_used))) \
+                    and abs(ent.get("max_iterations", -99) - max_iters_used) <= 2:
                 traffic = ent["dram_bytes_read"] + ent["dram_bytes_write"]
     except Exception:
         pass

@@ -87,6 +87,11 @@ void launch_graph_search(const SearchParams& p, cudaStream_t stream) {
         return e ? (uint32_t)atoi(e) : 1u;
     }();
     a.compact = compact_env;
+    static const uint32_t l2pf_env = [] {
+        const char* e = getenv("VSB_K4_L2PF");
+        return e ? (uint32_t)atoi(e) : 0u;
+    }();
+    a.l2pf = l2pf_env;
     const int cpl = pick_cpl((int)(p.x.row_bytes / 16));
     // filtered ANN always runs the warp-per-query kernel (the second list lives there)
     if (p.q.n <= graph_search_small_batch() && p.allow == nullptr) {

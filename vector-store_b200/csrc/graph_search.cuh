@@ -51,6 +51,7 @@ struct K4Args {
     uint32_t rk;            // length of the result list of the FILTER instantiation (k rounded up to 32)
     uint32_t mma;           // 1: 16-bit rows are evaluated on the tensor cores (mma.sync), distances are candidate-grade
     uint32_t compact;       // 1: survivors of an iteration are compacted before the sort + merge
+    uint32_t l2pf;          // rows of prefetch distance into L2 (0 = off), warp-per-query kernel
 };
 
 __device__ __forceinline__ bool hash_insert(uint32_t* tab, uint32_t mask, uint32_t bits, uint32_t slot) {
@@ -247,13 +248,26 @@ __device__ __forceinline__ void group_reduce_mma(const VecGroup<CPL, U>& grp, co
 
 // all queue entries of this warp: index(m) = first + m * stride, m < mine.  Double buffered: the loads of
 // group m+1 are in flight while group m is reduced.
+// whole-row prefetch into L2 by the bulk-copy engine: one instruction per row, nothing comes back to the SM
+__device__ __forceinline__ void prefetch_row_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// l2pf > 0: rows `l2pf` positions ahead of the group being loaded are prefetched into L2 (all rows of an iteration are
+// known when it starts).  The register double buffer holds at most 2 U rows in flight per warp; at HBM latency that is
+// what bounds the kernel, at L2 latency it is plenty — the bulk prefetches carry the HBM latency instead and cost
+// neither registers nor issue slots.
 template <int ST, int CPL, int U, bool MMA = false>
 __device__ __forceinline__ void evaluate_entries(const uint8_t* __restrict__ x_rows, uint32_t row_bytes,
                                                  const uint32_t* newq, float* newd, uint32_t first, uint32_t stride,
                                                  uint32_t mine, uint32_t n_new, const float* qf, const uint4* qc,
-                                                 bool is_l2, int lane, int n_chunks, bool full) {
+                                                 bool is_l2, int lane, int n_chunks, bool full, uint32_t l2pf = 0) {
     if (mine == 0) return;
     const uint32_t last = first + (mine - 1) * stride;
+    if (l2pf != 0) {
+        for (uint32_t m = 2 * U + lane; m < l2pf + 2 * U && m < mine; m += 32)
+            prefetch_row_l2(x_rows + (size_t)newq[first + m * stride] * row_bytes, row_bytes);
+    }
     auto reduce = [&](const VecGroup<CPL, U>& grp, uint32_t base) {
         if constexpr (MMA) group_reduce_mma<ST, CPL, U>(grp, qc, newd, base, stride, n_new, lane);
         else group_reduce<ST, CPL, U>(grp, qf, qc, is_l2, newd, base, stride, n_new, lane);
@@ -262,6 +276,10 @@ __device__ __forceinline__ void evaluate_entries(const uint8_t* __restrict__ x_r
     group_load<CPL, U>(ga, x_rows, row_bytes, newq, first, stride, last, lane, n_chunks, full);
     for (uint32_t m0 = 0; m0 < mine; m0 += 2 * U) {
         const bool has_b = m0 + U < mine;
+        if (l2pf != 0) {
+            const uint32_t m = m0 + 2 * U + l2pf + lane;
+            if (lane < 2 * U && m < mine) prefetch_row_l2(x_rows + (size_t)newq[first + m * stride] * row_bytes, row_bytes);
+        }
         if (has_b) group_load<CPL, U>(gb, x_rows, row_bytes, newq, first + (m0 + U) * stride, stride, last, lane, n_chunks, full);
         reduce(ga, first + m0 * stride);
         if (has_b) {
@@ -363,7 +381,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32, k4_min_blocks<ST, CPL>()) graph
             }
         }
         evaluate_entries<ST, CPL, U, MMA>(a.x_rows, a.x_row_bytes, newq, newd, 0, 1, n_new, n_new, qf, qc, is_l2, lane,
-                                          n_chunks, full);
+                                          n_chunks, full, a.l2pf);
         __syncwarp();
         // Candidates that cannot enter the list (most of them once the beam has converged) are dropped first and the
         // survivors of ALL batches of this iteration are compacted into `stage`, so the shuffle sort + list merge — the
