@@ -62,3 +62,58 @@ extern "C" int vsbsynth_embedding_mix(float* d_out, uint64_t row0, uint64_t n, u
                                                                                 centers_seed);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
+
+// ---- random-row gather probe (tools/rowgather_probe.py): the HBM ceiling of K4's access pattern ---------------------
+// Every warp streams whole rows chosen by a hash of (warp, step) with 128-bit loads, ROWS rows in flight per warp, and
+// does nothing else with them (xor into a register).  What it reaches for a given row size is the bandwidth a beam
+// search over rows of that size can at best reach: random rows open a DRAM page for a few hundred bytes each.
+namespace {
+template <int ROWS>
+__global__ void __launch_bounds__(256) row_gather_kernel(const uint4* __restrict__ base, uint64_t n_rows, uint32_t row_chunks,
+                                                         uint32_t steps, uint64_t seed, uint32_t* __restrict__ sink) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t acc = 0;
+    for (uint32_t s = 0; s < steps; ++s) {
+        uint4 v[ROWS][6];
+        const uint32_t cpl = (row_chunks + 31) / 32;  // <= 6
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const uint64_t row = h3(seed, warp, (uint64_t)s * ROWS + r) % n_rows;
+            const uint4* p = base + row * row_chunks + lane;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                v[r][j] = make_uint4(0, 0, 0, 0);
+                if (j < (int)cpl && j * 32 + lane < (int)row_chunks)
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(v[r][j].x), "=r"(v[r][j].y), "=r"(v[r][j].z), "=r"(v[r][j].w)
+                                 : "l"(p + j * 32));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc ^= v[r][j].x ^ v[r][j].y ^ v[r][j].z ^ v[r][j].w;
+    }
+    if (acc == 0x12345678u) sink[0] = acc;  // keeps the loads alive
+}
+}  // namespace
+
+// rows of row_bytes (multiple of 16, <= 3072) in a buffer of n_rows rows; every warp gathers steps * rows_in_flight rows
+extern "C" int vsbsynth_row_gather(const void* d_rows, uint64_t n_rows, uint32_t row_bytes, uint32_t rows_in_flight,
+                                   uint32_t warps, uint32_t steps, uint64_t seed, void* d_sink, void* stream) {
+    if (row_bytes % 16 || row_bytes > 3072 || n_rows == 0) return 1;
+    const uint32_t chunks = row_bytes / 16;
+    const unsigned blocks = (warps + 7) / 8;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint4* b = static_cast<const uint4*>(d_rows);
+    uint32_t* sink = static_cast<uint32_t*>(d_sink);
+    switch (rows_in_flight) {
+        case 1: row_gather_kernel<1><<<blocks, 256, 0, s>>>(b, n_rows, chunks, steps, seed, sink); break;
+        case 2: row_gather_kernel<2><<<blocks, 256, 0, s>>>(b, n_rows, chunks, steps, seed, sink); break;
+        case 4: row_gather_kernel<4><<<blocks, 256, 0, s>>>(b, n_rows, chunks, steps, seed, sink); break;
+        case 8: row_gather_kernel<8><<<blocks, 256, 0, s>>>(b, n_rows, chunks, steps, seed, sink); break;
+        default: return 1;
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}

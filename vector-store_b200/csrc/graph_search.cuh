@@ -294,8 +294,15 @@ constexpr int K4_MAX_WIDTH = 8;  // parents expanded per iteration (search_width
 
 // resident CTAs per SM the register budget is sized for: short int8 rows (the scaled-int8 traversal copy) need
 // few load registers, and the kernel is bound by the number of rows in flight per SM, not by bytes
-template <int ST, int CPL>
+// tools/rowgather_probe.py (profiles/r2_random_row_gather_probe.jsonl): a kernel that does nothing but gather random
+// 1.5 KB rows reaches 6.6 TB/s with >= 32 resident warps x 2 rows in flight, 4.4 TB/s with 16 warps x 4 rows, 2.6 TB/s
+// with 8 warps x 8 rows: the ceiling for this access pattern is the copy peak, but only with ~100 rows in flight per
+// SM.  K4 holds 12 warps x <= 8 rows with a ~50 % duty cycle, which is where its 0.75 comes from.  Measured and NOT
+// kept: 2 rows per group + four CTAs per SM for the tensor-core form (117 registers, 16 warps: 8.8 ms vs 8.3-8.6 ms).
+template <int ST, int CPL, bool MMA = false>
 constexpr int k4_min_blocks() { return (ST == VSB_ST_I8 && CPL <= 2) ? 4 : 3; }
+template <int CPL, bool MMA>
+constexpr int k4_rows_per_group() { return CPL <= 3 ? 4 : (CPL <= 6 ? 2 : 1); }
 
 // FILTER = true (vsb_search_filtered): the traversal is unchanged, but every evaluated row whose key is admissible is
 // ALSO folded into a second list of rk entries, and that list is what the kernel emits.  The beam still walks through
@@ -303,10 +310,10 @@ constexpr int k4_min_blocks() { return (ST == VSB_ST_I8 && CPL <= 2) ? 4 : 3; }
 // MMA = true (16-bit float storages): the rows of a group are multiplied on the tensor cores (group_reduce_mma) instead
 // of being unpacked and FMA'd lane by lane; the query stays packed in registers; the distances are candidate-grade.
 template <int ST, int CPL, bool FILTER, bool MMA = false>
-__global__ void __launch_bounds__(K4_WARPS * 32, k4_min_blocks<ST, CPL>()) graph_search_kernel(K4Args a) {
+__global__ void __launch_bounds__(K4_WARPS * 32, k4_min_blocks<ST, CPL, MMA>()) graph_search_kernel(K4Args a) {
     constexpr int E = Storage<ST>::ELEMS;
     constexpr bool kFloat = Storage<ST>::kFloat;
-    constexpr int U = CPL <= 3 ? 4 : (CPL <= 6 ? 2 : 1);  // vectors per load group
+    constexpr int U = k4_rows_per_group<CPL, MMA>();  // vectors per load group
     constexpr int QF = (kFloat && !MMA) ? CPL * E : 1;
 
     extern __shared__ __align__(16) uint8_t smem_raw[];
