@@ -61,7 +61,7 @@ def parse_args():
                     help="mixture components of the synthetic corpus (256 per million rows)")
     ap.add_argument("--target-recall", type=float, default=0.95)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="corpus rows of the bounded CPU-baseline sample")
-    ap.add_argument("--search-width", type=int, default=0, help="parents per K4 iteration (1..8); 0 = pick the fastest of 2, 4 and 8")
+    ap.add_argument("--search-width", type=int, default=0, help="parents per K4 iteration (1..4); 0 = pick the faster of 2 and 4")
     ap.add_argument("--traversal", default=None, choices=["bf16", "i8", "native"],
                     help="f32 storage: traverse a bf16 (or scaled-int8) copy and re-rank the best candidates on the f32 rows")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
@@ -456,7 +456,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return {"ef": ef_used, "max_iterations": hi_it, "search_width": sw, "ms_per_batch": float(t.item()), "sweep": sweep}
 
-    cands = [tune(sw) for sw in ((2, 4, 8) if a.search_width == 0 else (a.search_width,))]
+    cands = [tune(sw) for sw in ((2, 4) if a.search_width == 0 else (a.search_width,))]
     op = min(cands, key=lambda c: c["ms_per_batch"])
     ef_used, max_iters_used, sw_used = op["ef"], op["max_iterations"], op["search_width"]
     idx.set_search_params(expansion_search=ef_used, search_width=sw_used, max_iterations=max_iters_used)

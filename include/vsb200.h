@@ -98,7 +98,7 @@ typedef struct {
     uint32_t max_iterations;   /* beam-search iterations per query; 0 = keep, >= 1000000 = automatic */
     uint32_t n_seeds;          /* entry points taken from the seed layer, <= 32 */
     uint32_t min_graph_size;   /* below this many live vectors search is brute force */
-    uint32_t search_width;     /* parents expanded per iteration, 1..8 */
+    uint32_t search_width;     /* parents expanded per iteration, 1..4 */
     uint32_t stream_threshold; /* un-graphed rows that make vsb_add link them into the graph (K7);
                                   default 4096; UINT32_MAX = never (only vsb_insert_pending / vsb_build) */
     uint32_t filter_exact_below_pct; /* filtered search: if fewer than this percentage of the live rows is

@@ -73,6 +73,7 @@ struct TcArgs {
     uint32_t kp, n_splits, rows_per_split;  // n_splits = lists per query = TC_HALVES * gridDim.y
     uint64_t* part;
     int tile_min;  // 1: emit only each tile's best row per query (seed layer), no list maintenance
+    uint32_t tile_min_stride;  // tile-min mode: entries per query in `part`, entry = (global tile) * TC_HALVES + half
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -440,12 +441,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const size_t list_stride = (size_t)a.n_splits * a.kp;
         uint64_t* warp_lists = a.part + ((size_t)(q0 + quarter * 32) * a.n_splits + list_id) * a.kp;
         const uint64_t* warp_buf = buf + ((size_t)half * TC_M + quarter * 32) * TC_BUFCAP;
-        for (int r = 0; r < 32; ++r) {   // (tile-min mode: the entries of tiles this split does not have stay invalid)
-            if (q0 + quarter * 32 + r >= a.nq) break;
-            uint64_t* list = warp_lists + (size_t)r * list_stride;
-            for (uint32_t i = lane; i < a.kp; i += 32) list[i] = kInvalidPacked;
+        if constexpr (!TILE_MIN) {  // (tile-min mode writes one dense entry per tile half; the caller pre-fills the padding)
+            for (int r = 0; r < 32; ++r) {
+                if (q0 + quarter * 32 + r >= a.nq) break;
+                uint64_t* list = warp_lists + (size_t)r * list_stride;
+                for (uint32_t i = lane; i < a.kp; i += 32) list[i] = kInvalidPacked;
+            }
+            __syncwarp();
         }
-        __syncwarp();
         float thr = q_valid ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
         int cnt = 0;
         const uint32_t* deny = a.deny;
@@ -562,10 +565,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 }
             }
             if constexpr (TILE_MIN) {
-                if (q_valid && best_c != kInvalidSlot && t < a.kp) {
+                if (q_valid) {
+                    // dense layout: K4 sorts ceil(2 * tiles / 32) blocks of 32 entries per query, however the rows
+                    // were split over CTAs
                     if constexpr (METRIC == VSB_METRIC_L2SQ) best_d = fmaxf(best_d, 0.0f);
                     if constexpr (METRIC == VSB_METRIC_COS) best_d = fminf(fmaxf(best_d, 0.0f), 2.0f);
-                    a.part[((size_t)q * a.n_splits + list_id) * a.kp + t] = pack_ds(best_d, n0 + best_c);
+                    const uint32_t gt = split * (a.rows_per_split / TC_N) + t;
+                    a.part[(size_t)q * a.tile_min_stride + gt * TC_HALVES + half] =
+                        best_c != kInvalidSlot ? pack_ds(best_d, n0 + best_c) : kInvalidPacked;
                 }
             }
             // accumulator drained: hand the TMEM buffer back to the MMA warp
@@ -687,6 +694,12 @@ bool exact_tc_supported(int storage, int metric) {
     return storage == VSB_ST_F32 || storage == VSB_ST_BF16 || storage == VSB_ST_F16;
 }
 
+// tile-min mode: entries per query of the dense winner array (one per tile half, padded to whole blocks of 32)
+uint32_t exact_tc_tile_min_entries(uint32_t n_rows) {
+    const uint32_t tiles = (n_rows + TC_N - 1) / TC_N;
+    return (tiles * TC_HALVES + 31) / 32 * 32;
+}
+
 // Both functions return the number of candidate LISTS per query (what ExactParams::n_splits means to K3 and to the
 // part buffer): TC_HALVES lists — one per epilogue column half — for each row split of the corpus.
 // tile-min mode keeps one entry per (tile, column half): a row split may not hold more than kp tiles
@@ -752,6 +765,7 @@ bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream, bool 
     a.rows_per_split = ((rps + TC_N - 1) / TC_N) * TC_N;
     a.part = p.part;
     a.tile_min = tile_min ? 1 : 0;
+    a.tile_min_stride = exact_tc_tile_min_entries(p.x_hi - p.x_lo);
     uint32_t q_tiles = (p.q.n + TC_M - 1) / TC_M;
     if (cta2) q_tiles = (q_tiles + 1) & ~1u;  // CTA pairs: an odd tail tile gets an all-padding partner
     dim3 grid(q_tiles, row_splits);

@@ -290,7 +290,13 @@ __device__ __forceinline__ void evaluate_entries(const uint8_t* __restrict__ x_r
     }
 }
 
-constexpr int K4_MAX_WIDTH = 8;  // parents expanded per iteration (search_width)
+// Compile-time cap of search_width.  8 was measured: the wider unrolled parent / neighbour loops slow EVERY width down
+// (1.25 M x 768 bf16, ef 64, 2 parents: 3.65 ms with a cap of 4, 4.39 ms with a cap of 8), which costs more than
+// 8 parents per iteration gain on long searches.
+#ifndef VSB_K4_MAX_WIDTH
+#define VSB_K4_MAX_WIDTH 4
+#endif
+constexpr int K4_MAX_WIDTH = VSB_K4_MAX_WIDTH;  // parents expanded per iteration (search_width)
 
 // resident CTAs per SM the register budget is sized for: short int8 rows (the scaled-int8 traversal copy) need
 // few load registers, and the kernel is bound by the number of rows in flight per SM, not by bytes
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32, k4_min_blocks<ST, CPL, MMA>()) 
             const bool keep = res < worst;
             const uint32_t km = __ballot_sync(kFullMask, keep);
             if (km == 0) continue;  // nothing here can enter the list
-            if (!a.compact) {       // A/B switch (VSB_K4_COMPACT=0): sort + merge every batch that has a survivor
+            if (!a.compact || n_new <= 32) {  // a single batch (or VSB_K4_COMPACT=0): sort + merge it directly
                 res = warp_sort32(res, lane, less);
                 warp_list_merge(list, (int)a.itopk, res, lane, less);
                 continue;

@@ -487,7 +487,7 @@ vsb_status create_single(const vsb_options* o, vsb_index** out) {
     if (o->flags & VSB_FLAG_BUILD_REFINE) ix->refine_passes = 1;
     if (const char* v = getenv("VSB_REFINE_PASSES")) ix->refine_passes = (uint32_t)strtoul(v, nullptr, 10);
     if (const char* v = getenv("VSB_CHURN_REFINE")) ix->churn_refine = !(v[0] == '0');
-    if (const char* v = getenv("VSB_BUILD_SW")) ix->build_search_width = std::min<uint32_t>(8, std::max<uint32_t>(1, (uint32_t)strtoul(v, nullptr, 10)));
+    if (const char* v = getenv("VSB_BUILD_SW")) ix->build_search_width = std::min<uint32_t>(4, std::max<uint32_t>(1, (uint32_t)strtoul(v, nullptr, 10)));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
     // searches on a high-priority stream, mutators (build, streaming insert, refinement) on a low-priority one:
@@ -670,7 +670,7 @@ vsb_status vsb_set_search_params(vsb_index* ix, const vsb_search_params* p) {
         if (p->max_iterations) ix->max_iters = p->max_iterations >= 1000000u ? 0 : p->max_iterations;  // >= 1e6: back to auto
         if (p->n_seeds) ix->n_seeds = std::min<uint32_t>(p->n_seeds, 32);
         if (p->min_graph_size) ix->min_graph_size = p->min_graph_size;
-        if (p->search_width) ix->search_width = std::min<uint32_t>(p->search_width, 8);
+        if (p->search_width) ix->search_width = std::min<uint32_t>(p->search_width, 4);
         if (p->traversal) ix->native_traversal = p->traversal == 2;
         if (p->filter_exact_below_pct) ix->filter_min_pct = p->filter_exact_below_pct == 0xFFFFFFFFu ? 0 : std::min<uint32_t>(p->filter_exact_below_pct, 101);
     }

@@ -290,7 +290,7 @@ struct vsb_index {
     // ~2 % QPS at equal recall and costs 1.7x the rest of the build (10 M x 768: 5.7 s -> 16.6 s, profiles/r2_*)
     uint32_t refine_passes = 0;
     bool churn_refine = true;  // one refinement pass after 10 % of the graph has churned (VSB_CHURN_REFINE=0 turns it off)
-    uint32_t build_search_width = 8;  // parents per K4 iteration in the streaming insert / refinement searches (VSB_BUILD_SW): 10 M x 768 build 6.1 s at 2, 5.6 s at 4, 5.4 s at 8, same graph quality
+    uint32_t build_search_width = 4;  // parents per K4 iteration in the streaming insert / refinement searches (VSB_BUILD_SW): 10 M x 768 build 6.1 s at 2, 5.6 s at 4, same graph quality
     vsbi::Sharded* sharded = nullptr;  // n_devices > 1: every entry point forwards to the router (owned; sharded.cu)
 
     // ---- published state ----

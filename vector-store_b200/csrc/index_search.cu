@@ -200,7 +200,7 @@ vsb_status vsb_index::graph_block(const View& v, Scratch& sc, const GraphRun& ru
     // order, exactly like the results of the bf16 / int8 traversal copies (the build only needs the ranking)
     const int trav_storage = t16 ? (int)VSB_BF16 : storage;
     const bool use8_early = trav8 && t16 && packed_out == nullptr;
-    const bool mma = !use8_early && vsb::graph_search_uses_mma(trav_storage, nb, run.allow != nullptr);
+    const bool mma = !use8_early && vsb::graph_search_uses_mma(trav_storage, nb, run.allow != nullptr, std::max(run.itopk, k));
     const bool rerank = (t16 || mma) && packed_out == nullptr;
     // ---- bf16 shadow of the queries (f32 storage: tensor-core seed layer and/or bf16 traversal) ----
     bool seed_tc = tc_enabled && vsb::exact_tc_supported(storage, metric) && nb >= 16;
@@ -238,7 +238,7 @@ vsb_status vsb_index::graph_block(const View& v, Scratch& sc, const GraphRun& ru
     if (seed_tc) {
         // tensor cores: one winner per 256-row tile per query (no list maintenance);
         // f32 storage multiplies the bf16 shadows of the queries and of the seed block
-        sp.n_splits = std::max(vsb::exact_tc_pick_splits(nb, sd.n, sm_count, 0), vsb::exact_tc_min_splits_tile_min(sd.n, 32));
+        sp.n_splits = vsb::exact_tc_pick_splits(nb, sd.n, sm_count, 0);
         if (storage == VSB_F32) {
             sp.storage = VSB_BF16;
             sp.q = q16v;
@@ -252,10 +252,14 @@ vsb_status vsb_index::graph_block(const View& v, Scratch& sc, const GraphRun& ru
     }
     const bool seed_scan = !seed_tc && nb <= vsb::graph_search_small_batch();
     if (seed_scan) sp.n_splits = vsb::seed_scan_blocks(sd.n);
-    CU(sc.seed_part.ensure(vsb::exact_part_elems(nb, sp.n_splits, 32) * 8));
+    const uint32_t seed_dense = vsb::exact_tc_tile_min_entries(sd.n);  // tensor-core seed layer: dense winners per query
+    CU(sc.seed_part.ensure(std::max<size_t>(vsb::exact_part_elems(nb, sp.n_splits, 32), (size_t)nb * seed_dense) * 8));
     sp.part = sc.seed_part.as<uint64_t>();
     if (tp) t_begin(PH_SEED, s);
-    if (seed_tc) seed_tc = vsb::launch_exact_candidates_tc(sp, s, true);
+    if (seed_tc) {
+        CU(cudaMemsetAsync(sc.seed_part.p, 0xFF, (size_t)nb * seed_dense * 8, s));
+        seed_tc = vsb::launch_exact_candidates_tc(sp, s, true);
+    }
     if (!seed_tc) {
         const uint32_t splits = sp.n_splits;
         sp = sp_native;
@@ -307,7 +311,7 @@ vsb_status vsb_index::graph_block(const View& v, Scratch& sc, const GraphRun& ru
     gp.degree = degree;
     gp.n_graphed = v.n_graphed;
     gp.seed_lists = sc.seed_part.as<uint64_t>();
-    gp.seed_stride = sp.n_splits * 32;
+    gp.seed_stride = seed_tc ? seed_dense : sp.n_splits * 32;
     gp.n_seeds = run.n_seeds;
     gp.seed_slots = sd.slots.as<uint32_t>();
     gp.deny = deny_bm;

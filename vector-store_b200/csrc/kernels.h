@@ -78,6 +78,10 @@ bool exact_tc_supported(int storage, int metric);
 uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count, uint32_t kp);
 bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream, bool tile_min = false);
 uint32_t exact_tc_min_splits_tile_min(uint32_t n_rows, uint32_t kp);
+// tile-min launches write a DENSE array of exact_tc_tile_min_entries(rows) packed winners per query into p.part (one
+// per 256-row tile half, in row order; padding and empty tiles = kInvalidPacked, the caller pre-fills the padding with
+// 0xFF) whatever p.n_splits is; p.x_lo must be 0.
+uint32_t exact_tc_tile_min_entries(uint32_t n_rows);
 
 // K6 (graph_build.cu) ---------------------------------------------------------------------------
 // knn: [n][k_init] packed lists (ascending); produces fwd [n][R] pruned by detour count.
@@ -139,7 +143,7 @@ struct SearchParams {
     // distances — the caller re-ranks the rows it returns).  graph_search_uses_mma() tells which launches honour it.
     bool mma = false;
 };
-bool graph_search_uses_mma(int storage, uint32_t n_queries, bool filtered);
+bool graph_search_uses_mma(int storage, uint32_t n_queries, bool filtered, uint32_t itopk);
 void launch_graph_search(const SearchParams& p, cudaStream_t stream);
 bool graph_search_supported(uint32_t row_bytes);  // rows up to 6144 bytes
 uint32_t graph_search_small_batch();
