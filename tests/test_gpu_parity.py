@@ -688,8 +688,15 @@ def test_c_abi_client_replays_reference_scenario(tmp_path):
     # a plain C program (tests/abi_client.c) drives G1 through the C ABI — no Python in the data path
     import subprocess
     from test_abi import _build_c_client
-    r = subprocess.run([_build_c_client(tmp_path)], capture_output=True, text=True)
+    exe = _build_c_client(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "scenario passed" in r.stdout, r.stdout + r.stderr
+    # the same scenario on ONE handle sharded over every GPU of the box (vsb_options.n_devices), still plain C
+    import torch
+    n = min(torch.cuda.device_count(), 8)
+    if n >= 2:
+        r = subprocess.run([exe, str(n)], capture_output=True, text=True)
+        assert r.returncode == 0 and "sharded handle" in r.stdout, r.stdout + r.stderr
 
 
 # ---- edge cases the reference's tests touch: empty / tiny / oversized inputs, growth, everything deleted ---------
