@@ -684,6 +684,37 @@ def test_c2_full_size_properties():
     assert np.array_equal(sk[:, 0], np.arange(256, dtype=np.uint64)) and np.all(sd[:, 0] <= 1e-6)
 
 
+@pytest.mark.parametrize("storage,metric", [(O.BF16, O.L2SQ), (O.BF16, O.IP), (O.F16, O.COS), (O.F16, O.L2SQ)])
+def test_tensor_core_traversal_returns_canonical_distances(storage, metric):
+    """16-bit float rows, a batch above the small-batch limit and a beam >= 96: K4 multiplies the rows with mma.sync
+    (group_reduce_mma) and ranks by candidate-grade sums, K3 re-ranks what is returned.  Whatever the traversal
+    arithmetic, the hits must carry the canonical distances of the oracle, ascending, no key twice, recall >= 0.95.
+    200 dimensions = 400-byte rows: the last 16-byte chunk row of a lane group is ragged (zero-filled fragments)."""
+    n, dim, nq, k = 60_000, 200, 600, 10
+    x = embedding_like(n, dim, n_clusters=40)
+    q = embedding_like(nq, dim, seed=4321, n_clusters=40)
+    keys = np.arange(n, dtype=np.uint64) + np.uint64(7)
+    idx = make_index(x, keys, metric, storage)
+    idx.build()
+    idx.set_search_params(expansion_search=128, search_width=4)
+    gk, gd, gc = idx.search_batch(q, k)
+    tk, td, tc = idx.search_batch(q, k, exact=True)
+    assert np.all(gc == k)
+    assert np.all(np.diff(gd, axis=1) >= 0)
+    assert all(len(set(row.tolist())) == k for row in gk)
+    recall = O.recall_at_k(gk, tk)
+    print(f"tensor-core traversal storage={storage} metric={metric}: recall@10 = {recall:.4f}")
+    assert recall >= 0.95
+    for i in (0, 1, nq - 1):
+        od = O.distance_matrix(x[(gk[i] - np.uint64(7)).astype(np.int64)], q[i:i + 1], metric, storage)[0]
+        assert np.array_equal(gd[i].view(np.uint32), od.view(np.uint32))
+    # a batch-1 call (CTA-per-query kernel, SIMT evaluation, no re-rank) returns the same canonical distances for its hits
+    sk, sd, _ = idx.search_batch(q[:1], k)
+    od = O.distance_matrix(x[(sk[0] - np.uint64(7)).astype(np.int64)], q[:1], metric, storage)[0]
+    assert np.array_equal(sd[0].view(np.uint32), od.view(np.uint32))
+    idx.close()
+
+
 def test_c_abi_client_replays_reference_scenario(tmp_path):
     # a plain C program (tests/abi_client.c) drives G1 through the C ABI — no Python in the data path
     import subprocess
