@@ -41,6 +41,13 @@ def test_version_and_no_cpu_fallback():
             assert e.status == 6  # VSB_ECUDA
         else:
             raise AssertionError("GpuIndex was created without a CUDA device")
+        # the partition set (vsb_set_*) validates its options on a real handle: same loud failure
+        try:
+            v.IndexSet(8)
+        except v.VsbError as e:
+            assert e.status == 6
+        else:
+            raise AssertionError("IndexSet was created without a CUDA device")
 
 
 def test_product_never_imports_oracle():

@@ -700,14 +700,8 @@ uint32_t exact_tc_tile_min_entries(uint32_t n_rows) {
     return (tiles * TC_HALVES + 31) / 32 * 32;
 }
 
-// Both functions return the number of candidate LISTS per query (what ExactParams::n_splits means to K3 and to the
-// part buffer): TC_HALVES lists — one per epilogue column half — for each row split of the corpus.
-// tile-min mode keeps one entry per (tile, column half): a row split may not hold more than kp tiles
-uint32_t exact_tc_min_splits_tile_min(uint32_t n_rows, uint32_t kp) {
-    const uint32_t tiles = (n_rows + TC_N - 1) / TC_N;
-    return TC_HALVES * ((tiles + kp - 1) / kp);
-}
-
+// Returns the number of candidate LISTS per query (what ExactParams::n_splits means to K3 and to the part buffer):
+// TC_HALVES lists — one per epilogue column half — for each row split of the corpus.
 uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count, uint32_t kp) {
     // One CTA per SM: the sweep takes ceil(q_tiles * s / SMs) waves of 1/s of the corpus each.  Pick the row-split
     // count s that minimises waves / s, i.e. fills the last wave (79 query tiles x 1 split would leave 69 of 148 SMs

@@ -77,7 +77,6 @@ void launch_max_norm(const float* nrm, uint32_t lo, uint32_t hi, float* out, cud
 bool exact_tc_supported(int storage, int metric);
 uint32_t exact_tc_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count, uint32_t kp);
 bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream, bool tile_min = false);
-uint32_t exact_tc_min_splits_tile_min(uint32_t n_rows, uint32_t kp);
 // tile-min launches write a DENSE array of exact_tc_tile_min_entries(rows) packed winners per query into p.part (one
 // per 256-row tile half, in row order; padding and empty tiles = kInvalidPacked, the caller pre-fills the padding with
 // 0xFF) whatever p.n_splits is; p.x_lo must be 0.
