@@ -74,6 +74,9 @@ struct TcArgs {
     uint64_t* part;
     int tile_min;  // 1: emit only each tile's best row per query (seed layer), no list maintenance
     uint32_t tile_min_stride;  // tile-min mode: entries per query in `part`, entry = (global tile) * TC_HALVES + half
+    uint32_t tile_step;        // rows between the starts of consecutive tiles (TC_N; larger = a tile-strided SAMPLE of the rows)
+    uint32_t max_tiles;        // 0 = every tile of the split; else at most this many (sample passes)
+    const float* thr_init;     // [nq] initial k'-th-best bound per query (nullable): rows farther than this are never listed
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -320,7 +323,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t split = blockIdx.y;
     const uint32_t r_lo = a.x_lo + split * a.rows_per_split;
     const uint32_t r_hi = min(a.x_hi, r_lo + a.rows_per_split);
-    const uint32_t n_tiles = r_hi > r_lo ? (r_hi - r_lo + TC_N - 1) / TC_N : 0;
+    uint32_t n_tiles = r_hi > r_lo ? (r_hi - r_lo + a.tile_step - 1) / a.tile_step : 0;
+    if (a.max_tiles != 0 && n_tiles > a.max_tiles) n_tiles = a.max_tiles;
     const uint32_t n_slabs = (a.row_bytes + TC_KBYTES - 1) / TC_KBYTES;
     constexpr int ELEMS_PER_SLAB = KIND == KIND_TF32 ? 32 : 64;
     constexpr int STAGES = CTA2 ? TC2_STAGES : TC_STAGES;
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = 0; t < n_tiles; ++t) {
-                const int n0 = (int)(r_lo + t * TC_N);
+                const int n0 = (int)(r_lo + t * a.tile_step);
                 for (uint32_t slab = 0; slab < n_slabs; ++slab) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -449,7 +453,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
             __syncwarp();
         }
-        float thr = q_valid ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
+        float thr = q_valid ? (a.thr_init != nullptr ? a.thr_init[q] : __int_as_float(0x7F800000)) : __int_as_float(0xFF800000);
         int cnt = 0;
         const uint32_t* deny = a.deny;
         const uint32_t* allow = a.allow;
@@ -458,7 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
         for (uint32_t t = 0; t < n_tiles; ++t) {
             const uint32_t acc = t & 1, acc_phase = (t >> 1) & 1;
-            const uint32_t n0 = r_lo + t * TC_N + half * TC_HALF_N;   // first corpus row of this warp's columns
+            const uint32_t n0 = r_lo + t * a.tile_step + half * TC_HALF_N;   // first corpus row of this warp's columns
             float best_d = __int_as_float(0x7F800000);
             uint32_t best_c = kInvalidSlot;
             // per-column parameter of this tile (NaN marks columns outside the split); every epilogue warp keeps
@@ -598,6 +602,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         else
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
     }
+}
+
+// Sampled thresholds for long lists over few rows (the build's all-pairs kNN lists: k' = 96 over 131 072 rows cost
+// ~1 450 list insertions per row if every list starts empty).  A first pass lists the 32 best rows of a tile-strided
+// SAMPLE per query; the m-th best of the sample, m ~ 3 * k' * sample / rows, bounds the k'-th best of all rows with
+// room to spare, and the main pass starts every list at that bound: ~3 k' candidates per row instead of ~15 k'.
+// One warp per query: merge the two column-half lists of the sample pass, take rank m - 1.
+__global__ void __launch_bounds__(256) tc_sample_threshold_kernel(const uint64_t* __restrict__ part, uint32_t nq, uint32_t m,
+                                                                  float* __restrict__ thr) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const LessBySlot less;
+    const uint64_t a0 = part[((size_t)q * TC_HALVES + 0) * 32 + lane];        // ascending
+    const uint64_t b0 = part[((size_t)q * TC_HALVES + 1) * 32 + (31 - lane)];  // descending
+    uint64_t v = b0 < a0 ? b0 : a0;  // bitonic: the 32 smallest of the 64
+    v = warp_bitonic_merge32(v, lane, less);
+    const uint64_t pick = shfl_u64(v, (int)m - 1);
+    if (lane == 0) thr[q] = pick == kInvalidPacked ? __int_as_float(0x7F800000) : ord_to_f32(packed_hi(pick));
+}
+
+// queries whose lists of the thresholded pass hold fewer than `need` rows in total (the bound was too tight for them)
+__global__ void __launch_bounds__(256) tc_count_short_kernel(const uint64_t* __restrict__ part, uint32_t nq, uint32_t lists,
+                                                             uint32_t kp, uint32_t need, uint32_t* __restrict__ counter) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    uint32_t have = 0;
+    for (uint32_t i = lane; i < lists * kp; i += 32) have += part[(size_t)q * lists * kp + i] != kInvalidPacked ? 1u : 0u;
+    have = (uint32_t)butterfly_sum_i((int)have);
+    if (lane == 0 && have < need) atomicAdd(counter, 1u);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -760,6 +795,9 @@ bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream, bool 
     a.part = p.part;
     a.tile_min = tile_min ? 1 : 0;
     a.tile_min_stride = exact_tc_tile_min_entries(p.x_hi - p.x_lo);
+    a.tile_step = (!tile_min && p.tile_step >= (uint32_t)TC_N) ? p.tile_step / TC_N * TC_N : (uint32_t)TC_N;
+    a.max_tiles = tile_min ? 0u : p.max_tiles;
+    a.thr_init = tile_min ? nullptr : p.thr_init;
     uint32_t q_tiles = (p.q.n + TC_M - 1) / TC_M;
     if (cta2) q_tiles = (q_tiles + 1) & ~1u;  // CTA pairs: an odd tail tile gets an all-padding partner
     dim3 grid(q_tiles, row_splits);
@@ -772,5 +810,20 @@ bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream, bool 
     g_tc_launches += 1;
     return true;
 }
+
+void launch_tc_sample_threshold(const uint64_t* sample_part, uint32_t nq, uint32_t m, float* thr, cudaStream_t stream) {
+    if (nq == 0) return;
+    tc_sample_threshold_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(sample_part, nq, m < 1 ? 1 : (m > 32 ? 32 : m), thr);
+    g_kernel_launches += 1;
+}
+
+void launch_tc_count_short(const uint64_t* part, uint32_t nq, uint32_t lists, uint32_t kp, uint32_t need, uint32_t* counter,
+                           cudaStream_t stream) {
+    if (nq == 0) return;
+    tc_count_short_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(part, nq, lists, kp, need, counter);
+    g_kernel_launches += 1;
+}
+
+uint32_t exact_tc_halves() { return TC_HALVES; }
 
 }  // namespace vsb

@@ -487,6 +487,7 @@ vsb_status create_single(const vsb_options* o, vsb_index** out) {
     if (o->flags & VSB_FLAG_BUILD_REFINE) ix->refine_passes = 1;
     if (const char* v = getenv("VSB_REFINE_PASSES")) ix->refine_passes = (uint32_t)strtoul(v, nullptr, 10);
     if (const char* v = getenv("VSB_CHURN_REFINE")) ix->churn_refine = !(v[0] == '0');
+    if (const char* v = getenv("VSB_TC_SAMPLED_BOUNDS")) ix->sampled_bounds = !(v[0] == '0');
     if (const char* v = getenv("VSB_BUILD_SW")) ix->build_search_width = std::min<uint32_t>(4, std::max<uint32_t>(1, (uint32_t)strtoul(v, nullptr, 10)));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;

@@ -256,11 +256,12 @@ struct Scratch {
     DevBuf q_in, q_rows, q_sq, q_nrm, q16_rows, q16_sq, q16_nrm, q8_rows, q8_sq, q8_nrm;
     DevBuf part, seed_part, tmp_keys, tmp_dists, rr_packed, counters, allow;
     DevBuf cert_state, fb_map, fb_rows, fb_sq, fb_nrm;  // certified exact search
+    DevBuf thr_part, thr, thr_cnt;                       // sampled list bounds of the all-pairs build (exact_block)
     PinBuf pin;                                          // pinned staging of this caller class's read-backs
     size_t bytes() const {
         const DevBuf* all[] = {&q_in, &q_rows, &q_sq, &q_nrm, &q16_rows, &q16_sq, &q16_nrm, &q8_rows, &q8_sq, &q8_nrm, &part,
                                &seed_part, &tmp_keys, &tmp_dists, &rr_packed, &counters, &allow, &cert_state, &fb_map,
-                               &fb_rows, &fb_sq, &fb_nrm};
+                               &fb_rows, &fb_sq, &fb_nrm, &thr_part, &thr, &thr_cnt};
         size_t s = 0;
         for (auto* b : all) s += b->bytes;
         return s;
@@ -289,6 +290,7 @@ struct vsb_index {
     // refinement passes at the end of vsb_build (VSB_REFINE_PASSES).  0 by default: with detour-pruned K7 links a pass buys
     // ~2 % QPS at equal recall and costs 1.7x the rest of the build (10 M x 768: 5.7 s -> 16.6 s, profiles/r2_*)
     uint32_t refine_passes = 0;
+    bool sampled_bounds = true;  // all-pairs kNN lists start from sampled bounds (VSB_TC_SAMPLED_BOUNDS=0 turns it off)
     bool churn_refine = true;  // one refinement pass after 10 % of the graph has churned (VSB_CHURN_REFINE=0 turns it off)
     uint32_t build_search_width = 4;  // parents per K4 iteration in the streaming insert / refinement searches (VSB_BUILD_SW): 10 M x 768 build 6.1 s at 2, 5.6 s at 4, same graph quality
     vsbi::Sharded* sharded = nullptr;  // n_devices > 1: every entry point forwards to the router (owned; sharded.cu)

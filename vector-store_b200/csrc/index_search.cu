@@ -51,15 +51,55 @@ vsb_status vsb_index::exact_block(const View& v, Scratch& sc, const vsb::RowsVie
     CU(sc.part.ensure(vsb::exact_part_elems(q.n, p.n_splits, p.kp) * 8));
     p.part = sc.part.as<uint64_t>();
     if (tc) {
+        vsb::ExactParams pc = p;
         if (shadow_q != nullptr && shadow_x != nullptr && !certify) {
             // candidate stage on the bf16 shadow (half the bytes, kind::f16 rate); K3 re-ranks on the real rows
-            vsb::ExactParams pc = p;
             pc.storage = VSB_BF16;
             pc.q = *shadow_q;
             pc.x = *shadow_x;
-            tc = vsb::launch_exact_candidates_tc(pc, s);
+        }
+        // Long lists over few rows (the all-pairs kNN lists of a build): bound every list by the m-th best row of a
+        // tile-strided 8192-row sample first, so the main pass lists ~3 k' rows per query instead of ~15 k'.  The
+        // bound is statistical: if more than 2 % of the queries end up with fewer than k rows the block is redone
+        // without it (rows stored in the order of their clusters would do that).
+        const uint32_t rows = x_hi - x_lo;
+        const bool sampled = sampled_bounds && approx_ok && !certify && self_base >= 0 && rows >= 65536 && p.kp >= 64 &&
+                             p.n_splits == vsb::exact_tc_halves() && allow_bm == nullptr;
+        if (sampled) {
+            const uint32_t sample_tiles = 32, halves = vsb::exact_tc_halves();
+            vsb::ExactParams ps = pc;
+            ps.kp = 32;
+            ps.n_splits = halves;
+            ps.tile_step = rows / 256 / sample_tiles * 256;
+            ps.max_tiles = sample_tiles;
+            CU(sc.thr_part.ensure((size_t)q.n * halves * 32 * 8));
+            CU(sc.thr.ensure((size_t)q.n * 4));
+            CU(sc.thr_cnt.ensure(16));
+            ps.part = sc.thr_part.as<uint64_t>();
+            tc = vsb::launch_exact_candidates_tc(ps, s);
+            if (tc) {
+                const double frac = (double)sample_tiles * 256.0 / (double)rows;
+                const uint32_t m = (uint32_t)std::min(32.0, std::max(4.0, std::ceil(3.0 * (double)p.kp * frac)));
+                vsb::launch_tc_sample_threshold(sc.thr_part.as<uint64_t>(), q.n, m, sc.thr.as<float>(), s);
+                pc.thr_init = sc.thr.as<float>();
+                CU(cudaMemsetAsync(sc.thr_cnt.p, 0, 4, s));
+                tc = vsb::launch_exact_candidates_tc(pc, s);
+                vsb::launch_tc_count_short(p.part, q.n, p.n_splits, p.kp, k + (self_base >= 0 ? 1u : 0u),
+                                           sc.thr_cnt.as<uint32_t>(), s);
+                uint32_t n_short = 0;
+                {
+                    vsbi::HostReadback rb(sc.pin, s);
+                    CU(rb.reserve(4));
+                    CU(rb.copy(&n_short, sc.thr_cnt.p, 4));
+                    CU(rb.finish());
+                }
+                if ((uint64_t)n_short * 50 > q.n) {
+                    pc.thr_init = nullptr;
+                    tc = vsb::launch_exact_candidates_tc(pc, s);
+                }
+            }
         } else {
-            tc = vsb::launch_exact_candidates_tc(p, s);
+            tc = vsb::launch_exact_candidates_tc(pc, s);
         }
     }
     if (!tc) {

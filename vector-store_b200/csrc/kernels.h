@@ -44,6 +44,10 @@ struct ExactParams {
     uint32_t kp = 32;                 // candidate list length, multiple of 32, <= 256
     uint32_t n_splits = 1;
     uint64_t* part = nullptr;         // scratch [q.n][n_splits][kp]
+    // tensor-core launches only (exact_tc.cu): a tile-strided sample of the rows, and sampled initial list bounds
+    uint32_t tile_step = 0;           // rows between tile starts (0 = contiguous tiles)
+    uint32_t max_tiles = 0;           // at most this many tiles per row split (0 = all)
+    const float* thr_init = nullptr;  // [q.n] rows farther than this never enter the query's lists
 };
 size_t exact_part_elems(uint32_t nq, uint32_t n_splits, uint32_t kp);
 uint32_t exact_pick_splits(uint32_t nq, uint32_t n_rows, int sm_count);
@@ -81,6 +85,11 @@ bool launch_exact_candidates_tc(const ExactParams& p, cudaStream_t stream, bool 
 // per 256-row tile half, in row order; padding and empty tiles = kInvalidPacked, the caller pre-fills the padding with
 // 0xFF) whatever p.n_splits is; p.x_lo must be 0.
 uint32_t exact_tc_tile_min_entries(uint32_t n_rows);
+// sampled list bounds (see tc_sample_threshold_kernel): sample_part = [nq][exact_tc_halves()][32] lists of a sample pass
+uint32_t exact_tc_halves();
+void launch_tc_sample_threshold(const uint64_t* sample_part, uint32_t nq, uint32_t m, float* thr, cudaStream_t stream);
+void launch_tc_count_short(const uint64_t* part, uint32_t nq, uint32_t lists, uint32_t kp, uint32_t need, uint32_t* counter,
+                           cudaStream_t stream);
 
 // K6 (graph_build.cu) ---------------------------------------------------------------------------
 // knn: [n][k_init] packed lists (ascending); produces fwd [n][R] pruned by detour count.
