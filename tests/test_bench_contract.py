@@ -63,3 +63,18 @@ def test_committed_bench_lines_carry_the_contract_keys():
             cb = d["cpu_baseline"]
             assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "sample" in cb
             assert d["build_roofline"]["tensor"]["frac"] > 0 and d["build_roofline"]["hbm"]["frac"] > 0
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """The driver launches the reference arm like our arm (torchrun for N > 1): rank 0 alone runs and prints, the other
+    ranks exit 0 without work."""
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--rows", "20000", "--dim", "64", "--cpu-sample", "20000",
+                          "--cpu-queries", "200", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
