@@ -65,3 +65,34 @@ def test_scaled_int8_cosine_error_is_small_against_neighbour_gaps():
     top_i8 = np.argsort(approx, axis=1)[:, :40]
     kept = np.mean([len(np.intersect1d(a, b)) / 10 for a, b in zip(top_true, top_i8)])
     assert kept >= 0.999
+
+
+def test_sampled_list_bound_leaves_enough_rows():
+    """The all-pairs build bounds every kNN list by the m-th best row of a tile-strided sample (exact_block /
+    tc_sample_threshold_kernel): sample = 32 tiles of 256 rows spread over the block, m = 3 k' sample / rows.
+    Emulated in NumPy on the bench's corpus generator (131 072 rows = the all-pairs prefix of every large build): the bound
+    must leave at least k = 65 rows (k_init + self) for all but a small fraction of the queries — the library redoes a block
+    without bounds above 2 % — and on average ~3 k' of them."""
+    from importlib import import_module
+    ds = import_module("vector_store_b200.host.datasets")
+    rows, dim, kp, k = 131_072, 64, 96, 65
+    x = ds.embedding_mix(rows, dim, seed=1234, n_clusters=2560)
+    q = x[::257][:400]                                      # queries are rows of the block (all-pairs)
+    d = 1.0 - q.astype(np.float64) @ x.astype(np.float64).T  # cosine distance of unit rows
+    tile_step = rows // 256 // 32 * 256
+    cols = np.concatenate([np.arange(t * tile_step, t * tile_step + 256) for t in range(32)])
+    m = int(min(32, max(4, np.ceil(3.0 * kp * len(cols) / rows))))
+    assert m == 18
+    bound = np.sort(d[:, cols], axis=1)[:, m - 1]
+    below = (d <= bound[:, None]).sum(axis=1)
+    short = float((below < k).mean())
+    print(f"sampled bound: mean {below.mean():.0f} rows below it (3 k' = {3 * kp}), min {below.min()}, short lists {short:.4f}")
+    assert short <= 0.02
+    assert 1.5 * kp < below.mean() < 6 * kp
+    # rows stored in the order of their clusters break the sample (whole tiles of one cluster): that is what the
+    # library's short-list count + redo is for — the emulation must SEE the failure mode it guards against
+    order = np.argsort((x @ x[0]).astype(np.float64), kind="stable")
+    ds_sorted = d[:, order]
+    bound_s = np.sort(ds_sorted[:, cols], axis=1)[:, m - 1]
+    below_s = (ds_sorted <= bound_s[:, None]).sum(axis=1)
+    assert below_s.std() > below.std()                      # far more erratic than on shuffled rows
