@@ -96,3 +96,40 @@ def test_sampled_list_bound_leaves_enough_rows():
     bound_s = np.sort(ds_sorted[:, cols], axis=1)[:, m - 1]
     below_s = (ds_sorted <= bound_s[:, None]).sum(axis=1)
     assert below_s.std() > below.std()                      # far more erratic than on shuffled rows
+
+
+def test_mma_fragment_mapping_of_the_tensor_core_traversal():
+    """group_reduce_mma (graph_search.cuh) fills mma.sync.m16n8k16 fragments straight from the SIMT kernel's loads: lane
+    l = 4 g + t holds 16 contiguous bytes (8 elements) of row u, of row u + 1 and of the query; elements 0..3 feed one
+    MMA, 4..7 the next.  With the PTX fragment layouts (A: a0 = (g, 2t..), a1 = (g+8, 2t..), a2 = (g, 2t+8..),
+    a3 = (g+8, 2t+8..); B: b0 = (2t.., n = g), b1 = (2t+8.., n = g); D: c0,c1 = (g, 2t..), c2,c3 = (g+8, 2t..)) the
+    diagonal D[g][g] is quad g's partial dot product for row u and D[g+8][g] for row u + 1, held by thread t = g / 2 in
+    register g % 2.  Emulated here with exact integer arithmetic."""
+    rng = np.random.default_rng(3)
+    segs = 3                                   # 768 bf16 elements = 3 warp loads of 512 bytes
+    row_a = rng.integers(-8, 9, size=(segs, 32, 8)).astype(np.int64)   # [segment][lane][element]
+    row_b = rng.integers(-8, 9, size=(segs, 32, 8)).astype(np.int64)
+    qry = rng.integers(-8, 9, size=(segs, 32, 8)).astype(np.int64)
+    D = np.zeros((16, 8), dtype=np.int64)
+    for s in range(segs):
+        for half in (0, 4):                    # first MMA: elements 0..3, second: 4..7
+            A = np.zeros((16, 16), dtype=np.int64)
+            B = np.zeros((16, 8), dtype=np.int64)
+            for lane in range(32):
+                g, t = lane // 4, lane % 4
+                A[g, 2 * t:2 * t + 2] = row_a[s, lane, half:half + 2]               # a0
+                A[g + 8, 2 * t:2 * t + 2] = row_b[s, lane, half:half + 2]           # a1
+                A[g, 2 * t + 8:2 * t + 10] = row_a[s, lane, half + 2:half + 4]      # a2
+                A[g + 8, 2 * t + 8:2 * t + 10] = row_b[s, lane, half + 2:half + 4]  # a3
+                B[2 * t:2 * t + 2, g] = qry[s, lane, half:half + 2]                 # b0
+                B[2 * t + 8:2 * t + 10, g] = qry[s, lane, half + 2:half + 4]        # b1
+            D += A @ B
+    v0 = v1 = 0
+    for lane in range(32):
+        g, t = lane // 4, lane % 4
+        if t == g // 2:                        # the thread that holds the diagonal entry of quad g
+            c = [D[g, 2 * t], D[g, 2 * t + 1], D[g + 8, 2 * t], D[g + 8, 2 * t + 1]]
+            assert 2 * t + (g % 2) == g
+            v0 += c[g % 2]
+            v1 += c[2 + g % 2]
+    assert v0 == int((row_a * qry).sum()) and v1 == int((row_b * qry).sum())
