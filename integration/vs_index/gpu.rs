@@ -176,7 +176,7 @@ impl GpuIndex {
         })?;
         for (key, st) in keys.iter().zip(&status) {
             if *st != sys::VSB_OK {
-                warn!("add: unable to add embedding for primary id {key}: status {st}");
+                warn!("row {key} was not inserted (vsb status {st})");
             }
         }
         self.mark_rows(
@@ -354,7 +354,7 @@ fn to_primary_keys(
                 .primary_key(partition.partition_id, primary_id)
                 .or_else(|| {
                     debug!(
-                        "not defined primary key for partition_id {:?} and primary_id {primary_id:?}",
+                        "hit {primary_id:?} of partition {:?} has no primary key any more, dropped from the answer",
                         partition.partition_id
                     );
                     None
@@ -373,7 +373,7 @@ fn execute(run: Run, table: &RwLock<impl TableSearch>, index_size: &AtomicUsize)
             in_progress,
         } => {
             match partition.idx.add_many(&keys, &rows) {
-                Err(err) => warn!("add: unable to add {} embeddings: {err}", keys.len()),
+                Err(err) => warn!("a run of {} inserts failed as a whole: {err}", keys.len()),
                 Ok(added) => {
                     partition.size.fetch_add(added, Ordering::Relaxed);
                     index_size.fetch_add(added, Ordering::Relaxed);
@@ -387,7 +387,7 @@ fn execute(run: Run, table: &RwLock<impl TableSearch>, index_size: &AtomicUsize)
             in_progress,
         } => {
             match partition.idx.remove_many(&keys) {
-                Err(err) => warn!("remove: unable to remove embeddings: {err}"),
+                Err(err) => warn!("a run of {} removals failed as a whole: {err}", keys.len()),
                 Ok(removed) => {
                     partition.size.fetch_sub(removed, Ordering::Relaxed);
                     index_size.fetch_sub(removed, Ordering::Relaxed);
@@ -406,15 +406,15 @@ fn execute(run: Run, table: &RwLock<impl TableSearch>, index_size: &AtomicUsize)
                 Err(err) => {
                     let msg = err.to_string();
                     for tx in txs {
-                        tx.send(Err(anyhow!("ann: search failed: {msg}")))
-                            .unwrap_or_else(|_| trace!("ann: unable to send response"));
+                        tx.send(Err(anyhow!("batched search failed: {msg}")))
+                            .unwrap_or_else(|_| trace!("the requester of an ann went away"));
                     }
                 }
                 Ok(per_query) => {
                     for ((hits, limit), tx) in per_query.into_iter().zip(limits).zip(txs) {
                         let hits = hits.into_iter().take(limit).collect();
                         tx.send(Ok(to_primary_keys(&partition, table, hits)))
-                            .unwrap_or_else(|_| trace!("ann: unable to send response"));
+                            .unwrap_or_else(|_| trace!("the requester of an ann went away"));
                     }
                 }
             }
@@ -437,33 +437,34 @@ fn execute(run: Run, table: &RwLock<impl TableSearch>, index_size: &AtomicUsize)
                 partition
                     .idx
                     .search_filtered(embedding.as_slice(), limit.0.get(), id_ok)
-                    .map_err(|err| anyhow!("ann: search failed: {err}"))
+                    .map_err(|err| anyhow!("filtered search failed: {err}"))
                     .map(|hits| to_primary_keys(&partition, table, hits)),
             )
-            .unwrap_or_else(|_| trace!("ann: unable to send response"));
+            .unwrap_or_else(|_| trace!("the requester of an ann went away"));
         }
     }
 }
 
-fn check_memory_allocation(
-    msg: &Message,
-    rx_allocate: &watch::Receiver<Allocate>,
-    allocate_prev: &mut Allocate,
-    key: &IndexKey,
-) -> bool {
-    if !matches!(msg, Message::Modify(VsIndexModify::AddVector { .. })) {
-        return true;
-    }
-    let allocate = *rx_allocate.borrow();
-    if allocate == Allocate::Cannot {
-        if *allocate_prev == Allocate::Can {
-            error!("Unable to add vector for index {key}: not enough memory to reserve more space");
+/// The memory gate of usearch.rs:1157-1177 for a drained batch: while the monitor says `Cannot`, AddVector messages
+/// are dropped (everything else passes); the refusal is logged once per Can -> Cannot edge.
+struct MemoryGate {
+    rx: watch::Receiver<Allocate>,
+    refused_before: bool,
+}
+
+impl MemoryGate {
+    fn admits(&mut self, msg: &Message, key: &IndexKey) -> bool {
+        let is_add = matches!(msg, Message::Modify(VsIndexModify::AddVector { .. }));
+        if !is_add {
+            return true;
         }
-        *allocate_prev = allocate;
-        return false;
+        let refused = *self.rx.borrow() == Allocate::Cannot;
+        if refused && !self.refused_before {
+            error!("index {key}: vectors are being dropped, the memory monitor forbids new allocations");
+        }
+        self.refused_before = refused;
+        !refused
     }
-    *allocate_prev = allocate;
-    true
 }
 
 /// Appends `msg` to the last run if it is compatible, else starts a new run.  Mirrors `preprocess`
@@ -493,7 +494,7 @@ fn enqueue(
                     let idx = match index_fn() {
                         Ok(idx) => idx,
                         Err(err) => {
-                            error!("failed to create index for partition {partition_id:?}: {err}");
+                            error!("partition {partition_id:?}: no index could be created on the GPU: {err}");
                             return;
                         }
                     };
@@ -567,8 +568,8 @@ fn enqueue(
 
         Message::Search(VsIndexSearch::Count { index_key, tx }) => {
             let Some(index_id) = table.read().unwrap().index_id(&index_key) else {
-                let err = anyhow!("index id not found for index key {index_key:?}");
-                warn!("index count: {err}");
+                let err = anyhow!("count: {index_key:?} is not a known index");
+                warn!("{err}");
                 _ = tx.send(Err(err));
                 return;
             };
@@ -590,7 +591,7 @@ fn enqueue(
                 .partition_id(&index_key, None)
                 .and_then(|(partition_id, _)| partitions.get(&partition_id).map(Arc::clone));
             let Some(partition) = partition else {
-                warn!("partition not found for index key {index_key:?} during ann");
+                warn!("ann on {index_key:?}: no such partition yet, answering with no hits");
                 _ = tx.send(Ok((vec![], vec![])));
                 return;
             };
@@ -612,7 +613,7 @@ fn enqueue(
                     partitions.get(&partition_id).map(|p| (Arc::clone(p), restrictions))
                 });
             let Some((partition, restrictions)) = found else {
-                debug!("partition not found for index key {index_key:?} during filtered ann");
+                debug!("filtered ann on {index_key:?}: no such partition yet, answering with no hits");
                 _ = tx.send(Ok((vec![], vec![])));
                 return;
             };
@@ -650,7 +651,7 @@ fn push_ann(
 ) {
     if let Err(err) = validator::embedding_dimensions(&embedding, dimensions) {
         tx.send(Err(err))
-            .unwrap_or_else(|_| trace!("validate_dimensions: unable to send response"));
+            .unwrap_or_else(|_| trace!("the requester of an ann went away"));
         return;
     }
     if let Some(Run::Ann {
@@ -693,8 +694,10 @@ fn new(
                 debug!("starting");
                 let mut states: BTreeMap<IndexId, IndexState> = BTreeMap::new();
                 let mut partitions: BTreeMap<PartitionId, Arc<PartitionState>> = BTreeMap::new();
-                let mut allocate_prev = Allocate::Can;
-                let allocate_rx = memory.subscribe_allocate().await;
+                let mut gate = MemoryGate {
+                    rx: memory.subscribe_allocate().await,
+                    refused_before: false,
+                };
 
                 // vs_index::recv waits for the first message (searches first); everything already queued behind
                 // it is drained without waiting, searches first again, up to MAX_RUN per kind
@@ -715,7 +718,7 @@ fn new(
 
                     let mut runs = Vec::new();
                     for msg in batch {
-                        if !check_memory_allocation(&msg, &allocate_rx, &mut allocate_prev, &index_key) {
+                        if !gate.admits(&msg, &index_key) {
                             continue;
                         }
                         enqueue(
@@ -738,7 +741,7 @@ fn new(
                             let partition = Arc::clone(partition);
                             worker
                                 .spawn_blocking(move || match partition.idx.reserve(capacity) {
-                                    Err(err) => error!("unable to reserve index capacity for {capacity}: {err}"),
+                                    Err(err) => error!("growing a partition to {capacity} slots failed: {err}"),
                                     Ok(()) => partition.capacity.store(partition.idx.capacity(), Ordering::Relaxed),
                                 })
                                 .await;
